@@ -1,0 +1,137 @@
+/*
+ * ppkmhd_b200.h -- C ABI of the B200-native 3-D MUSCL-Hancock + constrained-transport MHD step.
+ *
+ * The reference (pkestene/ppkMHD) has no FFI: its hot path is reached through the C++ plug-in
+ * interface SolverBase / SolverFactory (src/shared/SolverBase.h:50-261, SolverFactory.h:43-116) and
+ * executes Kokkos functors.  This header is the boundary the replacement solver
+ * (ppkmhd_b200/host/SolverMHDMusclCuda3D.*, registered as "MHD_Muscl_3D") calls instead of those
+ * functors.  Each entry point names the reference member / functor sequence it replaces.
+ *
+ * Conventions: plain pointers and sizes, no C++ / torch types.  Every function returns 0 on
+ * success, otherwise a non-zero status (a cudaError_t, or PPK_ERR_* below) and
+ * ppk_last_error_string() describes it.  A handle drives ONE GPU (one slab of the domain) and is
+ * not re-entrant.  There is no CPU fallback: without a CUDA device ppk_mhd3d_create fails.
+ *
+ * Array layout (the reference's DataArray3d on a GPU, src/shared/kokkos_shared.h:25,44-53):
+ *   U[i + isize*(j + jsize*(k + ksize*var))], isize = nx + 2*3 ..., ghost cells included,
+ *   var: 0 rho, 1 E, 2..4 momentum x,y,z, 5..7 Bx,By,Bz on the LOWER x,y,z faces (enums.h:17-34).
+ */
+#ifndef PPKMHD_B200_H
+#define PPKMHD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPK_NBVAR 8
+#define PPK_GHOST_WIDTH 3
+
+enum ppk_status {
+  PPK_OK = 0,
+  PPK_ERR_INVALID_ARGUMENT = 10001,
+  PPK_ERR_UNSUPPORTED = 10002, /* e.g. riemann != hlld, mx*my != 1, ghost width != 3 */
+  PPK_ERR_NO_DEVICE = 10003,
+  PPK_ERR_NCCL = 10004,
+  PPK_ERR_STATE = 10005
+};
+
+/* src/shared/enums.h BoundaryConditionType */
+enum ppk_bc { PPK_BC_UNDEFINED = 0, PPK_BC_DIRICHLET = 1, PPK_BC_NEUMANN = 2, PPK_BC_PERIODIC = 3, PPK_BC_COPY = 4 };
+/* src/shared/enums.h RiemannSolverType */
+enum ppk_riemann { PPK_RIEMANN_APPROX = 0, PPK_RIEMANN_LLF = 1, PPK_RIEMANN_HLL = 2, PPK_RIEMANN_HLLC = 3, PPK_RIEMANN_HLLD = 4 };
+
+/* POD mirror of what the functors read from HydroParams / HydroSettings
+ * (src/shared/HydroParams.h:28-65,70-234; passed by value into every functor, MHDBaseFunctor3D.h:24-28).
+ * Floating-point members must already carry the reference's float-precision parsing
+ * (ConfigMap::getFloat, src/utils/config/ConfigMap.cpp:37-46). */
+typedef struct ppk_mhd3d_params {
+  int nx, ny, nz;      /* LOCAL interior sizes ([mesh] nx,ny,nz are per rank, HydroParams.cpp:400-410) */
+  int ghost_width;     /* must be 3 (HydroParams.cpp:64-71) */
+  double xmin, xmax, ymin, ymax, zmin, zmax; /* global domain bounds */
+  double dx, dy, dz;   /* (xmax-xmin)/(nx*mx) ... (HydroParams.cpp:400-402) */
+  int boundary_type[6];/* xmin,xmax,ymin,ymax,zmin,zmax of the GLOBAL domain (enum ppk_bc) */
+  double gamma0, cfl, slope_type, smallr, smallc, smallp; /* smallp = smallc*smallc/gamma0 (HydroParams.cpp:441) */
+  int riemann_solver;  /* enum ppk_riemann; only PPK_RIEMANN_HLLD is implemented */
+  int implementation_version; /* only 0 (the deterministic variant, SolverMHDMuscl.cpp:494-517) */
+  int mx, my, mz;      /* Cartesian decomposition ([mpi] mx,my,mz); this build supports z-slabs: mx = my = 1 */
+  int rank_x, rank_y, rank_z; /* position of this slab (replaces myMpiPos, HydroParams.cpp:269-277) */
+  int device;          /* CUDA device ordinal to run on */
+  int exact_arithmetic;/* 1: kernels compiled --fmad=false, reference operation order => bit-identical
+                          to the reference's OpenMP build; 0: same order, FMA contraction allowed */
+} ppk_mhd3d_params;
+
+typedef struct ppk_mhd3d ppk_mhd3d; /* opaque per-GPU solver state (U, U2, Q and all scratch arrays) */
+
+/* Replaces the allocation part of SolverMHDMuscl<3>::SolverMHDMuscl (src/muscl/SolverMHDMuscl.h:321-386). */
+int ppk_mhd3d_create(const ppk_mhd3d_params *params, ppk_mhd3d **handle);
+/* Replaces the View destructors run by `delete solver` (src/main.cpp:183). */
+int ppk_mhd3d_destroy(ppk_mhd3d *handle);
+
+/* Host <-> device copy of the CURRENT conservative array (U or U2 by iteration parity,
+ * SolverMHDMuscl.h:793-805, :896-907). `u_host` holds 8*isize*jsize*ksize doubles, ghosts included.
+ * Replaces Kokkos::deep_copy(Uhost, Udata) (src/utils/io/IO_VTK.cpp:253) and its inverse after init(). */
+int ppk_mhd3d_upload(ppk_mhd3d *handle, const double *u_host);
+int ppk_mhd3d_download(ppk_mhd3d *handle, double *u_host);
+
+/* Time bookkeeping of SolverBase (m_t, m_tEnd, m_iteration; SolverBase.cpp:119-124, 206-220). */
+int ppk_mhd3d_set_time(ppk_mhd3d *handle, double t, double t_end, long iteration);
+/* Synchronises the stream; returns m_t, the last m_dt and m_iteration. Any pointer may be NULL. */
+int ppk_mhd3d_get_time(ppk_mhd3d *handle, double *t, double *dt, long *iteration);
+
+/* SolverMHDMuscl<3>::make_boundaries (src/muscl/SolverMHDMuscl.cpp:49-64 ->
+ * SolverBase::make_boundaries_serial / _mpi, SolverBase.cpp:527-537, 610-693) on the current array. */
+int ppk_mhd3d_make_boundaries(ppk_mhd3d *handle);
+
+/* convertToPrimitives + SolverBase::compute_dt (SolverBase.cpp:149-179) on the current array,
+ * as the constructor does (SolverMHDMuscl.h:399-402). Synchronous; *dt receives the global dt. */
+int ppk_mhd3d_compute_dt(ppk_mhd3d *handle, double *dt);
+
+/* One SolverBase::next_iteration (SolverBase.cpp:206-220) = godunov_unsplit_impl
+ * (src/muscl/SolverMHDMuscl.cpp:465-517, v0) + ++m_iteration, m_t += m_dt.
+ * Asynchronous: enqueues the kernels (ghost fill/halo exchange, primitives + CFL reduction, edge
+ * electric field + face-B slopes, Hancock trace, HLLD face fluxes, edge EMFs, conservative + CT update)
+ * and returns; dt and t live in device memory. */
+int ppk_mhd3d_step(ppk_mhd3d *handle);
+/* `nsteps` steps back to back without host synchronisation (the loop of src/main.cpp:154-159 for a
+ * run that is nStepmax-limited). dt is clamped on the device so that t never passes t_end. */
+int ppk_mhd3d_run(ppk_mhd3d *handle, int nsteps);
+int ppk_mhd3d_synchronize(ppk_mhd3d *handle);
+
+/* Sums of the 8 conserved variables over the local interior and max |div B| (first differences of
+ * face B). Synchronous. No reference counterpart (the reference has no diagnostics); used by the
+ * parity tests of SURVEY 8(d). */
+int ppk_mhd3d_diagnostics(ppk_mhd3d *handle, double sums[8], double *max_divb);
+
+/* ---- multi-GPU: z-slab decomposition, one handle (one process) per GPU -------------------- */
+/* Replaces MpiCommCart / MPI_Sendrecv / MPI_Allreduce (SolverBase.cpp:842-925, :149-179;
+ * HydroParams.cpp:249-259) by NCCL send/recv of ghost k-planes over NVLink and an NCCL max-allreduce
+ * of 1/dt. `unique_id` is the 128-byte ncclUniqueId produced on rank 0 by ppk_nccl_get_unique_id
+ * and distributed by the caller (e.g. torch.distributed broadcast). */
+int ppk_nccl_get_unique_id(void *unique_id_128_bytes);
+int ppk_mhd3d_comm_init(ppk_mhd3d *handle, const void *unique_id_128_bytes, int nranks, int rank);
+
+/* ---- plumbing ----------------------------------------------------------------------------- */
+/* Run on a caller-owned stream (a cudaStream_t, e.g. torch's current stream) instead of the
+ * handle's own non-blocking stream. */
+int ppk_mhd3d_set_stream(ppk_mhd3d *handle, void *cuda_stream);
+/* Per-kernel CUDA-event timing (replaces the coarse timers of SolverBase.h:35-42 for profiling).
+ * While enabled every kernel launch is bracketed by events on the launch stream. */
+int ppk_mhd3d_profile(ppk_mhd3d *handle, int enable);
+/* Accumulated milliseconds and launch counts per kernel since the last reset; returns the number of
+ * kernel kinds (<= capacity). `names[i]` points to static strings. */
+int ppk_mhd3d_kernel_times(ppk_mhd3d *handle, int capacity, const char **names, double *ms, long *launches, int reset);
+/* Total number of kernels launched by this handle since creation (bench.py's gpu_launches). */
+long ppk_mhd3d_launch_count(ppk_mhd3d *handle);
+/* Copy an internal device array to the host for tests: "U","U2","Q" (8 comps), "ElecField" (3),
+ * "dbf" (6), "basis" (35), "Fluxes_x|y|z" (5), "Emf" (3). Returns the number of components. */
+int ppk_mhd3d_debug_array(ppk_mhd3d *handle, const char *name, double *host_out, int *ncomp);
+/* Bytes of device memory held by the handle. */
+long long ppk_mhd3d_device_bytes(ppk_mhd3d *handle);
+
+const char *ppk_last_error_string(void);
+const char *ppk_version_string(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPKMHD_B200_H */

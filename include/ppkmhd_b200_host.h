@@ -1,0 +1,34 @@
+/*
+ * ppkmhd_b200_host.h -- C entry points of the C++ host layer (ppkmhd_b200/host/), i.e. of the part that
+ * mirrors the reference's settings / driver code above the solver:
+ *   ConfigMap + HydroParams::setup   (src/utils/config/ConfigMap.cpp, src/shared/HydroParams.cpp:28-217)
+ *   SolverMHDMuscl<3>::init          (src/muscl/SolverMHDMuscl.h:653-713, MHDInitFunctors3D.h)
+ *   main()                           (src/main.cpp:51-189)
+ * They exist so that non-C++ callers (the Python tests, bench.py) go through exactly the same parsing and
+ * initial-condition code as the ppkMHD_b200 executable.
+ */
+#ifndef PPKMHD_B200_HOST_H
+#define PPKMHD_B200_HOST_H
+#include "ppkmhd_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Parse `ini_text` (NUL-terminated) like the reference's main does for slab `rank_z` of the [mpi] mz slabs
+ * and fill the POD handed to ppk_mhd3d_create (device and exact_arithmetic come from the optional [cuda]
+ * section: device=-1 -> LOCAL_RANK or 0, exact_arithmetic=true). t_end / nstepmax receive [run] tEnd,
+ * nStepmax. */
+int ppk_params_from_ini(const char *ini_text, int rank_z, ppk_mhd3d_params *params, double *t_end, int *nstepmax);
+
+/* Evaluate the initial condition selected by [hydro] problem on the host (orszag_tang, blast, field_loop;
+ * anything else falls back to orszag_tang like the reference) into u_host (8*isize*jsize*ksize doubles). */
+int ppk_init_condition_from_ini(const char *ini_text, int rank_z, double *u_host);
+
+/* The whole program of src/main.cpp: read the ini file, create the solver through SolverFactory, run the
+ * time loop, write VTK output, print the monitoring table. rank < 0: take RANK / WORLD_SIZE from the env. */
+int ppk_run_ini(const char *ini_path, int rank, int nranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,243 @@
+"""ctypes binding of include/ppkmhd_b200.h (+ the host-layer entry points of
+include/ppkmhd_b200_host.h).  The reference-side stub a maintainer would write is shown in
+INTEGRATION.md; this is the same thing for Python callers (tests, bench.py)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path() -> str:
+    return os.path.join(HERE, "lib", "libppkmhd_b200.so")
+
+
+def build_library(verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... (ppkmhd_b200/Makefile); works without a GPU."""
+    subprocess.check_call(["make", "-C", HERE, "-j4"], stdout=None if verbose else subprocess.DEVNULL)
+    return lib_path()
+
+
+class PpkError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """struct ppk_mhd3d_params"""
+
+    _fields_ = [
+        ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("ghost_width", C.c_int),
+        ("xmin", C.c_double), ("xmax", C.c_double), ("ymin", C.c_double), ("ymax", C.c_double),
+        ("zmin", C.c_double), ("zmax", C.c_double),
+        ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double),
+        ("boundary_type", C.c_int * 6),
+        ("gamma0", C.c_double), ("cfl", C.c_double), ("slope_type", C.c_double),
+        ("smallr", C.c_double), ("smallc", C.c_double), ("smallp", C.c_double),
+        ("riemann_solver", C.c_int), ("implementation_version", C.c_int),
+        ("mx", C.c_int), ("my", C.c_int), ("mz", C.c_int),
+        ("rank_x", C.c_int), ("rank_y", C.c_int), ("rank_z", C.c_int),
+        ("device", C.c_int), ("exact_arithmetic", C.c_int),
+    ]
+
+    @property
+    def shape(self):
+        return (8, self.nz + 6, self.ny + 6, self.nx + 6)
+
+
+_lib = None
+
+# every symbol include/*.h declares (tests/test_abi.py checks the library exports them all)
+EXPORTS = [
+    "ppk_mhd3d_create", "ppk_mhd3d_destroy", "ppk_mhd3d_upload", "ppk_mhd3d_download", "ppk_mhd3d_set_time",
+    "ppk_mhd3d_get_time", "ppk_mhd3d_make_boundaries", "ppk_mhd3d_compute_dt", "ppk_mhd3d_step", "ppk_mhd3d_run",
+    "ppk_mhd3d_synchronize", "ppk_mhd3d_diagnostics", "ppk_nccl_get_unique_id", "ppk_mhd3d_comm_init",
+    "ppk_mhd3d_set_stream", "ppk_mhd3d_profile", "ppk_mhd3d_kernel_times", "ppk_mhd3d_launch_count",
+    "ppk_mhd3d_debug_array", "ppk_mhd3d_device_bytes", "ppk_last_error_string", "ppk_version_string",
+    "ppk_params_from_ini", "ppk_init_condition_from_ini", "ppk_run_ini",
+]
+
+
+def load_library():
+    """Load the CUDA library. Fails loudly if it has not been built: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise PpkError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a)")
+    L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L.ppk_mhd3d_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    L.ppk_mhd3d_destroy.argtypes = [vp]
+    L.ppk_mhd3d_upload.argtypes = [vp, vp]
+    L.ppk_mhd3d_download.argtypes = [vp, vp]
+    L.ppk_mhd3d_set_time.argtypes = [vp, C.c_double, C.c_double, C.c_long]
+    L.ppk_mhd3d_get_time.argtypes = [vp, dp, dp, C.POINTER(C.c_long)]
+    L.ppk_mhd3d_make_boundaries.argtypes = [vp]
+    L.ppk_mhd3d_compute_dt.argtypes = [vp, dp]
+    L.ppk_mhd3d_step.argtypes = [vp]
+    L.ppk_mhd3d_run.argtypes = [vp, C.c_int]
+    L.ppk_mhd3d_synchronize.argtypes = [vp]
+    L.ppk_mhd3d_diagnostics.argtypes = [vp, dp, dp]
+    L.ppk_nccl_get_unique_id.argtypes = [vp]
+    L.ppk_mhd3d_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.ppk_mhd3d_set_stream.argtypes = [vp, vp]
+    L.ppk_mhd3d_profile.argtypes = [vp, C.c_int]
+    L.ppk_mhd3d_kernel_times.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), dp, C.POINTER(C.c_long), C.c_int]
+    L.ppk_mhd3d_launch_count.argtypes = [vp]
+    L.ppk_mhd3d_launch_count.restype = C.c_long
+    L.ppk_mhd3d_debug_array.argtypes = [vp, C.c_char_p, vp, ip]
+    L.ppk_mhd3d_device_bytes.argtypes = [vp]
+    L.ppk_mhd3d_device_bytes.restype = C.c_longlong
+    L.ppk_last_error_string.restype = C.c_char_p
+    L.ppk_version_string.restype = C.c_char_p
+    L.ppk_params_from_ini.argtypes = [C.c_char_p, C.c_int, C.POINTER(Params), dp, ip]
+    L.ppk_init_condition_from_ini.argtypes = [C.c_char_p, C.c_int, vp]
+    L.ppk_run_ini.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise PpkError(f"ppkmhd_b200 error {rc}: {load_library().ppk_last_error_string().decode()}")
+
+
+def params_from_ini(ini_text: str, rank_z: int = 0, device: int = 0, exact: bool = True):
+    """ConfigMap + HydroParams::setup of the C++ host layer. Returns (Params, t_end, nstepmax)."""
+    L = load_library()
+    p = Params()
+    t_end = C.c_double(0)
+    nstep = C.c_int(0)
+    _check(L.ppk_params_from_ini(ini_text.encode(), rank_z, C.byref(p), C.byref(t_end), C.byref(nstep)))
+    p.device = device
+    p.exact_arithmetic = 1 if exact else 0
+    return p, t_end.value, nstep.value
+
+
+def init_condition_from_ini(ini_text: str, rank_z: int = 0) -> np.ndarray:
+    """Host-side initial condition of the C++ host layer (SolverMHDMusclCuda3D::init)."""
+    L = load_library()
+    p, _, _ = params_from_ini(ini_text, rank_z)
+    U = np.zeros(p.shape, dtype=np.float64)
+    _check(L.ppk_init_condition_from_ini(ini_text.encode(), rank_z, U.ctypes.data))
+    return U
+
+
+class Mhd3d:
+    """One GPU slab of the 3-D MHD solver (a ppk_mhd3d handle)."""
+
+    def __init__(self, params: Params):
+        self.L = load_library()
+        self.params = params
+        self.h = C.c_void_p()
+        _check(self.L.ppk_mhd3d_create(C.byref(params), C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ppk_mhd3d_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def shape(self):
+        return self.params.shape
+
+    def upload(self, U):
+        """U: numpy float64 (8,ksize,jsize,isize) C-contiguous, or the address of such a host buffer."""
+        if isinstance(U, np.ndarray):
+            assert U.dtype == np.float64 and U.flags["C_CONTIGUOUS"] and U.shape == self.shape
+            _check(self.L.ppk_mhd3d_upload(self.h, U.ctypes.data))
+        else:
+            _check(self.L.ppk_mhd3d_upload(self.h, int(U)))
+
+    def download(self, out=None):
+        if out is None:
+            out = np.empty(self.shape, dtype=np.float64)
+        if isinstance(out, np.ndarray):
+            _check(self.L.ppk_mhd3d_download(self.h, out.ctypes.data))
+        else:
+            _check(self.L.ppk_mhd3d_download(self.h, int(out)))
+        return out
+
+    def interior(self):
+        return self.download()[:, 3:-3, 3:-3, 3:-3]
+
+    def set_time(self, t, t_end, iteration=0):
+        _check(self.L.ppk_mhd3d_set_time(self.h, t, t_end, iteration))
+
+    def get_time(self):
+        t, dt, it = C.c_double(), C.c_double(), C.c_long()
+        _check(self.L.ppk_mhd3d_get_time(self.h, C.byref(t), C.byref(dt), C.byref(it)))
+        return t.value, dt.value, it.value
+
+    def make_boundaries(self):
+        _check(self.L.ppk_mhd3d_make_boundaries(self.h))
+
+    def compute_dt(self):
+        dt = C.c_double()
+        _check(self.L.ppk_mhd3d_compute_dt(self.h, C.byref(dt)))
+        return dt.value
+
+    def step(self):
+        _check(self.L.ppk_mhd3d_step(self.h))
+
+    def run(self, nsteps):
+        _check(self.L.ppk_mhd3d_run(self.h, nsteps))
+
+    def synchronize(self):
+        _check(self.L.ppk_mhd3d_synchronize(self.h))
+
+    def diagnostics(self):
+        sums = np.zeros(8)
+        m = C.c_double()
+        _check(self.L.ppk_mhd3d_diagnostics(self.h, sums.ctypes.data_as(C.POINTER(C.c_double)), C.byref(m)))
+        return sums, m.value
+
+    def comm_init(self, unique_id: bytes, nranks: int, rank: int):
+        buf = C.create_string_buffer(unique_id, 128)
+        _check(self.L.ppk_mhd3d_comm_init(self.h, buf, nranks, rank))
+
+    def set_stream(self, stream_ptr):
+        _check(self.L.ppk_mhd3d_set_stream(self.h, stream_ptr))
+
+    def profile(self, enable=True):
+        _check(self.L.ppk_mhd3d_profile(self.h, 1 if enable else 0))
+
+    def kernel_times(self, reset=False):
+        n = 32
+        names = (C.c_char_p * n)()
+        ms = (C.c_double * n)()
+        cnt = (C.c_long * n)()
+        k = self.L.ppk_mhd3d_kernel_times(self.h, n, names, ms, cnt, 1 if reset else 0)
+        if k < 0:
+            raise PpkError(self.L.ppk_last_error_string().decode())
+        return {names[i].decode(): (ms[i], cnt[i]) for i in range(k)}
+
+    def launch_count(self):
+        return self.L.ppk_mhd3d_launch_count(self.h)
+
+    def device_bytes(self):
+        return self.L.ppk_mhd3d_device_bytes(self.h)
+
+    def debug_array(self, name: str):
+        nc = C.c_int()
+        _check(self.L.ppk_mhd3d_debug_array(self.h, name.encode(), None, C.byref(nc)))
+        out = np.empty((nc.value,) + self.shape[1:], dtype=np.float64)
+        _check(self.L.ppk_mhd3d_debug_array(self.h, name.encode(), out.ctypes.data, C.byref(nc)))
+        return out
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(load_library().ppk_nccl_get_unique_id(buf))
+    return buf.raw

@@ -1,0 +1,537 @@
+// Engine behind the C ABI of include/ppkmhd_b200.h: owns the device arrays of one z-slab, sequences
+// the kernels of one time step on CUDA streams, exchanges ghost planes with NCCL.
+//
+// Step schedule (replaces SolverMHDMuscl<3>::godunov_unsplit_impl, src/muscl/SolverMHDMuscl.cpp:465-517):
+//   main stream : BC x | BC y | ------- prim+CFL (planes needing no z ghost) ---- | wait | BC z(phys) |
+//                 prim+CFL (edge planes) | [allreduce max 1/dt] | dt | E+dB | trace | flux x,y,z | emf z,y,x |
+//                 update(+CT, +copy) | t += dt
+//   comm stream :              wait(x,y) | ncclSend/Recv ghost k-planes (8 vars, both z neighbours) | signal
+// dt, t and the iteration counter live in device memory (StepState), so a run of many steps needs no
+// host synchronisation at all.
+#include "../../include/ppkmhd_b200.h"
+#include "mhd_common.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ppk;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+  g_last_error = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e_ = (expr);                                                                        \
+    if (e_ != cudaSuccess)                                                                          \
+      return fail((int)e_, std::string(#expr) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                             std::to_string(__LINE__) + ")");                                       \
+  } while (0)
+
+// ---- NCCL, resolved at run time so that single-GPU use has no NCCL dependency -------------------
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi g_nccl;
+
+int load_nccl() {
+  if (g_nccl.ok) return 0;
+  // prefer a libnccl already mapped into the process (e.g. the one bundled with torch)
+  void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return fail(PPK_ERR_NCCL, std::string("cannot dlopen libnccl.so.2: ") + dlerror());
+  g_nccl.lib = lib;
+#define SYM(field, name)                                                               \
+  *(void **)(&g_nccl.field) = dlsym(lib, name);                                        \
+  if (!g_nccl.field) return fail(PPK_ERR_NCCL, std::string("missing NCCL symbol ") + name)
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(Send, "ncclSend");
+  SYM(Recv, "ncclRecv");
+  SYM(AllReduce, "ncclAllReduce");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  g_nccl.ok = true;
+  return 0;
+}
+#define NCCL_TRY(expr)                                                                         \
+  do {                                                                                         \
+    ncclResult_t r_ = (expr);                                                                  \
+    if (r_ != ncclSuccess)                                                                     \
+      return fail(PPK_ERR_NCCL, std::string(#expr) + ": " + g_nccl.GetErrorString(r_));       \
+  } while (0)
+
+const char *const kKernelNames[KK_COUNT] = {"boundary", "prim_dt", "finalize_dt", "elec_dbf", "trace",
+                                            "flux_x", "flux_y", "flux_z", "emf_z", "emf_y", "emf_x",
+                                            "update", "diagnostics", "halo_exchange"};
+
+}  // namespace
+
+struct ppk_mhd3d {
+  ppk_mhd3d_params params{};
+  GridParams g{};
+  const KernelTable *kt = nullptr;
+  int device = 0;
+  cudaStream_t stream = nullptr, own_stream = nullptr, comm_stream = nullptr;
+  cudaEvent_t ev_xy = nullptr, ev_halo = nullptr;
+  double *U[2] = {nullptr, nullptr};
+  double *Q = nullptr, *E = nullptr, *DBF = nullptr, *BASIS = nullptr, *F[3] = {nullptr, nullptr, nullptr}, *EMF = nullptr;
+  StepState *st = nullptr;
+  double *diag = nullptr;
+  long long bytes = 0;
+  long launches = 0;
+  long host_iteration = 0;  // parity selects U / U2 like SolverMHDMuscl::godunov_unsplit (SolverMHDMuscl.h:793-805)
+  // profiling
+  bool profile = false;
+  struct Timed { int kind; cudaEvent_t a, b; };
+  std::vector<Timed> pending;
+  std::vector<cudaEvent_t> pool;
+  double acc_ms[KK_COUNT] = {0};
+  long acc_n[KK_COUNT] = {0};
+  // NCCL
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0, zlo = 0, zhi = 0;
+  bool exch_lo = false, exch_hi = false;  // z faces filled by the halo exchange
+
+  double *cur() { return U[host_iteration & 1]; }
+  double *nxt() { return U[(host_iteration + 1) & 1]; }
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = 0;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int now;
+    cudaGetDevice(&now);
+    if (now != prev) cudaSetDevice(prev);
+  }
+};
+
+cudaEvent_t get_event(ppk_mhd3d *h) {
+  if (!h->pool.empty()) {
+    cudaEvent_t e = h->pool.back();
+    h->pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct Scope {  // brackets one kernel launch with events when profiling
+  ppk_mhd3d *h;
+  int kind;
+  cudaStream_t s;
+  cudaEvent_t a = nullptr, b = nullptr;
+  Scope(ppk_mhd3d *h_, int kind_, cudaStream_t s_) : h(h_), kind(kind_), s(s_) {
+    if (h->profile) {
+      a = get_event(h);
+      b = get_event(h);
+      cudaEventRecord(a, s);
+    }
+  }
+  ~Scope() {
+    h->launches += 1;
+    if (h->profile) {
+      cudaEventRecord(b, s);
+      h->pending.push_back({kind, a, b});
+    }
+  }
+};
+
+int collect_timings(ppk_mhd3d *h) {
+  for (auto &p : h->pending) {
+    CUDA_TRY(cudaEventSynchronize(p.b));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, p.a, p.b));
+    h->acc_ms[p.kind] += ms;
+    h->acc_n[p.kind] += 1;
+    h->pool.push_back(p.a);
+    h->pool.push_back(p.b);
+  }
+  h->pending.clear();
+  return 0;
+}
+
+int alloc_doubles(ppk_mhd3d *h, double **p, long long n) {
+  CUDA_TRY(cudaMalloc((void **)p, (size_t)n * sizeof(double)));
+  CUDA_TRY(cudaMemsetAsync(*p, 0, (size_t)n * sizeof(double), h->stream));  // Kokkos::View zero-initialises
+  h->bytes += n * (long long)sizeof(double);
+  return 0;
+}
+
+// z ghost planes through NCCL: replaces CopyDataArray_To_BorderBuf + MPI_Sendrecv + CopyBorderBuf_To_DataArray
+// (SolverBase.cpp:842-925, mpiBorderUtils.h:36-330). In the (i fastest, variable slowest) layout the 3 ghost
+// planes of one variable are contiguous, so no pack/unpack kernel exists: 8 sends + 8 receives per face.
+int halo_exchange_z(ppk_mhd3d *h, double *U, cudaStream_t s) {
+  const GridParams &g = h->g;
+  const size_t plane = (size_t)g.isize * g.jsize;
+  const size_t cnt = plane * g.gw;
+  Scope sc(h, KK_HALO, s);
+  NCCL_TRY(g_nccl.GroupStart());
+  for (int v = 0; v < NBVAR; ++v) {
+    double *base = U + (size_t)v * g.ncell;
+    if (h->exch_lo) NCCL_TRY(g_nccl.Send(base + plane * g.gw, cnt, ncclDouble, h->zlo, h->comm, s));
+    if (h->exch_hi) NCCL_TRY(g_nccl.Recv(base + plane * (g.nz + g.gw), cnt, ncclDouble, h->zhi, h->comm, s));
+    if (h->exch_hi) NCCL_TRY(g_nccl.Send(base + plane * g.nz, cnt, ncclDouble, h->zhi, h->comm, s));
+    if (h->exch_lo) NCCL_TRY(g_nccl.Recv(base, cnt, ncclDouble, h->zlo, h->comm, s));
+  }
+  NCCL_TRY(g_nccl.GroupEnd());
+  return 0;
+}
+
+// make_boundaries on array U, optionally overlapped with the part of prim+CFL that needs no z ghost
+int boundaries_and_primitives(ppk_mhd3d *h, double *U, bool with_prim) {
+  const GridParams &g = h->g;
+  cudaStream_t s = h->stream;
+  { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, U, 0, s); }
+  { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, U, 1, s); }
+  const bool exch = h->exch_lo || h->exch_hi;
+  if (exch) {
+    if (!h->comm) return fail(PPK_ERR_STATE, "mz > 1 but ppk_mhd3d_comm_init was not called");
+    CUDA_TRY(cudaEventRecord(h->ev_xy, s));
+    CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_xy, 0));
+    if (int rc = halo_exchange_z(h, U, h->comm_stream)) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev_halo, h->comm_stream));
+    if (with_prim) {  // interior planes: Q(k) reads U(k) and U(k+1), both inside [gw, nz+gw)
+      Scope sc(h, KK_PRIM_DT, s);
+      h->kt->prim_dt(g, U, h->Q, h->st, g.gw, g.nz + g.gw - 1, s);
+    }
+    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_halo, 0));
+  }
+  { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, U, 2, s); }  // physical / locally periodic z faces
+  if (with_prim) {
+    if (exch) {
+      { Scope sc(h, KK_PRIM_DT, s); h->kt->prim_dt(g, U, h->Q, h->st, 0, g.gw, s); }
+      { Scope sc(h, KK_PRIM_DT, s); h->kt->prim_dt(g, U, h->Q, h->st, g.nz + g.gw - 1, g.ksize - 1, s); }
+    } else {
+      Scope sc(h, KK_PRIM_DT, s);
+      h->kt->prim_dt(g, U, h->Q, h->st, 0, g.ksize - 1, s);
+    }
+    if (h->comm && h->nranks > 1) {
+      // MPI_Allreduce(MIN) of dt (SolverBase.cpp:152-165) == max-allreduce of 1/dt: the division
+      // cfl/invDt is monotonic, so min_r(cfl/invDt_r) and cfl/max_r(invDt_r) are the same double.
+      NCCL_TRY(g_nccl.AllReduce(&h->st->inv_dt_bits, &h->st->inv_dt_bits, 1, ncclDouble, ncclMax, h->comm, s));
+    }
+    { Scope sc(h, KK_FINALIZE_DT, s); h->kt->finalize_dt(g, h->st, s); }
+  }
+  return 0;
+}
+
+int enqueue_step(ppk_mhd3d *h) {
+  const GridParams &g = h->g;
+  cudaStream_t s = h->stream;
+  double *Uin = h->cur(), *Uout = h->nxt();
+  if (int rc = boundaries_and_primitives(h, Uin, true)) return rc;
+  { Scope sc(h, KK_ELEC_DBF, s); h->kt->elec_dbf(g, Uin, h->Q, h->E, h->DBF, s); }
+  { Scope sc(h, KK_TRACE, s); h->kt->trace(g, h->st, Uin, h->Q, h->E, h->BASIS, s); }
+  { Scope sc(h, KK_FLUX_X, s); h->kt->flux(g, 0, h->BASIS, h->F[0], s); }
+  { Scope sc(h, KK_FLUX_Y, s); h->kt->flux(g, 1, h->BASIS, h->F[1], s); }
+  { Scope sc(h, KK_FLUX_Z, s); h->kt->flux(g, 2, h->BASIS, h->F[2], s); }
+  { Scope sc(h, KK_EMF_Z, s); h->kt->emf(g, 2, h->BASIS, h->DBF, h->EMF, s); }
+  { Scope sc(h, KK_EMF_Y, s); h->kt->emf(g, 1, h->BASIS, h->DBF, h->EMF, s); }
+  { Scope sc(h, KK_EMF_X, s); h->kt->emf(g, 0, h->BASIS, h->DBF, h->EMF, s); }
+  { Scope sc(h, KK_UPDATE, s); h->kt->update(g, h->st, Uin, Uout, h->F[0], h->F[1], h->F[2], h->EMF, s); }
+  h->kt->advance_time(h->st, s);
+  h->launches += 1;
+  h->host_iteration += 1;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *ppk_last_error_string(void) { return g_last_error.c_str(); }
+const char *ppk_version_string(void) { return "ppkmhd_b200 0.1 (sm_100a; MHD_Muscl_3D v0; exact+fast fp64)"; }
+
+int ppk_mhd3d_create(const ppk_mhd3d_params *p, ppk_mhd3d **out) {
+  if (!p || !out) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  if (p->ghost_width != PPK_GHOST_WIDTH) return fail(PPK_ERR_UNSUPPORTED, "ghost_width must be 3 (MHD_Muscl_3D)");
+  if (p->riemann_solver != PPK_RIEMANN_HLLD)
+    return fail(PPK_ERR_UNSUPPORTED, "only riemann=hlld is implemented (the reference's 'approx' is a silent no-op flux for MHD)");
+  if (p->implementation_version != 0)
+    return fail(PPK_ERR_UNSUPPORTED, "only implementationVersion=0 (the deterministic reference variant) is implemented");
+  if (p->mx != 1 || p->my != 1 || p->mz < 1) return fail(PPK_ERR_UNSUPPORTED, "only z-slab decompositions (mx=my=1) are supported");
+  if (p->rank_z < 0 || p->rank_z >= p->mz) return fail(PPK_ERR_INVALID_ARGUMENT, "rank_z out of range");
+  if (p->nx < 3 || p->ny < 3 || p->nz < 3) return fail(PPK_ERR_INVALID_ARGUMENT, "nx, ny, nz must be >= 3 (ghost width)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(PPK_ERR_NO_DEVICE, "no CUDA device: ppkmhd_b200 has no CPU fallback");
+  if (p->device < 0 || p->device >= ndev) return fail(PPK_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+
+  ppk_mhd3d *h = new ppk_mhd3d();
+  h->params = *p;
+  h->device = p->device;
+  h->kt = p->exact_arithmetic ? kernel_table_exact() : kernel_table_fast();
+  GridParams &g = h->g;
+  g.nx = p->nx; g.ny = p->ny; g.nz = p->nz; g.gw = p->ghost_width;
+  g.isize = p->nx + 2 * g.gw; g.jsize = p->ny + 2 * g.gw; g.ksize = p->nz + 2 * g.gw;
+  g.ncell = (long long)g.isize * g.jsize * g.ksize;
+  g.dx = p->dx; g.dy = p->dy; g.dz = p->dz;
+  g.gamma0 = p->gamma0; g.cfl = p->cfl; g.slope_type = p->slope_type;
+  g.smallr = p->smallr; g.smallc = p->smallc; g.smallp = p->smallp;
+  for (int f = 0; f < 6; ++f) g.bc[f] = p->boundary_type[f];
+  // z faces of a decomposed run: inner faces, and outer faces of a periodic domain, belong to the halo
+  // exchange (HydroParams.cpp:300-351: neighborsBC = BC_COPY unless on the outer boundary).
+  if (p->mz > 1) {
+    const bool lo_outer = p->rank_z == 0, hi_outer = p->rank_z == p->mz - 1;
+    h->exch_lo = !lo_outer || p->boundary_type[4] == PPK_BC_PERIODIC;
+    h->exch_hi = !hi_outer || p->boundary_type[5] == PPK_BC_PERIODIC;
+    if (h->exch_lo) g.bc[4] = BC_COPY;
+    if (h->exch_hi) g.bc[5] = BC_COPY;
+    h->zlo = (p->rank_z - 1 + p->mz) % p->mz;
+    h->zhi = (p->rank_z + 1) % p->mz;
+  }
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_xy, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+  int rc = 0;
+  const long long n = g.ncell;
+  if ((rc = alloc_doubles(h, &h->U[0], NBVAR * n)) || (rc = alloc_doubles(h, &h->U[1], NBVAR * n)) ||
+      (rc = alloc_doubles(h, &h->Q, NBVAR * n)) || (rc = alloc_doubles(h, &h->E, NELEC * n)) ||
+      (rc = alloc_doubles(h, &h->DBF, NDBF * n)) || (rc = alloc_doubles(h, &h->BASIS, NBASIS * n)) ||
+      (rc = alloc_doubles(h, &h->F[0], NFLUX * n)) || (rc = alloc_doubles(h, &h->F[1], NFLUX * n)) ||
+      (rc = alloc_doubles(h, &h->F[2], NFLUX * n)) || (rc = alloc_doubles(h, &h->EMF, NEMF * n)) ||
+      (rc = alloc_doubles(h, &h->diag, 16))) {
+    ppk_mhd3d_destroy(h);
+    return rc;
+  }
+  CUDA_TRY(cudaMalloc((void **)&h->st, sizeof(StepState)));
+  StepState st0{};
+  st0.t = 0.0; st0.t_end = 1e300; st0.dt = 0.0; st0.inv_dt_bits = 0ull; st0.iteration = 0;
+  CUDA_TRY(cudaMemcpyAsync(h->st, &st0, sizeof(st0), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return 0;
+}
+
+int ppk_mhd3d_destroy(ppk_mhd3d *h) {
+  if (!h) return 0;
+  DeviceGuard guard(h->device);
+  cudaDeviceSynchronize();
+  if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+  for (double *p : {h->U[0], h->U[1], h->Q, h->E, h->DBF, h->BASIS, h->F[0], h->F[1], h->F[2], h->EMF, h->diag})
+    if (p) cudaFree(p);
+  if (h->st) cudaFree(h->st);
+  for (auto &p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+  for (auto e : h->pool) cudaEventDestroy(e);
+  if (h->ev_xy) cudaEventDestroy(h->ev_xy);
+  if (h->ev_halo) cudaEventDestroy(h->ev_halo);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  delete h;
+  return 0;
+}
+
+int ppk_mhd3d_upload(ppk_mhd3d *h, const double *u_host) {
+  if (!h || !u_host) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaMemcpyAsync(h->cur(), u_host, (size_t)NBVAR * h->g.ncell * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+int ppk_mhd3d_download(ppk_mhd3d *h, double *u_host) {
+  if (!h || !u_host) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaMemcpyAsync(u_host, h->cur(), (size_t)NBVAR * h->g.ncell * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int ppk_mhd3d_set_time(ppk_mhd3d *h, double t, double t_end, long iteration) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  DeviceGuard guard(h->device);
+  // keep the array that is current now current after the parity change
+  if (((iteration ^ h->host_iteration) & 1) != 0) std::swap(h->U[0], h->U[1]);
+  StepState st{};
+  st.t = t; st.t_end = t_end; st.dt = 0.0; st.inv_dt_bits = 0ull; st.iteration = iteration;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(h->st, &st, sizeof(st), cudaMemcpyHostToDevice));
+  h->host_iteration = iteration;
+  return 0;
+}
+
+int ppk_mhd3d_get_time(ppk_mhd3d *h, double *t, double *dt, long *iteration) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  DeviceGuard guard(h->device);
+  StepState st{};
+  CUDA_TRY(cudaMemcpyAsync(&st, h->st, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (t) *t = st.t;
+  if (dt) *dt = st.dt;
+  if (iteration) *iteration = (long)st.iteration;
+  return 0;
+}
+
+int ppk_mhd3d_make_boundaries(ppk_mhd3d *h) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  DeviceGuard guard(h->device);
+  if (int rc = boundaries_and_primitives(h, h->cur(), false)) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int ppk_mhd3d_compute_dt(ppk_mhd3d *h, double *dt) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  DeviceGuard guard(h->device);
+  if (int rc = boundaries_and_primitives(h, h->cur(), true)) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return ppk_mhd3d_get_time(h, nullptr, dt, nullptr);
+}
+
+int ppk_mhd3d_step(ppk_mhd3d *h) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  DeviceGuard guard(h->device);
+  return enqueue_step(h);
+}
+
+int ppk_mhd3d_run(ppk_mhd3d *h, int nsteps) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  DeviceGuard guard(h->device);
+  for (int s = 0; s < nsteps; ++s)
+    if (int rc = enqueue_step(h)) return rc;
+  return 0;
+}
+
+int ppk_mhd3d_synchronize(ppk_mhd3d *h) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int ppk_mhd3d_diagnostics(ppk_mhd3d *h, double sums[8], double *max_divb) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  DeviceGuard guard(h->device);
+  if (int rc = boundaries_and_primitives(h, h->cur(), false)) return rc;  // upper ghost faces feed div B
+  CUDA_TRY(cudaMemsetAsync(h->diag, 0, 16 * sizeof(double), h->stream));
+  { Scope sc(h, KK_DIAG, h->stream); h->kt->diagnostics(h->g, h->cur(), h->diag, h->stream); }
+  double out[9];
+  CUDA_TRY(cudaMemcpyAsync(out, h->diag, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (sums) memcpy(sums, out, 8 * sizeof(double));
+  if (max_divb) *max_divb = out[8];
+  return 0;
+}
+
+int ppk_nccl_get_unique_id(void *out) {
+  if (!out) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
+  if (int rc = load_nccl()) return rc;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  NCCL_TRY(g_nccl.GetUniqueId(&id));
+  memcpy(out, &id, sizeof(id));
+  return 0;
+}
+
+int ppk_mhd3d_comm_init(ppk_mhd3d *h, const void *unique_id, int nranks, int rank) {
+  if (!h || !unique_id) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
+  if (nranks != h->params.mz || rank != h->params.rank_z)
+    return fail(PPK_ERR_INVALID_ARGUMENT, "communicator shape must match (mz, rank_z)");
+  if (int rc = load_nccl()) return rc;
+  DeviceGuard guard(h->device);
+  ncclUniqueId id;
+  memcpy(&id, unique_id, sizeof(id));
+  NCCL_TRY(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+  h->nranks = nranks;
+  h->rank = rank;
+  return 0;
+}
+
+int ppk_mhd3d_set_stream(ppk_mhd3d *h, void *cuda_stream) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  return 0;
+}
+
+int ppk_mhd3d_profile(ppk_mhd3d *h, int enable) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  DeviceGuard guard(h->device);
+  if (int rc = collect_timings(h)) return rc;
+  h->profile = enable != 0;
+  return 0;
+}
+
+int ppk_mhd3d_kernel_times(ppk_mhd3d *h, int capacity, const char **names, double *ms, long *launches, int reset) {
+  if (!h) return -1;
+  DeviceGuard guard(h->device);
+  if (collect_timings(h)) return -1;
+  const int n = capacity < KK_COUNT ? capacity : KK_COUNT;
+  for (int i = 0; i < n; ++i) {
+    if (names) names[i] = kKernelNames[i];
+    if (ms) ms[i] = h->acc_ms[i];
+    if (launches) launches[i] = h->acc_n[i];
+  }
+  if (reset)
+    for (int i = 0; i < KK_COUNT; ++i) { h->acc_ms[i] = 0; h->acc_n[i] = 0; }
+  return n;
+}
+
+long ppk_mhd3d_launch_count(ppk_mhd3d *h) { return h ? h->launches : 0; }
+long long ppk_mhd3d_device_bytes(ppk_mhd3d *h) { return h ? h->bytes : 0; }
+
+int ppk_mhd3d_debug_array(ppk_mhd3d *h, const char *name, double *host_out, int *ncomp) {
+  if (!h || !name) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
+  DeviceGuard guard(h->device);
+  const std::string s(name);
+  const double *src = nullptr;
+  int nc = 0;
+  if (s == "U") { src = h->cur(); nc = NBVAR; }
+  else if (s == "U2") { src = h->nxt(); nc = NBVAR; }
+  else if (s == "Q") { src = h->Q; nc = NBVAR; }
+  else if (s == "ElecField") { src = h->E; nc = NELEC; }
+  else if (s == "dbf") { src = h->DBF; nc = NDBF; }
+  else if (s == "basis") { src = h->BASIS; nc = NBASIS; }
+  else if (s == "Fluxes_x") { src = h->F[0]; nc = NFLUX; }
+  else if (s == "Fluxes_y") { src = h->F[1]; nc = NFLUX; }
+  else if (s == "Fluxes_z") { src = h->F[2]; nc = NFLUX; }
+  else if (s == "Emf") { src = h->EMF; nc = NEMF; }
+  else return fail(PPK_ERR_INVALID_ARGUMENT, "unknown array name " + s);
+  if (ncomp) *ncomp = nc;
+  if (host_out) {
+    CUDA_TRY(cudaMemcpyAsync(host_out, src, (size_t)nc * h->g.ncell * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+  }
+  return 0;
+}
+
+}  // extern "C"

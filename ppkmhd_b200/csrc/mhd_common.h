@@ -1,0 +1,71 @@
+// Shared between the engine (host) and the two kernel builds (exact / fast arithmetic).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ppk {
+
+// variable order of the reference (src/shared/enums.h:17-34)
+enum { ID = 0, IP = 1, IU = 2, IV = 3, IW = 4, IA = 5, IB = 6, IC = 7, NBVAR = 8 };
+enum { BC_UNDEFINED = 0, BC_DIRICHLET = 1, BC_NEUMANN = 2, BC_PERIODIC = 3, BC_COPY = 4 };
+
+// "Trace basis": what ComputeTraceFunctor3D_MHD (MHDRunFunctors3D.h:543-856) would expand into
+// 18 stored states (144 doubles per cell). Every one of those states is an exact 1- or 2-addition
+// combination of these 35 numbers (MHDBaseFunctor3D.h:898-1112), so we store the 35 and rebuild a
+// state in registers where a Riemann problem needs it.
+enum {
+  BQ = 0,       // 8: half-step-updated cell-centred primitives r,p,u,v,w,A,B,C (order ID..IC)
+  BSX = 8,      // 7: halved x-slopes  r,p,u,v,w,B,C
+  BSY = 15,     // 7: halved y-slopes  r,p,u,v,w,A,C
+  BSZ = 22,     // 7: halved z-slopes  r,p,u,v,w,A,B
+  BFACE = 29,   // 6: half-step-updated face fields AL,AR,BL,BR,CL,CR
+  NBASIS = 35
+};
+// limited transverse slopes of the face-centred field (DeltaA/B/C of the reference, only the
+// 6 non-trivial ones): dA/dy, dA/dz, dB/dx, dB/dz, dC/dx, dC/dy
+enum { NDBF = 6, NFLUX = 5, NEMF = 3, NELEC = 3 };
+
+struct GridParams {
+  int nx, ny, nz, gw;
+  int isize, jsize, ksize;
+  long long ncell;  // isize*jsize*ksize
+  double dx, dy, dz;
+  double gamma0, cfl, slope_type, smallr, smallc, smallp;
+  int bc[6];  // effective BC of this slab's faces (BC_COPY on faces owned by the halo exchange)
+};
+
+// Device-resident time-loop state (replaces SolverBase::m_t, m_dt, m_iteration living on the host).
+struct StepState {
+  double t;
+  double t_end;
+  double dt;
+  unsigned long long inv_dt_bits;  // max over cells of sum_d (c_f,d + |v_d|)/dx_d as ordered bits
+  long long iteration;
+};
+
+// kernel kinds, for the per-kernel timers
+enum KernelKind {
+  KK_BOUNDARY = 0, KK_PRIM_DT, KK_FINALIZE_DT, KK_ELEC_DBF, KK_TRACE,
+  KK_FLUX_X, KK_FLUX_Y, KK_FLUX_Z, KK_EMF_Z, KK_EMF_Y, KK_EMF_X, KK_UPDATE, KK_DIAG, KK_HALO, KK_COUNT
+};
+
+// Launchers exported by each arithmetic build (mhd_kernels.cu compiled twice).
+struct KernelTable {
+  const char *mode;
+  void (*boundary)(const GridParams &g, double *U, int dir, cudaStream_t s);
+  void (*prim_dt)(const GridParams &g, const double *U, double *Q, StepState *st, int k0, int k1, cudaStream_t s);
+  void (*finalize_dt)(const GridParams &g, StepState *st, cudaStream_t s);
+  void (*advance_time)(StepState *st, cudaStream_t s);
+  void (*elec_dbf)(const GridParams &g, const double *U, const double *Q, double *E, double *DBF, cudaStream_t s);
+  void (*trace)(const GridParams &g, const StepState *st, const double *U, const double *Q, const double *E,
+                double *BASIS, cudaStream_t s);
+  void (*flux)(const GridParams &g, int dir, const double *BASIS, double *F, cudaStream_t s);
+  void (*emf)(const GridParams &g, int edir, const double *BASIS, const double *DBF, double *EMF, cudaStream_t s);
+  void (*update)(const GridParams &g, const StepState *st, const double *Uin, double *Uout, const double *Fx,
+                 const double *Fy, const double *Fz, const double *EMF, cudaStream_t s);
+  void (*diagnostics)(const GridParams &g, const double *U, double *out9, cudaStream_t s);
+};
+
+const KernelTable *kernel_table_exact();
+const KernelTable *kernel_table_fast();
+
+}  // namespace ppk

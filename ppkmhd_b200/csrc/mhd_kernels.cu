@@ -1,0 +1,864 @@
+// Hand-written fp64 CUDA kernels (sm_100a) for ppkMHD's 3-D MUSCL-Hancock + CT MHD step, variant
+// "implementationVersion 0" (src/muscl/SolverMHDMuscl.cpp:494-517).
+//
+// This translation unit is compiled TWICE:
+//   -DPPK_EXACT=1 --fmad=false : every expression keeps the reference's operation order and is
+//                                evaluated without FMA contraction => results are bit-identical to
+//                                the reference's OpenMP build (IEEE fp64 +,*,/,sqrt on both sides);
+//   -DPPK_EXACT=0              : same source, FMA contraction allowed, the EMF upwind blend is a
+//                                branch instead of a 0/1-weighted sum of all branches.
+// Not a port of the Kokkos functors: the reference stores 18 reconstructed states per cell
+// (1152 B) between its trace and Riemann kernels; here the trace kernel stores a 35-number
+// "basis" per cell and the face-flux / edge-EMF kernels rebuild the states they need in registers
+// (each state component is an exact 1- or 2-addition combination of basis numbers).
+#include "mhd_common.h"
+
+#include <math.h>
+
+#ifndef PPK_EXACT
+#  error "compile with -DPPK_EXACT=0 or 1"
+#endif
+#if PPK_EXACT
+#  define PPK_NS ppk_exact
+#else
+#  define PPK_NS ppk_fast
+#endif
+
+namespace ppk {
+namespace PPK_NS {
+
+#define DEV __device__ __forceinline__
+
+DEV long long cidx(const GridParams &g, int i, int j, int k) {
+  return (long long)i + (long long)g.isize * ((long long)j + (long long)g.jsize * (long long)k);
+}
+
+// ---------------------------------------------------------------------------------------------
+// device math
+// ---------------------------------------------------------------------------------------------
+
+// TVD limited slope, MHDBaseFunctor3D.h:280-288 (hydro) and :605-665 (face B)
+DEV double limited_slope(double st, double q, double qplus, double qminus) {
+  const double dlft = st * (q - qminus);
+  const double drgt = st * (qplus - q);
+  const double dcen = 0.5 * (qplus - qminus);
+  const double dsgn = (dcen >= 0.0) ? 1.0 : -1.0;
+  const double slop = fmin(fabs(dlft), fabs(drgt));
+  double dlim = slop;
+  if ((dlft * drgt) <= 0.0) dlim = 0.0;
+  return dsgn * fmin(dlim, fabs(dcen));
+}
+
+// find_speed_fast<dir>, mhd_utils.h:89-117; `n` is the field component normal to the direction
+DEV void fast_speed_common(double gamma0, double d, double p, double a, double b, double c, double &c2, double &d2) {
+  const double b2 = a * a + b * b + c * c;
+  c2 = gamma0 * p / d;
+  d2 = 0.5 * (b2 / d + c2);
+}
+DEV double fast_speed_dir(double c2, double d2, double d, double n) {
+  return sqrt(d2 + sqrt(d2 * d2 - c2 * n * n / d));
+}
+
+// riemann_hlld, RiemannSolvers_MHD.h:133-367. Inputs are in the frame of the face normal
+// (un,bn normal; t1,t2 transverse). Only the 5 hydro fluxes are produced: the induction part of
+// the reference's flux vector is never used (the field is advanced by the edge EMFs).
+DEV void riemann_hlld(double gamma0, double rl, double pl, double ul, double vl, double wl, double al, double bl,
+                      double cl, double rr, double pr, double ur, double vr, double wr, double ar, double br,
+                      double cr, double &f_d, double &f_p, double &f_u, double &f_v, double &f_w) {
+  const double entho = 1.0 / (gamma0 - 1.0);
+  const double a = 0.5 * (al + ar);
+  const double sgnm = (a >= 0) ? 1.0 : -1.0;
+
+  const double ecinl = 0.5 * (ul * ul + vl * vl + wl * wl) * rl;
+  const double emagl = 0.5 * (a * a + bl * bl + cl * cl);
+  const double etotl = pl * entho + ecinl + emagl;
+  const double ptotl = pl + emagl;
+  const double vdotbl = ul * a + vl * bl + wl * cl;
+
+  const double ecinr = 0.5 * (ur * ur + vr * vr + wr * wr) * rr;
+  const double emagr = 0.5 * (a * a + br * br + cr * cr);
+  const double etotr = pr * entho + ecinr + emagr;
+  const double ptotr = pr + emagr;
+  const double vdotbr = ur * a + vr * br + wr * cr;
+
+  double c2, d2;
+  fast_speed_common(gamma0, rl, pl, a, bl, cl, c2, d2);
+  const double cfastl = fast_speed_dir(c2, d2, rl, a);
+  fast_speed_common(gamma0, rr, pr, a, br, cr, c2, d2);
+  const double cfastr = fast_speed_dir(c2, d2, rr, a);
+
+  const double cfmax = fmax(cfastl, cfastr);
+  const double sl = fmin(ul, ur) - cfmax;
+  const double sr = fmax(ul, ur) + cfmax;
+
+  const double rcl = rl * (ul - sl);
+  const double rcr = rr * (sr - ur);
+
+  const double ustar = (rcr * ur + rcl * ul + (ptotl - ptotr)) / (rcr + rcl);
+  const double ptotstar = (rcr * ptotl + rcl * ptotr + rcl * rcr * (ul - ur)) / (rcr + rcl);
+
+  // left star region
+  const double rstarl = rl * (sl - ul) / (sl - ustar);
+  double estar = rl * (sl - ul) * (sl - ustar) - a * a;
+  const double el = rl * (sl - ul) * (sl - ul) - a * a;
+  double vstarl, wstarl, bstarl, cstarl;
+  if (a * a > 0 && fabs(estar / (a * a) - 1.0) <= 1e-8) {
+    vstarl = vl; bstarl = bl; wstarl = wl; cstarl = cl;
+  } else {
+    vstarl = vl - a * bl * (ustar - ul) / estar;
+    bstarl = bl * el / estar;
+    wstarl = wl - a * cl * (ustar - ul) / estar;
+    cstarl = cl * el / estar;
+  }
+  const double vdotbstarl = ustar * a + vstarl * bstarl + wstarl * cstarl;
+  const double etotstarl = ((sl - ul) * etotl - ptotl * ul + ptotstar * ustar + a * (vdotbl - vdotbstarl)) / (sl - ustar);
+  const double sqrrstarl = sqrt(rstarl);
+  const double calfvenl = fabs(a) / sqrrstarl;
+  const double sal = ustar - calfvenl;
+
+  // right star region
+  const double rstarr = rr * (sr - ur) / (sr - ustar);
+  estar = rr * (sr - ur) * (sr - ustar) - a * a;
+  const double er = rr * (sr - ur) * (sr - ur) - a * a;
+  double vstarr, wstarr, bstarr, cstarr;
+  if (a * a > 0 && fabs(estar / (a * a) - 1.0) <= 1e-8) {
+    vstarr = vr; bstarr = br; wstarr = wr; cstarr = cr;
+  } else {
+    vstarr = vr - a * br * (ustar - ur) / estar;
+    bstarr = br * er / estar;
+    wstarr = wr - a * cr * (ustar - ur) / estar;
+    cstarr = cr * er / estar;
+  }
+  const double vdotbstarr = ustar * a + vstarr * bstarr + wstarr * cstarr;
+  const double etotstarr = ((sr - ur) * etotr - ptotr * ur + ptotstar * ustar + a * (vdotbr - vdotbstarr)) / (sr - ustar);
+  const double sqrrstarr = sqrt(rstarr);
+  const double calfvenr = fabs(a) / sqrrstarr;
+  const double sar = ustar + calfvenr;
+
+  // double star region
+  const double vstarstar = (sqrrstarl * vstarl + sqrrstarr * vstarr + sgnm * (bstarr - bstarl)) / (sqrrstarl + sqrrstarr);
+  const double wstarstar = (sqrrstarl * wstarl + sqrrstarr * wstarr + sgnm * (cstarr - cstarl)) / (sqrrstarl + sqrrstarr);
+  const double bstarstar =
+    (sqrrstarl * bstarr + sqrrstarr * bstarl + sgnm * sqrrstarl * sqrrstarr * (vstarr - vstarl)) / (sqrrstarl + sqrrstarr);
+  const double cstarstar =
+    (sqrrstarl * cstarr + sqrrstarr * cstarl + sgnm * sqrrstarl * sqrrstarr * (wstarr - wstarl)) / (sqrrstarl + sqrrstarr);
+  const double vdotbstarstar = ustar * a + vstarstar * bstarstar + wstarstar * cstarstar;
+  const double etotstarstarl = etotstarl - sgnm * sqrrstarl * (vdotbstarl - vdotbstarstar);
+  const double etotstarstarr = etotstarr + sgnm * sqrrstarr * (vdotbstarr - vdotbstarstar);
+
+  // sample the fan at x/t = 0
+  double ro, uo, vo, wo, bo, co, ptoto, etoto, vdotbo;
+  if (sl > 0) {
+    ro = rl; uo = ul; vo = vl; wo = wl; bo = bl; co = cl; ptoto = ptotl; etoto = etotl; vdotbo = vdotbl;
+  } else if (sal > 0) {
+    ro = rstarl; uo = ustar; vo = vstarl; wo = wstarl; bo = bstarl; co = cstarl; ptoto = ptotstar; etoto = etotstarl; vdotbo = vdotbstarl;
+  } else if (ustar > 0) {
+    ro = rstarl; uo = ustar; vo = vstarstar; wo = wstarstar; bo = bstarstar; co = cstarstar; ptoto = ptotstar; etoto = etotstarstarl; vdotbo = vdotbstarstar;
+  } else if (sar > 0) {
+    ro = rstarr; uo = ustar; vo = vstarstar; wo = wstarstar; bo = bstarstar; co = cstarstar; ptoto = ptotstar; etoto = etotstarstarr; vdotbo = vdotbstarstar;
+  } else if (sr > 0) {
+    ro = rstarr; uo = ustar; vo = vstarr; wo = wstarr; bo = bstarr; co = cstarr; ptoto = ptotstar; etoto = etotstarr; vdotbo = vdotbstarr;
+  } else {
+    ro = rr; uo = ur; vo = vr; wo = wr; bo = br; co = cr; ptoto = ptotr; etoto = etotr; vdotbo = vdotbr;
+  }
+
+  f_d = ro * uo;
+  f_p = (etoto + ptoto) * uo - a * vdotbo;
+  f_u = ro * uo * uo - a * a + ptoto;
+  f_v = ro * uo * vo - a * bo;
+  f_w = ro * uo * wo - a * co;
+}
+
+// comparison chains of mhd_utils.h:36-77 (not fmax/fmin)
+DEV double max4(double a0, double a1, double a2, double a3) {
+  double r = a0; r = (a1 > r) ? a1 : r; r = (a2 > r) ? a2 : r; r = (a3 > r) ? a3 : r; return r;
+}
+DEV double min4(double a0, double a1, double a2, double a3) {
+  double r = a0; r = (a1 < r) ? a1 : r; r = (a2 < r) ? a2 : r; r = (a3 < r) ? a3 : r; return r;
+}
+DEV double max5(double a0, double a1, double a2, double a3, double a4) {
+  double r = a0; r = (a1 > r) ? a1 : r; r = (a2 > r) ? a2 : r; r = (a3 > r) ? a3 : r; r = (a4 > r) ? a4 : r; return r;
+}
+
+// One corner state of the 2-D magnetic Riemann problem: r,p, the two in-plane velocities and the
+// three field components in the (d1,d2,e) frame. (The out-of-plane velocity is never read.)
+struct Corner { double r, p, u, v, a, b, c; };
+
+// mag_riemann2d_hlld, RiemannSolvers_MHD.h:398-630
+DEV double mag_riemann2d_hlld(double gamma0, double smallc, const Corner &LL, const Corner &RL, const Corner &LR,
+                              const Corner &RR, double ELL, double ERL, double ELR, double ERR) {
+  double c2, d2;
+  fast_speed_common(gamma0, LL.r, LL.p, LL.a, LL.b, LL.c, c2, d2);
+  const double cFastLLx = fast_speed_dir(c2, d2, LL.r, LL.a), cFastLLy = fast_speed_dir(c2, d2, LL.r, LL.b);
+  fast_speed_common(gamma0, LR.r, LR.p, LR.a, LR.b, LR.c, c2, d2);
+  const double cFastLRx = fast_speed_dir(c2, d2, LR.r, LR.a), cFastLRy = fast_speed_dir(c2, d2, LR.r, LR.b);
+  fast_speed_common(gamma0, RL.r, RL.p, RL.a, RL.b, RL.c, c2, d2);
+  const double cFastRLx = fast_speed_dir(c2, d2, RL.r, RL.a), cFastRLy = fast_speed_dir(c2, d2, RL.r, RL.b);
+  fast_speed_common(gamma0, RR.r, RR.p, RR.a, RR.b, RR.c, c2, d2);
+  const double cFastRRx = fast_speed_dir(c2, d2, RR.r, RR.a), cFastRRy = fast_speed_dir(c2, d2, RR.r, RR.b);
+
+  const double cxmax = max4(cFastLLx, cFastLRx, cFastRLx, cFastRRx);
+  const double cymax = max4(cFastLLy, cFastLRy, cFastRLy, cFastRRy);
+  const double SL = min4(LL.u, LR.u, RL.u, RR.u) - cxmax;
+  const double SR = max4(LL.u, LR.u, RL.u, RR.u) + cxmax;
+  const double SB = min4(LL.v, LR.v, RL.v, RR.v) - cymax;
+  const double ST = max4(LL.v, LR.v, RL.v, RR.v) + cymax;
+
+  const double PtotLL = LL.p + 0.5 * (LL.a * LL.a + LL.b * LL.b + LL.c * LL.c);
+  const double PtotLR = LR.p + 0.5 * (LR.a * LR.a + LR.b * LR.b + LR.c * LR.c);
+  const double PtotRL = RL.p + 0.5 * (RL.a * RL.a + RL.b * RL.b + RL.c * RL.c);
+  const double PtotRR = RR.p + 0.5 * (RR.a * RR.a + RR.b * RR.b + RR.c * RR.c);
+
+  const double rcLLx = LL.r * (LL.u - SL), rcRLx = RL.r * (SR - RL.u), rcLRx = LR.r * (LR.u - SL), rcRRx = RR.r * (SR - RR.u);
+  const double rcLLy = LL.r * (LL.v - SB), rcLRy = LR.r * (ST - LR.v), rcRLy = RL.r * (RL.v - SB), rcRRy = RR.r * (ST - RR.v);
+
+  const double ustar = (rcLLx * LL.u + rcLRx * LR.u + rcRLx * RL.u + rcRRx * RR.u + (PtotLL - PtotRL + PtotLR - PtotRR)) /
+                       (rcLLx + rcLRx + rcRLx + rcRRx);
+  const double vstar = (rcLLy * LL.v + rcLRy * LR.v + rcRLy * RL.v + rcRRy * RR.v + (PtotLL - PtotLR + PtotRL - PtotRR)) /
+                       (rcLLy + rcLRy + rcRLy + rcRRy);
+
+  const double rstarLLx = LL.r * (SL - LL.u) / (SL - ustar);
+  const double BstarLL = LL.b * (SL - LL.u) / (SL - ustar);
+  const double rstarLLy = LL.r * (SB - LL.v) / (SB - vstar);
+  const double AstarLL = LL.a * (SB - LL.v) / (SB - vstar);
+  const double rstarLL = LL.r * (SL - LL.u) / (SL - ustar) * (SB - LL.v) / (SB - vstar);
+  const double EstarLLx = ustar * BstarLL - LL.v * LL.a;
+  const double EstarLLy = LL.u * LL.b - vstar * AstarLL;
+  const double EstarLL = ustar * BstarLL - vstar * AstarLL;
+
+  const double rstarLRx = LR.r * (SL - LR.u) / (SL - ustar);
+  const double BstarLR = LR.b * (SL - LR.u) / (SL - ustar);
+  const double rstarLRy = LR.r * (ST - LR.v) / (ST - vstar);
+  const double AstarLR = LR.a * (ST - LR.v) / (ST - vstar);
+  const double rstarLR = LR.r * (SL - LR.u) / (SL - ustar) * (ST - LR.v) / (ST - vstar);
+  const double EstarLRx = ustar * BstarLR - LR.v * LR.a;
+  const double EstarLRy = LR.u * LR.b - vstar * AstarLR;
+  const double EstarLR = ustar * BstarLR - vstar * AstarLR;
+
+  const double rstarRLx = RL.r * (SR - RL.u) / (SR - ustar);
+  const double BstarRL = RL.b * (SR - RL.u) / (SR - ustar);
+  const double rstarRLy = RL.r * (SB - RL.v) / (SB - vstar);
+  const double AstarRL = RL.a * (SB - RL.v) / (SB - vstar);
+  const double rstarRL = RL.r * (SR - RL.u) / (SR - ustar) * (SB - RL.v) / (SB - vstar);
+  const double EstarRLx = ustar * BstarRL - RL.v * RL.a;
+  const double EstarRLy = RL.u * RL.b - vstar * AstarRL;
+  const double EstarRL = ustar * BstarRL - vstar * AstarRL;
+
+  const double rstarRRx = RR.r * (SR - RR.u) / (SR - ustar);
+  const double BstarRR = RR.b * (SR - RR.u) / (SR - ustar);
+  const double rstarRRy = RR.r * (ST - RR.v) / (ST - vstar);
+  const double AstarRR = RR.a * (ST - RR.v) / (ST - vstar);
+  const double rstarRR = RR.r * (SR - RR.u) / (SR - ustar) * (ST - RR.v) / (ST - vstar);
+  const double EstarRRx = ustar * BstarRR - RR.v * RR.a;
+  const double EstarRRy = RR.u * RR.b - vstar * AstarRR;
+  const double EstarRR = ustar * BstarRR - vstar * AstarRR;
+
+  const double calfvenL = max5(fabs(LR.a) / sqrt(rstarLRx), fabs(AstarLR) / sqrt(rstarLR), fabs(LL.a) / sqrt(rstarLLx),
+                               fabs(AstarLL) / sqrt(rstarLL), smallc);
+  const double calfvenR = max5(fabs(RR.a) / sqrt(rstarRRx), fabs(AstarRR) / sqrt(rstarRR), fabs(RL.a) / sqrt(rstarRLx),
+                               fabs(AstarRL) / sqrt(rstarRL), smallc);
+  const double calfvenB = max5(fabs(LL.b) / sqrt(rstarLLy), fabs(BstarLL) / sqrt(rstarLL), fabs(RL.b) / sqrt(rstarRLy),
+                               fabs(BstarRL) / sqrt(rstarRL), smallc);
+  const double calfvenT = max5(fabs(LR.b) / sqrt(rstarLRy), fabs(BstarLR) / sqrt(rstarLR), fabs(RR.b) / sqrt(rstarRRy),
+                               fabs(BstarRR) / sqrt(rstarRR), smallc);
+
+  const double SAL = fmin(ustar - calfvenL, 0.0);
+  const double SAR = fmax(ustar + calfvenR, 0.0);
+  const double SAB = fmin(vstar - calfvenB, 0.0);
+  const double SAT = fmax(vstar + calfvenT, 0.0);
+
+#if PPK_EXACT
+  // RiemannSolvers_MHD.h:555-596 evaluated as written: every branch, blended with 0/1 weights
+  const double AstarT = (SAR * AstarRR - SAL * AstarLR) / (SAR - SAL);
+  const double AstarB = (SAR * AstarRL - SAL * AstarLL) / (SAR - SAL);
+  const double BstarR = (SAT * BstarRR - SAB * BstarRL) / (SAT - SAB);
+  const double BstarL = (SAT * BstarLR - SAB * BstarLL) / (SAT - SAB);
+
+  double E = 0, tmpE = 0;
+  const int SB_pos = signbit(SB) ? 0 : 1, SB_neg = 1 - SB_pos;
+  const int ST_pos = signbit(ST) ? 0 : 1, ST_neg = 1 - ST_pos;
+  const int SL_pos = signbit(SL) ? 0 : 1, SL_neg = 1 - SL_pos;
+  const int SR_pos = signbit(SR) ? 0 : 1, SR_neg = 1 - SR_pos;
+
+  tmpE = (SAL * SAB * EstarRR - SAL * SAT * EstarRL - SAR * SAB * EstarLR + SAR * SAT * EstarLL) / (SAR - SAL) / (SAT - SAB) -
+         SAT * SAB / (SAT - SAB) * (AstarT - AstarB) + SAR * SAL / (SAR - SAL) * (BstarR - BstarL);
+  E += (double)(SB_neg * ST_pos * SL_neg * SR_pos) * tmpE;
+
+  tmpE = (SAR * EstarLLx - SAL * EstarRLx + SAR * SAL * (RL.b - LL.b)) / (SAR - SAL);
+  tmpE = (double)SL_pos * ELL + (double)(SL_neg * SR_neg) * ERL + (double)(SL_neg * SR_pos) * tmpE;
+  E += (double)SB_pos * tmpE;
+
+  tmpE = (SAR * EstarLRx - SAL * EstarRRx + SAR * SAL * (RR.b - LR.b)) / (SAR - SAL);
+  tmpE = (double)SL_pos * ELR + (double)(SL_neg * SR_neg) * ERR + (double)(SL_neg * SR_pos) * tmpE;
+  E += (double)(SB_neg * ST_neg) * tmpE;
+
+  tmpE = (SAT * EstarLLy - SAB * EstarLRy - SAT * SAB * (LR.a - LL.a)) / (SAT - SAB);
+  E += (double)(SB_neg * ST_pos * SL_pos) * tmpE;
+
+  tmpE = (SAT * EstarRLy - SAB * EstarRRy - SAT * SAB * (RR.a - RL.a)) / (SAT - SAB);
+  E += (double)(SB_neg * ST_pos * SL_neg * SR_neg) * tmpE;
+  return E;
+#else
+  // same selection (sign bits, RiemannSolvers_MHD.h:569-572), only the chosen branch is evaluated
+  const bool SB_pos = !signbit(SB), ST_pos = !signbit(ST), SL_pos = !signbit(SL), SR_pos = !signbit(SR);
+  if (SB_pos) {
+    if (SL_pos) return ELL;
+    if (!SR_pos) return ERL;
+    return (SAR * EstarLLx - SAL * EstarRLx + SAR * SAL * (RL.b - LL.b)) / (SAR - SAL);
+  }
+  if (!ST_pos) {
+    if (SL_pos) return ELR;
+    if (!SR_pos) return ERR;
+    return (SAR * EstarLRx - SAL * EstarRRx + SAR * SAL * (RR.b - LR.b)) / (SAR - SAL);
+  }
+  if (SL_pos) return (SAT * EstarLLy - SAB * EstarLRy - SAT * SAB * (LR.a - LL.a)) / (SAT - SAB);
+  if (!SR_pos) return (SAT * EstarRLy - SAB * EstarRRy - SAT * SAB * (RR.a - RL.a)) / (SAT - SAB);
+  const double AstarT = (SAR * AstarRR - SAL * AstarLR) / (SAR - SAL);
+  const double AstarB = (SAR * AstarRL - SAL * AstarLL) / (SAR - SAL);
+  const double BstarR = (SAT * BstarRR - SAB * BstarRL) / (SAT - SAB);
+  const double BstarL = (SAT * BstarLR - SAB * BstarLL) / (SAT - SAB);
+  return (SAL * SAB * EstarRR - SAL * SAT * EstarRL - SAR * SAB * EstarLR + SAR * SAT * EstarLL) / (SAR - SAL) / (SAT - SAB) -
+         SAT * SAB / (SAT - SAB) * (AstarT - AstarB) + SAR * SAL / (SAR - SAL) * (BstarR - BstarL);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+
+// Ghost fill of one direction (both faces), MakeBoundariesFunctor3D_MHD<face>
+// (BoundariesFunctors.h:749-1053). Faces whose BC is BC_COPY belong to the halo exchange.
+template <int DIR>
+__global__ void k_boundary(const GridParams g, double *__restrict__ U) {
+  const int gw = g.gw;
+  const int e0 = DIR == 0 ? g.jsize : g.isize;
+  const int e1 = DIR == 2 ? g.jsize : g.ksize;
+  const int n = DIR == 0 ? g.nx : (DIR == 1 ? g.ny : g.nz);
+  const long long total = 2LL * gw * e0 * e1;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  // fastest index: for DIR==0 the ghost layer (only 3 wide), otherwise i
+  int a, b, gl, hi;
+  long long r = t;
+  if (DIR == 0) { gl = (int)(r % gw); r /= gw; a = (int)(r % e0); r /= e0; b = (int)(r % e1); hi = (int)(r / e1); }
+  else { a = (int)(r % e0); r /= e0; gl = (int)(r % gw); r /= gw; b = (int)(r % e1); hi = (int)(r / e1); }
+  const int bc = g.bc[2 * DIR + hi];
+  if (bc == BC_COPY) return;
+  const int c = hi ? gl + n + gw : gl;
+  int c0;
+  if (bc == BC_DIRICHLET) c0 = hi ? 2 * n + 2 * gw - 1 - c : 2 * gw - 1 - c;
+  else if (bc == BC_NEUMANN) c0 = hi ? n + gw - 1 : gw;
+  else c0 = hi ? c - n : n + c;
+  long long dst, src;
+  if (DIR == 0) { dst = cidx(g, c, a, b); src = cidx(g, c0, a, b); }
+  else if (DIR == 1) { dst = cidx(g, a, c, b); src = cidx(g, a, c0, b); }
+  else { dst = cidx(g, a, b, c); src = cidx(g, a, b, c0); }
+  const int vflip = IU + DIR, bflip = IA + DIR;
+#pragma unroll
+  for (int v = 0; v < NBVAR; ++v) {
+    double val = U[src + v * g.ncell];
+    if (bc == BC_DIRICHLET && (v == vflip || v == bflip)) val = val * -1.0;
+    U[dst + v * g.ncell] = val;
+  }
+}
+
+DEV double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ConvertToPrimitivesFunctor3D_MHD (MHDRunFunctors3D.h:88-163, constoprim_mhd MHDBaseFunctor3D.h:192-242)
+// fused with ComputeDtFunctor3D_MHD (MHDRunFunctors3D.h:16-83, find_speed_info<3> mhd_utils.h:319-366):
+// Q is written on [0,size-1)^3 and the CFL max is reduced over interior cells with warp shuffles,
+// one shared-memory stage and one 64-bit atomicMax per block (positive doubles order like their bits).
+__global__ void __launch_bounds__(256) k_prim_dt(const GridParams g, const double *__restrict__ U, double *__restrict__ Q,
+                                                 StepState *st, int k0) {
+  const int k = k0 + blockIdx.y;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned j = t / (unsigned)g.isize;
+  const unsigned i = t - j * (unsigned)g.isize;
+  double inv = 0.0;
+  if (j < (unsigned)(g.jsize - 1) && i < (unsigned)(g.isize - 1) && k < g.ksize - 1) {
+    const long long c = cidx(g, i, j, k);
+    const long long N = g.ncell;
+    const double ur = U[c + ID * N], ue = U[c + IP * N];
+    const double mu = U[c + IU * N], mv = U[c + IV * N], mw = U[c + IW * N];
+    const double fa = U[c + IA * N], fb = U[c + IB * N], fc = U[c + IC * N];
+    const double fa1 = U[c + 1 + IA * N];
+    const double fb1 = U[c + g.isize + IB * N];
+    const double fc1 = U[c + (long long)g.isize * g.jsize + IC * N];
+    const double r = fmax(ur, g.smallr);
+    const double u = mu / r, v = mv / r, w = mw / r;
+    const double A = 0.5 * (fa + fa1), B = 0.5 * (fb + fb1), C = 0.5 * (fc + fc1);
+    const double eken = 0.5 * (u * u + v * v + w * w);
+    const double emag = 0.5 * (A * A + B * B + C * C);
+    const double eint = (ue - emag) / r - eken;
+    const double p = fmax((g.gamma0 - 1.0) * r * eint, r * g.smallp);
+    Q[c + ID * N] = r; Q[c + IP * N] = p; Q[c + IU * N] = u; Q[c + IV * N] = v; Q[c + IW * N] = w;
+    Q[c + IA * N] = A; Q[c + IB * N] = B; Q[c + IC * N] = C;
+    const int gw = g.gw;
+    if ((int)i >= gw && (int)i < g.isize - gw && (int)j >= gw && (int)j < g.jsize - gw && k >= gw && k < g.ksize - gw) {
+      double c2, d2;
+      fast_speed_common(g.gamma0, r, p, A, B, C, c2, d2);
+      const double vx = fast_speed_dir(c2, d2, r, A) + fabs(u);
+      const double vy = fast_speed_dir(c2, d2, r, B) + fabs(v);
+      const double vz = fast_speed_dir(c2, d2, r, C) + fabs(w);
+      inv = vx / g.dx + vy / g.dy + vz / g.dz;
+    }
+  }
+  // NaN-safe like fmax(invDt, x) in the reference: fmax drops NaNs
+  inv = warp_max(inv);
+  __shared__ double smax[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) smax[wid] = inv;
+  __syncthreads();
+  if (wid == 0) {
+    inv = lane < (int)(blockDim.x >> 5) ? smax[lane] : 0.0;
+    inv = warp_max(inv);
+    if (lane == 0 && inv > 0.0) atomicMax(&st->inv_dt_bits, (unsigned long long)__double_as_longlong(inv));
+  }
+}
+
+// compute_dt_local (SolverMHDMuscl.h:724-741) + the clamp of SolverBase::compute_dt (SolverBase.cpp:174-177)
+__global__ void k_finalize_dt(const GridParams g, StepState *st) {
+  const double inv = __longlong_as_double((long long)st->inv_dt_bits);
+  double dt = g.cfl / inv;
+  if (st->t + dt > st->t_end) dt = st->t_end - st->t;
+  st->dt = dt;
+  st->inv_dt_bits = 0ull;
+}
+// ++m_iteration; m_t += m_dt (SolverBase.cpp:216-218)
+__global__ void k_advance_time(StepState *st) {
+  st->iteration += 1;
+  st->t += st->dt;
+}
+
+// ComputeElecFieldFunctor3D (MHDRunFunctors3D.h:278-362) + ComputeMagSlopesFunctor3D (:441-538,
+// slope_unsplit_mhd_3d MHDBaseFunctor3D.h:561-668) on [1,size-1)^3.
+__global__ void __launch_bounds__(256) k_elec_dbf(const GridParams g, const double *__restrict__ U,
+                                                  const double *__restrict__ Q, double *__restrict__ E,
+                                                  double *__restrict__ DBF) {
+  const int k = 1 + blockIdx.y;
+  const unsigned ni = g.isize - 2;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned jj = t / ni;
+  const int i = 1 + (int)(t - jj * ni), j = 1 + (int)jj;
+  if (j >= g.jsize - 1) return;
+  const long long N = g.ncell, sj = g.isize, sk = (long long)g.isize * g.jsize;
+  const long long c = cidx(g, i, j, k);
+  const double *Qu = Q + IU * N, *Qv = Q + IV * N, *Qw = Q + IW * N;
+  const double *Ua = U + IA * N, *Ub = U + IB * N, *Uc = U + IC * N;
+  const double a0 = Ua[c], b0 = Ub[c], c0 = Uc[c];
+  double u, v, w, A, B, C;
+  // Ex: average over (j-1,k-1),(j-1,k),(j,k-1),(j,k) in this order
+  v = 0.25 * (Qv[c - sj - sk] + Qv[c - sj] + Qv[c - sk] + Qv[c]);
+  w = 0.25 * (Qw[c - sj - sk] + Qw[c - sj] + Qw[c - sk] + Qw[c]);
+  B = 0.5 * (Ub[c - sk] + b0);
+  C = 0.5 * (Uc[c - sj] + c0);
+  E[c + 0 * N] = v * C - w * B;
+  // Ey: (i-1,k-1),(i-1,k),(i,k-1),(i,k)
+  u = 0.25 * (Qu[c - 1 - sk] + Qu[c - 1] + Qu[c - sk] + Qu[c]);
+  w = 0.25 * (Qw[c - 1 - sk] + Qw[c - 1] + Qw[c - sk] + Qw[c]);
+  A = 0.5 * (Ua[c - sk] + a0);
+  C = 0.5 * (Uc[c - 1] + c0);
+  E[c + 1 * N] = w * A - u * C;
+  // Ez: (i-1,j-1),(i-1,j),(i,j-1),(i,j)
+  u = 0.25 * (Qu[c - 1 - sj] + Qu[c - 1] + Qu[c - sj] + Qu[c]);
+  v = 0.25 * (Qv[c - 1 - sj] + Qv[c - 1] + Qv[c - sj] + Qv[c]);
+  A = 0.5 * (Ua[c - sj] + a0);
+  B = 0.5 * (Ub[c - 1] + b0);
+  E[c + 2 * N] = u * B - v * A;
+
+  const double st = fmin(g.slope_type, 2.0);
+  DBF[c + 0 * N] = limited_slope(st, a0, Ua[c + sj], Ua[c - sj]);  // dA/dy
+  DBF[c + 1 * N] = limited_slope(st, a0, Ua[c + sk], Ua[c - sk]);  // dA/dz
+  DBF[c + 2 * N] = limited_slope(st, b0, Ub[c + 1], Ub[c - 1]);    // dB/dx
+  DBF[c + 3 * N] = limited_slope(st, b0, Ub[c + sk], Ub[c - sk]);  // dB/dz
+  DBF[c + 4 * N] = limited_slope(st, c0, Uc[c + 1], Uc[c - 1]);    // dC/dx
+  DBF[c + 5 * N] = limited_slope(st, c0, Uc[c + sj], Uc[c - sj]);  // dC/dy
+}
+
+// ComputeTraceFunctor3D_MHD (MHDRunFunctors3D.h:543-856): hydro slopes (slope_unsplit_hydro_3d,
+// MHDBaseFunctor3D.h:362-495) + Hancock half step (trace_unsplit_mhd_3d_simpler, :688-896).
+// Writes the 35-number basis on [2,size-2)^3 (the cells whose states a face or an edge consumes).
+__global__ void __launch_bounds__(128) k_trace(const GridParams g, const StepState *__restrict__ stp,
+                                               const double *__restrict__ U, const double *__restrict__ Q,
+                                               const double *__restrict__ E, double *__restrict__ BASIS) {
+  const int k = 2 + blockIdx.y;
+  const unsigned ni = g.isize - 4;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned jj = t / ni;
+  const int i = 2 + (int)(t - jj * ni), j = 2 + (int)jj;
+  if (j >= g.jsize - 2) return;
+  const long long N = g.ncell, sj = g.isize, sk = (long long)g.isize * g.jsize;
+  const long long c = cidx(g, i, j, k);
+  const double dt = stp->dt;
+  const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
+  const double st = g.slope_type;
+  const bool lim = (st == 1.0 || st == 2.0);
+
+  double q[NBVAR], sx[NBVAR], sy[NBVAR], sz[NBVAR];
+#pragma unroll
+  for (int v = 0; v < NBVAR; ++v) {
+    const double *Qv = Q + v * N;
+    const double qc = Qv[c];
+    q[v] = qc;
+    // slopes are halved in place first (MHDBaseFunctor3D.h:767-813)
+    sx[v] = lim ? 0.5 * limited_slope(st, qc, Qv[c + 1], Qv[c - 1]) : 0.0;
+    sy[v] = lim ? 0.5 * limited_slope(st, qc, Qv[c + sj], Qv[c - sj]) : 0.0;
+    sz[v] = lim ? 0.5 * limited_slope(st, qc, Qv[c + sk], Qv[c - sk]) : 0.0;
+  }
+  double r = q[ID], p = q[IP], u = q[IU], v = q[IV], w = q[IW], A = q[IA], B = q[IB], C = q[IC];
+  const double drx = sx[ID], dpx = sx[IP], dux = sx[IU], dvx = sx[IV], dwx = sx[IW], dBx = sx[IB], dCx = sx[IC];
+  const double dry = sy[ID], dpy = sy[IP], duy = sy[IU], dvy = sy[IV], dwy = sy[IW], dAy = sy[IA], dCy = sy[IC];
+  const double drz = sz[ID], dpz = sz[IP], duz = sz[IU], dvz = sz[IV], dwz = sz[IW], dAz = sz[IA], dBz = sz[IB];
+
+  double AL = U[c + IA * N], AR = U[c + 1 + IA * N];
+  double BL = U[c + IB * N], BR = U[c + sj + IB * N];
+  double CL = U[c + IC * N], CR = U[c + sk + IC * N];
+  const double dAx = 0.5 * (AR - AL), dBy = 0.5 * (BR - BL), dCz = 0.5 * (CR - CL);
+
+  const double gamma = g.gamma0;
+  // source terms, MHDBaseFunctor3D.h:843-857
+  const double sr0 = (-u * drx - dux * r) * dtdx + (-v * dry - dvy * r) * dtdy + (-w * drz - dwz * r) * dtdz;
+  const double su0 = (-u * dux - (dpx + B * dBx + C * dCx) / r) * dtdx + (-v * duy + B * dAy / r) * dtdy +
+                     (-w * duz + C * dAz / r) * dtdz;
+  const double sv0 = (-u * dvx + A * dBx / r) * dtdx + (-v * dvy - (dpy + A * dAy + C * dCy) / r) * dtdy +
+                     (-w * dvz + C * dBz / r) * dtdz;
+  const double sw0 = (-u * dwx + A * dCx / r) * dtdx + (-v * dwy + B * dCy / r) * dtdy +
+                     (-w * dwz - (dpz + A * dAz + B * dBz) / r) * dtdz;
+  const double sp0 = (-u * dpx - dux * gamma * p) * dtdx + (-v * dpy - dvy * gamma * p) * dtdy +
+                     (-w * dpz - dwz * gamma * p) * dtdz;
+  const double sA0 = (u * dBy + B * duy - v * dAy - A * dvy) * dtdy + (u * dCz + C * duz - w * dAz - A * dwz) * dtdz;
+  const double sB0 = (v * dAx + A * dvx - u * dBx - B * dux) * dtdx + (v * dCz + C * dvz - w * dBz - B * dwz) * dtdz;
+  const double sC0 = (w * dAx + A * dwx - u * dCx - C * dux) * dtdx + (w * dBy + B * dwy - v * dCy - C * dvy) * dtdy;
+
+  // face-centred field from the edge electric field, :872-877
+  const double *Ex = E, *Ey = E + N, *Ez = E + 2 * N;
+  const double ELL = Ex[c], ELR = Ex[c + sk], ERL = Ex[c + sj], ERR = Ex[c + sj + sk];
+  const double FLL = Ey[c], FLR = Ey[c + sk], FRL = Ey[c + 1], FRR = Ey[c + 1 + sk];
+  const double GLL = Ez[c], GLR = Ez[c + sj], GRL = Ez[c + 1], GRR = Ez[c + 1 + sj];
+  const double sAL0 = +(GLR - GLL) * dtdy * 0.5 - (FLR - FLL) * dtdz * 0.5;
+  const double sAR0 = +(GRR - GRL) * dtdy * 0.5 - (FRR - FRL) * dtdz * 0.5;
+  const double sBL0 = -(GRL - GLL) * dtdx * 0.5 + (ELR - ELL) * dtdz * 0.5;
+  const double sBR0 = -(GRR - GLR) * dtdx * 0.5 + (ERR - ERL) * dtdz * 0.5;
+  const double sCL0 = +(FRL - FLL) * dtdx * 0.5 - (ERL - ELL) * dtdy * 0.5;
+  const double sCR0 = +(FRR - FLR) * dtdx * 0.5 - (ERR - ELR) * dtdy * 0.5;
+
+  r = r + sr0; u = u + su0; v = v + sv0; w = w + sw0; p = p + sp0; A = A + sA0; B = B + sB0; C = C + sC0;
+  AL = AL + sAL0; AR = AR + sAR0; BL = BL + sBL0; BR = BR + sBR0; CL = CL + sCL0; CR = CR + sCR0;
+
+  double *Bs = BASIS + c;
+  Bs[(BQ + ID) * N] = r; Bs[(BQ + IP) * N] = p; Bs[(BQ + IU) * N] = u; Bs[(BQ + IV) * N] = v; Bs[(BQ + IW) * N] = w;
+  Bs[(BQ + IA) * N] = A; Bs[(BQ + IB) * N] = B; Bs[(BQ + IC) * N] = C;
+  Bs[(BSX + 0) * N] = drx; Bs[(BSX + 1) * N] = dpx; Bs[(BSX + 2) * N] = dux; Bs[(BSX + 3) * N] = dvx; Bs[(BSX + 4) * N] = dwx;
+  Bs[(BSX + 5) * N] = dBx; Bs[(BSX + 6) * N] = dCx;
+  Bs[(BSY + 0) * N] = dry; Bs[(BSY + 1) * N] = dpy; Bs[(BSY + 2) * N] = duy; Bs[(BSY + 3) * N] = dvy; Bs[(BSY + 4) * N] = dwy;
+  Bs[(BSY + 5) * N] = dAy; Bs[(BSY + 6) * N] = dCy;
+  Bs[(BSZ + 0) * N] = drz; Bs[(BSZ + 1) * N] = dpz; Bs[(BSZ + 2) * N] = duz; Bs[(BSZ + 3) * N] = dvz; Bs[(BSZ + 4) * N] = dwz;
+  Bs[(BSZ + 5) * N] = dAz; Bs[(BSZ + 6) * N] = dBz;
+  Bs[(BFACE + 0) * N] = AL; Bs[(BFACE + 1) * N] = AR; Bs[(BFACE + 2) * N] = BL; Bs[(BFACE + 3) * N] = BR;
+  Bs[(BFACE + 4) * N] = CL; Bs[(BFACE + 5) * N] = CR;
+}
+
+// index, inside the 7 slopes of direction D, of field component m (m != D): r,p,u,v,w then the two
+// transverse field components in increasing order
+DEV constexpr int slope_b(int D, int m) { return 5 + (m > D ? m - 1 : m); }
+DEV constexpr int slope_base(int D) { return D == 0 ? BSX : (D == 1 ? BSY : BSZ); }
+
+// ComputeFluxesAndStoreFunctor3D_MHD (MHDRunFunctors3D.h:1783-1909), one direction per launch.
+// Face (i,j,k) = lower D-face of cell (i,j,k): left state = qm_D of cell - e_D, right state = qp_D of
+// the cell (MHDBaseFunctor3D.h:898-968), rotated into the face frame exactly like the swapValues calls
+// of the reference (y: u<->v, A<->B ; z: u<->w, A<->C). Only faces the update reads are computed:
+// normal index in [gw, n+gw], transverse indices interior. Stores (rho, E, normal, t1, t2) fluxes.
+template <int D>
+__global__ void __launch_bounds__(128) k_flux(const GridParams g, const double *__restrict__ BASIS, double *__restrict__ F) {
+  const int gw = g.gw;
+  const int k = gw + blockIdx.y;
+  const unsigned ni = g.nx + (D == 0 ? 1 : 0);
+  const unsigned nj = g.ny + (D == 1 ? 1 : 0);
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned jj = t / ni;
+  if (jj >= nj) return;
+  const int i = gw + (int)(t - jj * ni), j = gw + (int)jj;
+  const long long N = g.ncell;
+  const long long sD = D == 0 ? 1 : (D == 1 ? (long long)g.isize : (long long)g.isize * g.jsize);
+  const long long cR = cidx(g, i, j, k), cL = cR - sD;
+  constexpr int T1 = D == 0 ? 1 : (D == 1 ? 0 : 1);  // frame after the reference's swaps
+  constexpr int T2 = D == 0 ? 2 : (D == 1 ? 2 : 0);
+  constexpr int SB = slope_base(D);
+  const double *BL_ = BASIS + cL, *BR_ = BASIS + cR;
+
+  // left state: q + slope (qm), normal field = upper-face value of the left cell
+  const double rl = fmax(g.smallr, BL_[(BQ + ID) * N] + BL_[(SB + 0) * N]);
+  const double pl = fmax(g.smallp, BL_[(BQ + IP) * N] + BL_[(SB + 1) * N]);
+  const double unl = BL_[(BQ + IU + D) * N] + BL_[(SB + 2 + D) * N];
+  const double t1l = BL_[(BQ + IU + T1) * N] + BL_[(SB + 2 + T1) * N];
+  const double t2l = BL_[(BQ + IU + T2) * N] + BL_[(SB + 2 + T2) * N];
+  const double bnl = BL_[(BFACE + 2 * D + 1) * N];
+  const double b1l = BL_[(BQ + IA + T1) * N] + BL_[(SB + slope_b(D, T1)) * N];
+  const double b2l = BL_[(BQ + IA + T2) * N] + BL_[(SB + slope_b(D, T2)) * N];
+  // right state: q - slope (qp), normal field = lower-face value of the right cell
+  const double rr = fmax(g.smallr, BR_[(BQ + ID) * N] - BR_[(SB + 0) * N]);
+  const double pr = fmax(g.smallp, BR_[(BQ + IP) * N] - BR_[(SB + 1) * N]);
+  const double unr = BR_[(BQ + IU + D) * N] - BR_[(SB + 2 + D) * N];
+  const double t1r = BR_[(BQ + IU + T1) * N] - BR_[(SB + 2 + T1) * N];
+  const double t2r = BR_[(BQ + IU + T2) * N] - BR_[(SB + 2 + T2) * N];
+  const double bnr = BR_[(BFACE + 2 * D) * N];
+  const double b1r = BR_[(BQ + IA + T1) * N] - BR_[(SB + slope_b(D, T1)) * N];
+  const double b2r = BR_[(BQ + IA + T2) * N] - BR_[(SB + slope_b(D, T2)) * N];
+
+  double fd, fp, fu, fv, fw;
+  riemann_hlld(g.gamma0, rl, pl, unl, t1l, t2l, bnl, b1l, b2l, rr, pr, unr, t1r, t2r, bnr, b1r, b2r, fd, fp, fu, fv, fw);
+  double *Fo = F + cR;
+  Fo[0 * N] = fd; Fo[1 * N] = fp; Fo[2 * N] = fu; Fo[3 * N] = fv; Fo[4 * N] = fw;
+}
+
+// index of the limited slope of face component m along direction a (a != m) in DBF
+DEV constexpr int dbf_idx(int m, int a) { return 2 * m + (a > m ? a - 1 : a); }
+
+// One of the 12 edge states of trace_unsplit_mhd_3d_simpler (MHDBaseFunctor3D.h:970-1112) in the
+// (d1,d2,e) frame of edge direction E, with signs (s1,s2) = position of the edge relative to the cell
+// centre along d1,d2 (RT:++, RB:+-, LT:-+, LB:--).
+template <int E>
+DEV Corner edge_state(const GridParams &g, const double *__restrict__ BASIS, const double *__restrict__ DBF,
+                      long long c, const bool s1p, const bool s2p) {
+  constexpr int D1 = (E + 1) % 3, D2 = (E + 2) % 3;
+  constexpr int S1 = slope_base(D1), S2 = slope_base(D2);
+  const long long N = g.ncell;
+  const long long st1 = D1 == 0 ? 1 : (D1 == 1 ? (long long)g.isize : (long long)g.isize * g.jsize);
+  const long long st2 = D2 == 0 ? 1 : (D2 == 1 ? (long long)g.isize : (long long)g.isize * g.jsize);
+  const double *Bc = BASIS + c;
+  auto comb = [&](int qi, int i1, int i2) {
+    const double a = Bc[(S1 + i1) * N], b = Bc[(S2 + i2) * N];
+    return Bc[qi * N] + ((s1p ? a : -a) + (s2p ? b : -b));
+  };
+  Corner o;
+  o.r = fmax(g.smallr, comb(BQ + ID, 0, 0));
+  o.p = fmax(g.smallp, comb(BQ + IP, 1, 1));
+  o.u = comb(BQ + IU + D1, 2 + D1, 2 + D1);
+  o.v = comb(BQ + IU + D2, 2 + D2, 2 + D2);
+  // field component normal to d1: face value on side s1, plus/minus half its limited slope along d2
+  {
+    const double face = Bc[(BFACE + 2 * D1 + (s1p ? 1 : 0)) * N];
+    const double h = 0.5 * DBF[(s1p ? c + st1 : c) + dbf_idx(D1, D2) * N];
+    o.a = face + (s2p ? h : -h);
+  }
+  {
+    const double face = Bc[(BFACE + 2 * D2 + (s2p ? 1 : 0)) * N];
+    const double h = 0.5 * DBF[(s2p ? c + st2 : c) + dbf_idx(D2, D1) * N];
+    o.b = face + (s1p ? h : -h);
+  }
+  o.c = comb(BQ + IA + E, slope_b(D1, E), slope_b(D2, E));
+  return o;
+}
+
+// ComputeEmfAndStoreFunctor3D (MHDRunFunctors3D.h:2100-2238) + compute_emf<dir>
+// (RiemannSolvers_MHD.h:651-874), one edge direction per launch. With the cyclic frame
+// (d1,d2) = Z:(x,y) X:(y,z) Y:(z,x) the reference's three cases (including its RB/LT swap for EMF_y)
+// are one pattern: RT from c-e1-e2, RB from c-e1, LT from c-e2, LB from c.
+template <int E>
+__global__ void __launch_bounds__(128) k_emf(const GridParams g, const double *__restrict__ BASIS,
+                                             const double *__restrict__ DBF, double *__restrict__ EMF) {
+  constexpr int D1 = (E + 1) % 3, D2 = (E + 2) % 3;
+  const int gw = g.gw;
+  const int k = gw + blockIdx.y;
+  const unsigned ni = g.nx + (E == 0 ? 0 : 1);
+  const unsigned nj = g.ny + (E == 1 ? 0 : 1);
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned jj = t / ni;
+  if (jj >= nj) return;
+  const int i = gw + (int)(t - jj * ni), j = gw + (int)jj;
+  const long long N = g.ncell;
+  const long long st1 = D1 == 0 ? 1 : (D1 == 1 ? (long long)g.isize : (long long)g.isize * g.jsize);
+  const long long st2 = D2 == 0 ? 1 : (D2 == 1 ? (long long)g.isize : (long long)g.isize * g.jsize);
+  const long long c = cidx(g, i, j, k);
+
+  const Corner RT = edge_state<E>(g, BASIS, DBF, c - st1 - st2, true, true);
+  const Corner RB = edge_state<E>(g, BASIS, DBF, c - st1, true, false);
+  const Corner LT = edge_state<E>(g, BASIS, DBF, c - st2, false, true);
+  const Corner LB = edge_state<E>(g, BASIS, DBF, c, false, false);
+
+  // compute_emf: LL<-RT, RL<-LT, LR<-RB, RR<-LB ; in-plane field averaged across the edge
+  Corner LL = RT, RL = LT, LR = RB, RR = LB;
+  const double a_top = 0.5 * (RT.a + LT.a), a_bot = 0.5 * (RB.a + LB.a);
+  const double b_rgt = 0.5 * (RT.b + RB.b), b_lft = 0.5 * (LT.b + LB.b);
+  LL.a = a_top; RL.a = a_top; LR.a = a_bot; RR.a = a_bot;
+  LL.b = b_rgt; LR.b = b_rgt; RL.b = b_lft; RR.b = b_lft;
+  const double ELL = LL.u * LL.b - LL.v * LL.a;
+  const double ERL = RL.u * RL.b - RL.v * RL.a;
+  const double ELR = LR.u * LR.b - LR.v * LR.a;
+  const double ERR = RR.u * RR.b - RR.v * RR.a;
+  EMF[c + (2 - E) * N] = mag_riemann2d_hlld(g.gamma0, g.smallc, LL, RL, LR, RR, ELL, ERL, ELR, ERR);
+}
+
+// Kokkos::deep_copy(data_out, data_in) (SolverMHDMuscl.cpp:477) + UpdateFunctor3D_MHD
+// (MHDRunFunctors3D.h:2430-2544) + UpdateEmfFunctor3D (:2549-2628) in one pass over the array:
+// ghost cells are copied, interior cells receive the 6 face fluxes (fixed order) and the CT update.
+__global__ void __launch_bounds__(256) k_update(const GridParams g, const StepState *__restrict__ stp,
+                                                const double *__restrict__ Uin, double *__restrict__ Uout,
+                                                const double *__restrict__ Fx, const double *__restrict__ Fy,
+                                                const double *__restrict__ Fz, const double *__restrict__ EMF) {
+  const int k = blockIdx.y;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned jj = t / (unsigned)g.isize;
+  const int i = (int)(t - jj * (unsigned)g.isize), j = (int)jj;
+  if (j >= g.jsize) return;
+  const long long N = g.ncell, sj = g.isize, sk = (long long)g.isize * g.jsize;
+  const long long c = cidx(g, i, j, k);
+  double u[NBVAR];
+#pragma unroll
+  for (int v = 0; v < NBVAR; ++v) u[v] = Uin[c + v * N];
+  const int gw = g.gw;
+  if (i >= gw && i < g.isize - gw && j >= gw && j < g.jsize - gw && k >= gw && k < g.ksize - gw) {
+    const double dt = stp->dt;
+    const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
+    // x faces: (rho,E,mx,my,mz) <- (0,1,2,3,4)
+    u[ID] += Fx[c + 0 * N] * dtdx; u[IP] += Fx[c + 1 * N] * dtdx; u[IU] += Fx[c + 2 * N] * dtdx;
+    u[IV] += Fx[c + 3 * N] * dtdx; u[IW] += Fx[c + 4 * N] * dtdx;
+    u[ID] -= Fx[c + 1 + 0 * N] * dtdx; u[IP] -= Fx[c + 1 + 1 * N] * dtdx; u[IU] -= Fx[c + 1 + 2 * N] * dtdx;
+    u[IV] -= Fx[c + 1 + 3 * N] * dtdx; u[IW] -= Fx[c + 1 + 4 * N] * dtdx;
+    // y faces, stored in the rotated frame: normal=my (2), t1=mx (3), t2=mz (4)
+    u[ID] += Fy[c + 0 * N] * dtdy; u[IP] += Fy[c + 1 * N] * dtdy; u[IU] += Fy[c + 3 * N] * dtdy;
+    u[IV] += Fy[c + 2 * N] * dtdy; u[IW] += Fy[c + 4 * N] * dtdy;
+    u[ID] -= Fy[c + sj + 0 * N] * dtdy; u[IP] -= Fy[c + sj + 1 * N] * dtdy; u[IU] -= Fy[c + sj + 3 * N] * dtdy;
+    u[IV] -= Fy[c + sj + 2 * N] * dtdy; u[IW] -= Fy[c + sj + 4 * N] * dtdy;
+    // z faces: normal=mz (2), t1=my (3), t2=mx (4)
+    u[ID] += Fz[c + 0 * N] * dtdz; u[IP] += Fz[c + 1 * N] * dtdz; u[IU] += Fz[c + 4 * N] * dtdz;
+    u[IV] += Fz[c + 3 * N] * dtdz; u[IW] += Fz[c + 2 * N] * dtdz;
+    u[ID] -= Fz[c + sk + 0 * N] * dtdz; u[IP] -= Fz[c + sk + 1 * N] * dtdz; u[IU] -= Fz[c + sk + 4 * N] * dtdz;
+    u[IV] -= Fz[c + sk + 3 * N] * dtdz; u[IW] -= Fz[c + sk + 2 * N] * dtdz;
+    // constrained transport, exact expression order of MHDRunFunctors3D.h:2602-2616
+    const double *Ez = EMF, *Ey = EMF + N, *Ex = EMF + 2 * N;
+    const double ez = Ez[c], ey = Ey[c], ex = Ex[c];
+    u[IA] += (Ez[c + sj] - ez) * dtdy;
+    u[IB] -= (Ez[c + 1] - ez) * dtdx;
+    u[IA] -= (Ey[c + sk] - ey) * dtdz;
+    u[IB] += (Ex[c + sk] - ex) * dtdz;
+    u[IC] += (Ey[c + 1] - ey) * dtdx;
+    u[IC] -= (Ex[c + sj] - ex) * dtdy;
+  }
+#pragma unroll
+  for (int v = 0; v < NBVAR; ++v) Uout[c + v * N] = u[v];
+}
+
+// Diagnostics: per-variable sums over the interior and max |div B| (needs filled upper ghosts).
+// Two-stage: per-block partials with warp shuffles, then double atomicAdd / ordered-bits atomicMax.
+__global__ void __launch_bounds__(256) k_diagnostics(const GridParams g, const double *__restrict__ U, double *out9) {
+  const int gw = g.gw;
+  const int k = gw + blockIdx.y;
+  const unsigned ni = g.nx;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned jj = t / ni;
+  double s[NBVAR], m = 0.0;
+#pragma unroll
+  for (int v = 0; v < NBVAR; ++v) s[v] = 0.0;
+  if (jj < (unsigned)g.ny) {
+    const int i = gw + (int)(t - jj * ni), j = gw + (int)jj;
+    const long long N = g.ncell, sj = g.isize, sk = (long long)g.isize * g.jsize;
+    const long long c = cidx(g, i, j, k);
+#pragma unroll
+    for (int v = 0; v < NBVAR; ++v) s[v] = U[c + v * N];
+    m = fabs((U[c + 1 + IA * N] - s[IA]) / g.dx + (U[c + sj + IB * N] - s[IB]) / g.dy + (U[c + sk + IC * N] - s[IC]) / g.dz);
+  }
+  __shared__ double red[8][NBVAR + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int v = 0; v < NBVAR; ++v)
+    for (int o = 16; o > 0; o >>= 1) s[v] += __shfl_xor_sync(0xffffffffu, s[v], o);
+  m = warp_max(m);
+  if (lane == 0) {
+    for (int v = 0; v < NBVAR; ++v) red[wid][v] = s[v];
+    red[wid][NBVAR] = m;
+  }
+  __syncthreads();
+  if (threadIdx.x < NBVAR) {
+    double a = 0.0;
+    for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) a += red[w2][threadIdx.x];
+    atomicAdd(&out9[threadIdx.x], a);
+  } else if (threadIdx.x == NBVAR) {
+    double a = 0.0;
+    for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) a = fmax(a, red[w2][NBVAR]);
+    atomicMax((unsigned long long *)&out9[NBVAR], (unsigned long long)__double_as_longlong(a));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+static void l_boundary(const GridParams &g, double *U, int dir, cudaStream_t s) {
+  const long long e0 = dir == 0 ? g.jsize : g.isize, e1 = dir == 2 ? g.jsize : g.ksize;
+  const long long total = 2LL * g.gw * e0 * e1;
+  const int bs = 256;
+  if (dir == 0) k_boundary<0><<<cdiv(total, bs), bs, 0, s>>>(g, U);
+  else if (dir == 1) k_boundary<1><<<cdiv(total, bs), bs, 0, s>>>(g, U);
+  else k_boundary<2><<<cdiv(total, bs), bs, 0, s>>>(g, U);
+}
+static void l_prim_dt(const GridParams &g, const double *U, double *Q, StepState *st, int k0, int k1, cudaStream_t s) {
+  if (k1 <= k0) return;
+  const int bs = 256;
+  dim3 grid(cdiv((long long)g.isize * g.jsize, bs), k1 - k0);
+  k_prim_dt<<<grid, bs, 0, s>>>(g, U, Q, st, k0);
+}
+static void l_finalize_dt(const GridParams &g, StepState *st, cudaStream_t s) { k_finalize_dt<<<1, 1, 0, s>>>(g, st); }
+static void l_advance_time(StepState *st, cudaStream_t s) { k_advance_time<<<1, 1, 0, s>>>(st); }
+static void l_elec_dbf(const GridParams &g, const double *U, const double *Q, double *E, double *DBF, cudaStream_t s) {
+  const int bs = 256;
+  dim3 grid(cdiv((long long)(g.isize - 2) * (g.jsize - 2), bs), g.ksize - 2);
+  k_elec_dbf<<<grid, bs, 0, s>>>(g, U, Q, E, DBF);
+}
+static void l_trace(const GridParams &g, const StepState *st, const double *U, const double *Q, const double *E,
+                    double *BASIS, cudaStream_t s) {
+  const int bs = 128;
+  dim3 grid(cdiv((long long)(g.isize - 4) * (g.jsize - 4), bs), g.ksize - 4);
+  k_trace<<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS);
+}
+static void l_flux(const GridParams &g, int dir, const double *BASIS, double *F, cudaStream_t s) {
+  const int bs = 128;
+  const long long ni = g.nx + (dir == 0), nj = g.ny + (dir == 1), nk = g.nz + (dir == 2);
+  dim3 grid(cdiv(ni * nj, bs), (unsigned)nk);
+  if (dir == 0) k_flux<0><<<grid, bs, 0, s>>>(g, BASIS, F);
+  else if (dir == 1) k_flux<1><<<grid, bs, 0, s>>>(g, BASIS, F);
+  else k_flux<2><<<grid, bs, 0, s>>>(g, BASIS, F);
+}
+static void l_emf(const GridParams &g, int e, const double *BASIS, const double *DBF, double *EMF, cudaStream_t s) {
+  const int bs = 128;
+  const long long ni = g.nx + (e != 0), nj = g.ny + (e != 1), nk = g.nz + (e != 2);
+  dim3 grid(cdiv(ni * nj, bs), (unsigned)nk);
+  if (e == 0) k_emf<0><<<grid, bs, 0, s>>>(g, BASIS, DBF, EMF);
+  else if (e == 1) k_emf<1><<<grid, bs, 0, s>>>(g, BASIS, DBF, EMF);
+  else k_emf<2><<<grid, bs, 0, s>>>(g, BASIS, DBF, EMF);
+}
+static void l_update(const GridParams &g, const StepState *st, const double *Uin, double *Uout, const double *Fx,
+                     const double *Fy, const double *Fz, const double *EMF, cudaStream_t s) {
+  const int bs = 256;
+  dim3 grid(cdiv((long long)g.isize * g.jsize, bs), g.ksize);
+  k_update<<<grid, bs, 0, s>>>(g, st, Uin, Uout, Fx, Fy, Fz, EMF);
+}
+static void l_diagnostics(const GridParams &g, const double *U, double *out9, cudaStream_t s) {
+  const int bs = 256;
+  dim3 grid(cdiv((long long)g.nx * g.ny, bs), g.nz);
+  k_diagnostics<<<grid, bs, 0, s>>>(g, U, out9);
+}
+
+static const KernelTable table = {
+#if PPK_EXACT
+  "exact",
+#else
+  "fast",
+#endif
+  l_boundary, l_prim_dt, l_finalize_dt, l_advance_time, l_elec_dbf, l_trace, l_flux, l_emf, l_update, l_diagnostics,
+};
+
+}  // namespace PPK_NS
+
+#if PPK_EXACT
+const KernelTable *kernel_table_exact() { return &ppk_exact::table; }
+#else
+const KernelTable *kernel_table_fast() { return &ppk_fast::table; }
+#endif
+
+}  // namespace ppk

@@ -1,0 +1,261 @@
+#include "SolverMHDMusclCuda3D.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <vector>
+
+namespace ppkMHD {
+
+namespace {
+[[noreturn]] void die(const char *what, int rc) {
+  // no exceptions on the solver path: print and abort like the reference does for fatal conditions
+  fprintf(stderr, "ppkmhd_b200: %s failed (status %d): %s\n", what, rc, ppk_last_error_string());
+  std::abort();
+}
+#define PPK_CALL(expr)                 \
+  do {                                 \
+    int rc_ = (expr);                  \
+    if (rc_ != 0) die(#expr, rc_);     \
+  } while (0)
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// problem parameters
+// ---------------------------------------------------------------------------------------------
+BlastParams::BlastParams(ConfigMap &c) {  // src/shared/problems/BlastParams.h:24-40
+  const double xmin = c.getFloat("mesh", "xmin", 0.0), ymin = c.getFloat("mesh", "ymin", 0.0), zmin = c.getFloat("mesh", "zmin", 0.0);
+  const double xmax = c.getFloat("mesh", "xmax", 1.0), ymax = c.getFloat("mesh", "ymax", 1.0), zmax = c.getFloat("mesh", "zmax", 1.0);
+  blast_radius = c.getFloat("blast", "radius", (xmin + xmax) / 2.0 / 10);
+  blast_center_x = c.getFloat("blast", "center_x", (xmin + xmax) / 2);
+  blast_center_y = c.getFloat("blast", "center_y", (ymin + ymax) / 2);
+  blast_center_z = c.getFloat("blast", "center_z", (zmin + zmax) / 2);
+  blast_density_in = c.getFloat("blast", "density_in", 1.0);
+  blast_density_out = c.getFloat("blast", "density_out", 1.2);
+  blast_pressure_in = c.getFloat("blast", "pressure_in", 10.0);
+  blast_pressure_out = c.getFloat("blast", "pressure_out", 0.1);
+}
+FieldLoopParams::FieldLoopParams(ConfigMap &c) {  // src/shared/problems/FieldLoopParams.h:24-33
+  radius = c.getFloat("FieldLoop", "radius", 1.0);
+  density_in = c.getFloat("FieldLoop", "density_in", 1.0);
+  amplitude = c.getFloat("FieldLoop", "amplitude", 1.0);
+  vflow = c.getFloat("FieldLoop", "vflow", 1.0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// initial conditions (host, then uploaded)
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct CellCoords {
+  const HydroParams &p;
+  double x(int i) const { return p.xmin + p.dx / 2 + (i + p.nx * p.myMpiPos[0] - p.ghostWidth) * p.dx; }
+  double y(int j) const { return p.ymin + p.dy / 2 + (j + p.ny * p.myMpiPos[1] - p.ghostWidth) * p.dy; }
+  double z(int k) const { return p.zmin + p.dz / 2 + (k + p.nz * p.myMpiPos[2] - p.ghostWidth) * p.dz; }
+};
+inline double sqr(double v) { return v * v; }
+}  // namespace
+
+void init_orszag_tang(const HydroParams &p, const OrszagTangParams &ot, DataArray3dHost &U) {
+  const double pi = 3.141592653589793238462643383279502884L, twopi = 2 * pi;
+  const double gamma0 = p.settings.gamma0;
+  const double B0 = 1.0 / sqrt(4 * pi), p0 = gamma0 / (4 * pi), d0 = gamma0 * p0, v0 = 1.0, kt = ot.kt;
+  const CellCoords cc{p};
+  // sweep 1: everything but the energy, on the whole array
+  for (int k = 0; k < p.ksize; ++k)
+    for (int j = 0; j < p.jsize; ++j)
+      for (int i = 0; i < p.isize; ++i) {
+        const double xPos = cc.x(i), yPos = cc.y(j), zPos = cc.z(k);
+        const double zphase = cos(2 * twopi * kt * (zPos - p.zmin) / (p.zmax - p.zmin));
+        U(i, j, k, ID) = d0;
+        U(i, j, k, IU) = -d0 * v0 * sin(yPos * twopi);
+        U(i, j, k, IV) = d0 * v0 * sin(xPos * twopi);
+        U(i, j, k, IW) = 0.0;
+        U(i, j, k, IBX) = -B0 * zphase * sin(yPos * twopi);
+        U(i, j, k, IBY) = B0 * zphase * sin(2.0 * xPos * twopi);
+        U(i, j, k, IBZ) = 0.0;
+      }
+  // sweep 2: energy from the cell-centred field; the last i / j planes are skipped (they are ghosts)
+  for (int k = 0; k < p.ksize; ++k)
+    for (int j = 0; j < p.jsize - 1; ++j)
+      for (int i = 0; i < p.isize - 1; ++i)
+        U(i, j, k, IP) = p0 / (gamma0 - 1.0) +
+                         0.5 * (sqr(U(i, j, k, IU)) / U(i, j, k, ID) + sqr(U(i, j, k, IV)) / U(i, j, k, ID) +
+                                0.25 * sqr(U(i, j, k, IBX) + U(i + 1, j, k, IBX)) + 0.25 * sqr(U(i, j, k, IBY) + U(i, j + 1, k, IBY)));
+}
+
+void init_blast(const HydroParams &p, const BlastParams &b, DataArray3dHost &U) {
+  const double radius2 = b.blast_radius * b.blast_radius;
+  const CellCoords cc{p};
+  for (int k = 0; k < p.ksize; ++k)
+    for (int j = 0; j < p.jsize; ++j)
+      for (int i = 0; i < p.isize; ++i) {
+        const double x = cc.x(i), y = cc.y(j), z = cc.z(k);
+        const double d2 = (x - b.blast_center_x) * (x - b.blast_center_x) + (y - b.blast_center_y) * (y - b.blast_center_y) +
+                          (z - b.blast_center_z) * (z - b.blast_center_z);
+        const bool in = d2 < radius2;
+        U(i, j, k, ID) = in ? b.blast_density_in : b.blast_density_out;
+        U(i, j, k, IU) = 0.0;
+        U(i, j, k, IV) = 0.0;
+        U(i, j, k, IW) = 0.0;
+        U(i, j, k, IA) = 0.5;  // hard-coded uniform field of the reference
+        U(i, j, k, IB) = 0.5;
+        U(i, j, k, IC) = 0.5;
+        U(i, j, k, IP) = (in ? b.blast_pressure_in : b.blast_pressure_out) / (p.settings.gamma0 - 1.0) +
+                         0.5 * (sqr(U(i, j, k, IA)) + sqr(U(i, j, k, IB)) + sqr(U(i, j, k, IC)));
+      }
+}
+
+void init_field_loop(const HydroParams &p, const FieldLoopParams &fl, DataArray3dHost &U) {
+  const int gw = p.ghostWidth;
+  const CellCoords cc{p};
+  // vector potential: only A_z is non-zero
+  std::vector<double> Az((size_t)p.isize * p.jsize, 0.0);  // z-invariant
+  for (int j = 0; j < p.jsize; ++j)
+    for (int i = 0; i < p.isize; ++i) {
+      const double x = cc.x(i), y = cc.y(j);
+      const double r = sqrt(x * x + y * y);
+      Az[(size_t)i + (size_t)p.isize * j] = r < fl.radius ? fl.amplitude * (fl.radius - r) : 0.0;
+    }
+  auto A = [&](int i, int j) { return Az[(size_t)i + (size_t)p.isize * j]; };
+  const double cos_theta = 2.0 / sqrt(5.0);
+  const double sin_theta = sqrt(1 - cos_theta * cos_theta);
+  for (int k = gw; k < p.ksize - gw; ++k)
+    for (int j = gw; j < p.jsize - gw; ++j)
+      for (int i = gw; i < p.isize - gw; ++i) {
+        const double x = cc.x(i), y = cc.y(j);
+        const double r = sqrt(x * x + y * y);
+        const double d = r < fl.radius ? fl.density_in : 1.0;
+        U(i, j, k, ID) = d;
+        U(i, j, k, IU) = d * fl.vflow * cos_theta;
+        U(i, j, k, IV) = d * fl.vflow * sin_theta;
+        U(i, j, k, IW) = d * fl.vflow;
+        U(i, j, k, IA) = (A(i, j + 1) - A(i, j)) / p.dy - (0.0 - 0.0) / p.dz;   // B = curl A, first differences
+        U(i, j, k, IB) = (0.0 - 0.0) / p.dz - (A(i + 1, j) - A(i, j)) / p.dx;
+        U(i, j, k, IC) = (0.0 - 0.0) / p.dx - (0.0 - 0.0) / p.dy;
+      }
+  // energy; the upper neighbours of the last interior cells are still-zero ghosts, as in the reference
+  for (int k = gw; k < p.ksize - gw; ++k)
+    for (int j = gw; j < p.jsize - gw; ++j)
+      for (int i = gw; i < p.isize - gw; ++i)
+        U(i, j, k, IP) = 1.0f / (p.settings.gamma0 - 1.0) +
+                         0.5 * (0.25 * sqr(U(i, j, k, IA) + U(i + 1, j, k, IA)) + 0.25 * sqr(U(i, j, k, IB) + U(i, j + 1, k, IB)) +
+                                0.25 * sqr(U(i, j, k, IC) + U(i, j, k + 1, IC))) +
+                         0.5 * (U(i, j, k, IU) * U(i, j, k, IU) + U(i, j, k, IV) * U(i, j, k, IV) + U(i, j, k, IW) * U(i, j, k, IW)) /
+                           U(i, j, k, ID);
+}
+
+std::string init_problem(const HydroParams &params, ConfigMap &configMap, const std::string &problem, DataArray3dHost &U) {
+  if (problem == "blast") {
+    init_blast(params, BlastParams(configMap), U);
+    return problem;
+  }
+  if (problem == "orszag_tang") {
+    init_orszag_tang(params, OrszagTangParams(configMap), U);
+    return problem;
+  }
+  if (problem == "field_loop" || problem == "field loop") {
+    init_field_loop(params, FieldLoopParams(configMap), U);
+    return problem;
+  }
+  // implode / kelvin_helmholtz / rotor / wave are "next" rows; like the reference's final else,
+  // an unknown name falls back to Orszag-Tang with a message (SolverMHDMuscl.h:701-709)
+  std::cout << "Problem : " << problem << " is not recognized / implemented." << std::endl;
+  std::cout << "Use default - Orszag-Tang vortex" << std::endl;
+  init_orszag_tang(params, OrszagTangParams(configMap), U);
+  return "orszag_tang";
+}
+
+// ---------------------------------------------------------------------------------------------
+// the solver
+// ---------------------------------------------------------------------------------------------
+SolverMHDMusclCuda3D::SolverMHDMusclCuda3D(HydroParams &params_, ConfigMap &configMap_) : SolverBase(params_, configMap_) {
+  solver_type = SOLVER_MUSCL_HANCOCK;
+  m_nCells = (long)params.isize * params.jsize * params.ksize;  // ghosts included, like the reference
+  m_nDofsPerCell = 1;
+  if (params.riemannSolverType != RIEMANN_HLLD) {
+    fprintf(stderr, "MHD_Muscl_3D (CUDA): riemann=%s is not implemented; only hlld is "
+                    "(the reference silently computes a zero flux for 'approx')\n",
+            configMap.getString("hydro", "riemann", "approx").c_str());
+    std::abort();
+  }
+  ppk_mhd3d_params cp = params.to_c_params();
+  PPK_CALL(ppk_mhd3d_create(&cp, &m_handle));
+
+  Uhost = DataArray3dHost(params.isize, params.jsize, params.ksize, params.nbvar);
+  const bool restartEnabled = configMap.getBool("run", "restart_enabled", false);
+  if (restartEnabled)
+    std::cout << "restart needs HDF5 (as in the reference, IO_ReadWrite.cpp:245-287): not available, starting from t=0\n";
+  m_problem_name = init_problem(params, configMap, m_problem_name, Uhost);
+
+  // constructor sequence of the reference (SolverMHDMuscl.h:390-402): upload, ghost fill, dt
+  PPK_CALL(ppk_mhd3d_upload(m_handle, Uhost.data()));
+  PPK_CALL(ppk_mhd3d_set_time(m_handle, m_t, m_tEnd, 0));
+  if (params.nProcs == 1) {
+    make_boundaries();
+    compute_dt();
+  }  // a decomposed run does this in comm_init(), once the communicator exists
+
+  if (params.myRank == 0) {
+    std::cout << "##########################" << "\n";
+    std::cout << "Solver is " << m_solver_name << " (B200-native CUDA, " << ppk_version_string() << ")\n";
+    std::cout << "Problem (init condition) is " << m_problem_name << "\n";
+    std::cout << "##########################" << "\n";
+    params.print();
+    std::cout << "##########################" << "\n";
+    std::cout << "Memory requested : " << (ppk_mhd3d_device_bytes(m_handle) / 1e6) << " MBytes\n";
+    std::cout << "##########################" << "\n";
+  }
+}
+
+SolverMHDMusclCuda3D::~SolverMHDMusclCuda3D() { ppk_mhd3d_destroy(m_handle); }
+
+void SolverMHDMusclCuda3D::comm_init(const void *unique_id_128) {
+  PPK_CALL(ppk_mhd3d_comm_init(m_handle, unique_id_128, params.nProcs, params.myRank));
+  make_boundaries();
+  compute_dt();
+}
+
+void SolverMHDMusclCuda3D::make_boundaries() {
+  timers[TIMER_BOUNDARIES]->start();
+  PPK_CALL(ppk_mhd3d_make_boundaries(m_handle));
+  timers[TIMER_BOUNDARIES]->stop();
+}
+
+double SolverMHDMusclCuda3D::compute_dt_local() {
+  double dt = 0.0;
+  PPK_CALL(ppk_mhd3d_compute_dt(m_handle, &dt));  // global value already (NCCL max-allreduce of 1/dt)
+  return dt;
+}
+
+void SolverMHDMusclCuda3D::next_iteration_impl() {  // SolverMHDMuscl.h:747-784
+  if (m_iteration % m_nlog == 0 && params.myRank == 0)
+    printf("time step=%7d (dt=% 10.8f t=% 10.8f)\n", m_iteration, m_dt, m_t);
+  if (params.enableOutput && should_save_solution()) {
+    if (params.myRank == 0)
+      std::cout << "Output results at time t=" << m_t << " step " << m_iteration << " dt=" << m_dt << std::endl;
+    save_solution();
+  }
+  godunov_unsplit();
+}
+
+void SolverMHDMusclCuda3D::godunov_unsplit() {
+  // the whole of godunov_unsplit_impl is one asynchronous C-ABI call; reading back (t, dt) is the only
+  // synchronisation, it replaces the reference's per-step device->host read of the Max reduction
+  timers[TIMER_NUM_SCHEME]->start();
+  PPK_CALL(ppk_mhd3d_step(m_handle));
+  double t_after = 0.0, dt = 0.0;
+  PPK_CALL(ppk_mhd3d_get_time(m_handle, &t_after, &dt, nullptr));
+  timers[TIMER_NUM_SCHEME]->stop();
+  m_dt = dt;  // SolverBase::next_iteration then does m_t += m_dt, the same addition the device did
+  (void)t_after;
+}
+
+void SolverMHDMusclCuda3D::save_solution_impl() {  // SolverMHDMuscl.h:896-907
+  timers[TIMER_IO]->start();
+  PPK_CALL(ppk_mhd3d_download(m_handle, Uhost.data()));
+  save_data(Uhost, m_times_saved, m_t);
+  timers[TIMER_IO]->stop();
+}
+
+}  // namespace ppkMHD

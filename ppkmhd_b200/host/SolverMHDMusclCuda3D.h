@@ -1,0 +1,53 @@
+// Drop-in for SolverMHDMuscl<3> (src/muscl/SolverMHDMuscl.h:48-200) registered under "MHD_Muscl_3D":
+// same SolverBase interface and time-loop semantics, the Kokkos functors of godunov_unsplit_impl
+// (src/muscl/SolverMHDMuscl.cpp:465-517) replaced by the C ABI of include/ppkmhd_b200.h.
+#pragma once
+#include "SolverBase.h"
+
+namespace ppkMHD {
+
+// problem parameter blocks of the reference (src/shared/problems/*.h), float-precision parsing included
+struct BlastParams {
+  real_t blast_radius, blast_center_x, blast_center_y, blast_center_z;
+  real_t blast_density_in, blast_density_out, blast_pressure_in, blast_pressure_out;
+  explicit BlastParams(ConfigMap &configMap);
+};
+struct OrszagTangParams {
+  real_t kt;
+  explicit OrszagTangParams(ConfigMap &configMap) { kt = configMap.getFloat("OrszagTang", "kt", 0.0); }
+};
+struct FieldLoopParams {
+  real_t radius, density_in, amplitude, vflow;
+  explicit FieldLoopParams(ConfigMap &configMap);
+};
+
+// host-side initial conditions (libm sin/cos/sqrt like the reference's OpenMP build); they fill the
+// whole array, ghosts included, exactly where the reference's init functors do
+void init_orszag_tang(const HydroParams &params, const OrszagTangParams &ot, DataArray3dHost &U);  // MHDInitFunctors3D.h:264-415
+void init_blast(const HydroParams &params, const BlastParams &b, DataArray3dHost &U);              // MHDInitFunctors3D.h:155-259
+void init_field_loop(const HydroParams &params, const FieldLoopParams &fl, DataArray3dHost &U);    // MHDInitFunctors3D.h:759-1023
+// SolverMHDMuscl<dim>::init dispatch (SolverMHDMuscl.h:653-713); returns the problem name actually used
+std::string init_problem(const HydroParams &params, ConfigMap &configMap, const std::string &problem, DataArray3dHost &U);
+
+class SolverMHDMusclCuda3D : public SolverBase {
+public:
+  SolverMHDMusclCuda3D(HydroParams &params, ConfigMap &configMap);
+  ~SolverMHDMusclCuda3D() override;
+  static SolverBase *create(HydroParams &params, ConfigMap &configMap) { return new SolverMHDMusclCuda3D(params, configMap); }
+
+  double compute_dt_local() override;
+  void next_iteration_impl() override;
+  void save_solution_impl() override;
+  void make_boundaries() override;
+
+  // attach the NCCL communicator of a decomposed run (unique id produced on rank 0)
+  void comm_init(const void *unique_id_128);
+  ppk_mhd3d *handle() { return m_handle; }
+  DataArray3dHost Uhost;
+
+private:
+  void godunov_unsplit();
+  ppk_mhd3d *m_handle = nullptr;
+};
+
+}  // namespace ppkMHD

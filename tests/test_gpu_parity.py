@@ -1,0 +1,190 @@
+"""GPU parity tests (run with -m gpu on the B200 box). Everything goes through the C ABI of
+include/ppkmhd_b200.h; the checker is (a) the golden fixtures written by the unmodified reference and
+(b) the plain-C oracle, itself pinned to the reference bit for bit.
+
+Bars (BASELINE.json north_star): exact-arithmetic build => BIT-IDENTICAL conserved variables;
+fast (FMA) build => |a-b| <= 1e-12*max(|a|, max_domain|var|) per cell after one step, conserved sums
+within 1e-10 relative and max|div B| <= 1e-12 after 100 steps.
+"""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, golden_cases
+
+pytestmark = pytest.mark.gpu
+
+import ppkmhd_b200 as ppk  # noqa: E402
+
+OT = "[OrszagTang]\nkt=1\n"
+BLAST = "[blast]\nradius=0.25\ndensity_in=1.0\ndensity_out=1.2\npressure_in=10.0\npressure_out=0.1\n"
+
+
+def make_solver(ini, exact=True):
+    p, t_end, nstep = ppk.params_from_ini(ini, exact=exact)
+    s = ppk.Mhd3d(p)
+    s.upload(ppk.init_condition_from_ini(ini))
+    s.set_time(0.0, t_end, 0)
+    return s, nstep
+
+
+def close_per_cell(a, b, rtol=1e-12):
+    """|a-b| <= rtol * max(|a|, max_domain |var|), per variable."""
+    for v in range(8):
+        scale = np.maximum(np.abs(b[v]), np.abs(b[v]).max())
+        bad = np.abs(a[v] - b[v]) > rtol * scale + 1e-300
+        assert not bad.any(), f"var {v}: max abs diff {np.abs(a[v] - b[v]).max():.3e} (field max {np.abs(b[v]).max():.3e})"
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_exact_mode_bit_identical_to_reference(case):
+    g = np.load(f"{GOLDEN}/{case}.npz")
+    s, nstep = make_solver(str(g["ini"]), exact=True)
+    assert np.array_equal(s.interior(), g["init"])
+    s.step()
+    t, dt, it = s.get_time()
+    assert it == 1 and abs(dt - g["log_dt"][0]) <= 0.5e-8 + 1e-15
+    assert np.array_equal(s.interior(), g["step1"]), "step 1 differs from the reference"
+    s.run(nstep - 1)
+    t, dt, it = s.get_time()
+    assert it == nstep and abs(t - float(g["final_time"])) <= 0.5e-6 + 1e-12
+    assert np.array_equal(s.interior(), g["stepN"]), f"step {nstep} differs from the reference"
+    s.close()
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_fast_mode_within_1e12_of_reference(case):
+    g = np.load(f"{GOLDEN}/{case}.npz")
+    s, nstep = make_solver(str(g["ini"]), exact=False)
+    s.step()
+    close_per_cell(s.interior(), g["step1"], 1e-12)
+    s.run(nstep - 1)
+    close_per_cell(s.interior(), g["stepN"], 1e-11)  # a few steps of round-off growth
+    s.close()
+
+
+@pytest.mark.parametrize("problem,n,extra,bounds,cfl", [
+    ("orszag_tang", (48, 40, 36), OT, None, 0.8),
+    ("blast", (40, 40, 40), BLAST, None, 0.8),
+    ("field_loop", (64, 32, 32), "[FieldLoop]\nradius=0.3\namplitude=0.001\nvflow=3\ndensity_in=1\n", (-1, 1, -0.5, 0.5, -0.5, 0.5), 0.4),
+])
+def test_exact_mode_vs_oracle_with_intermediates(problem, n, extra, bounds, cfl, oracle_mod):
+    """Larger grids than the fixtures, against the C oracle, including every intermediate array."""
+    O = oracle_mod
+    ini = O.make_ini(problem, n, nstepmax=4, extra=extra, bounds=bounds, cfl=cfl, tend=10.0)
+    orc = O.Oracle(ini)
+    s, _ = make_solver(ini, exact=True)
+    for step in range(4):
+        orc.step()
+        s.step()
+        t, dt, it = s.get_time()
+        assert dt == orc.dt and t == orc.t, f"dt/t differ at step {step}: {dt} vs {orc.dt}"
+        if step == 0:
+            gw = 3
+            Q = s.debug_array("Q")
+            assert np.array_equal(Q[:, :-1, :-1, :-1], orc.Q[:, :-1, :-1, :-1]), "primitive variables"
+            E = s.debug_array("ElecField")
+            assert np.array_equal(E[:, 1:-1, 1:-1, 1:-1], orc.scratch_array("ElecField", 3)[:, 1:-1, 1:-1, 1:-1])
+            emf = s.debug_array("Emf")
+            eo = orc.scratch_array("Emf", 3)
+            nz, ny, nx = n[2], n[1], n[0]
+            # each EMF component on the edges the CT update reads
+            assert np.array_equal(emf[0, gw:gw + nz, gw:gw + ny + 1, gw:gw + nx + 1], eo[0, gw:gw + nz, gw:gw + ny + 1, gw:gw + nx + 1]), "EMF_z"
+            assert np.array_equal(emf[1, gw:gw + nz + 1, gw:gw + ny, gw:gw + nx + 1], eo[1, gw:gw + nz + 1, gw:gw + ny, gw:gw + nx + 1]), "EMF_y"
+            assert np.array_equal(emf[2, gw:gw + nz + 1, gw:gw + ny + 1, gw:gw + nx], eo[2, gw:gw + nz + 1, gw:gw + ny + 1, gw:gw + nx]), "EMF_x"
+            for d, name in enumerate(("Fluxes_x", "Fluxes_y", "Fluxes_z")):
+                F = s.debug_array(name)
+                Fo = orc.scratch_array(name, 8)[:5]  # rho, E, normal, t1, t2 momentum fluxes
+                sl = [slice(gw, gw + nz + (d == 2)), slice(gw, gw + ny + (d == 1)), slice(gw, gw + nx + (d == 0))]
+                assert np.array_equal(F[(slice(None), *sl)], Fo[(slice(None), *sl)]), name
+        assert np.array_equal(s.interior(), orc.interior()), f"state differs at step {step + 1}"
+    sums, divb = s.diagnostics()
+    so, do = orc.diagnostics()
+    assert np.allclose(sums, so, rtol=1e-13, atol=1e-12) and abs(divb - do) <= 1e-18 + 1e-12 * do
+    s.close()
+
+
+def test_hundred_steps_conserved_sums_and_divb(oracle_mod):
+    """North-star 100-step criterion at 32^3 (oracle run takes ~20 s): sums within 1e-10, div B <= 1e-12."""
+    O = oracle_mod
+    ini = O.make_ini("orszag_tang", (32, 32, 32), nstepmax=100, extra=OT, tend=10.0)
+    orc = O.Oracle(ini).run()
+    so, divb_o = orc.diagnostics()
+    for exact in (True, False):
+        s, nstep = make_solver(ini, exact=exact)
+        s.run(nstep)
+        t, _, it = s.get_time()
+        assert it == 100
+        sums, divb = s.diagnostics()
+        scale = np.abs(orc.interior()).reshape(8, -1).sum(axis=1)
+        assert np.all(np.abs(sums - so) <= 1e-10 * np.maximum(np.abs(so), 1e-10 * scale) + 1e-10 * scale * 1e-2), (sums, so)
+        assert divb <= max(1e-12, 4 * divb_o)
+        if exact:
+            assert t == orc.t and np.array_equal(s.interior(), orc.interior())
+        else:
+            assert abs(t - orc.t) <= 1e-12
+        s.close()
+
+
+def test_dropin_executable_matches_reference_vti_bytes(oracle_mod):
+    """ppkMHD_b200 <ini> (SolverFactory -> 'MHD_Muscl_3D' -> C ABI) writes the same .vti payload as the
+    reference; when the reference binary travelled to this box, compare the files byte for byte."""
+    O = oracle_mod
+    g = np.load(f"{GOLDEN}/ot_16x12x8.npz")
+    ini = str(g["ini"])
+    exe = os.path.join(ROOT, "ppkmhd_b200", "bin", "ppkMHD_b200")
+    with tempfile.TemporaryDirectory() as tmp:
+        open(os.path.join(tmp, "run.ini"), "w").write(ini)
+        out = subprocess.run([exe, "run.ini"], cwd=tmp, capture_output=True, text=True, check=True).stdout
+        files = sorted(f for f in os.listdir(tmp) if f.endswith(".vti"))
+        assert len(files) == 2, out
+        assert np.array_equal(O.read_vti(os.path.join(tmp, files[0])), g["init"])
+        assert np.array_equal(O.read_vti(os.path.join(tmp, files[1])), g["stepN"])
+        assert "final time is %f" % float(g["final_time"]) in out
+        assert "time step=      0 (dt=% 10.8f t=% 10.8f)" % (g["log_dt"][0], 0.0) in out
+        if O.have_reference():
+            with tempfile.TemporaryDirectory() as tmp2:
+                open(os.path.join(tmp2, "run.ini"), "w").write(ini)
+                subprocess.run([O.REF_BIN, "run.ini"], cwd=tmp2, capture_output=True, check=True,
+                               env=dict(os.environ, OMP_NUM_THREADS="4"))
+                for f in files:
+                    assert open(os.path.join(tmp, f), "rb").read() == open(os.path.join(tmp2, f), "rb").read(), f
+
+
+def test_full_size_properties_256():
+    """BASELINE configs[1] size (256^3): checks that need no oracle run.
+    * 2.5-D Orszag-Tang (kt=0) stays exactly z-invariant in exact mode (every k-plane bit-identical);
+    * periodic box: mass, momentum, energy and mean field conserved to round-off; div B at round-off."""
+    from oracle import oracle as O  # ini text helper only
+
+    ini = O.make_ini("orszag_tang", (256, 256, 256), nstepmax=3, tend=10.0)
+    s, _ = make_solver(ini, exact=True)
+    s0, d0 = s.diagnostics()
+    s.run(3)
+    s1, d1 = s.diagnostics()
+    U = s.interior()
+    assert np.array_equal(U[:, :1].repeat(256, axis=1), U), "z-invariance broken"
+    ncell = 256.0 ** 3
+    for v in range(8):
+        assert abs(s1[v] - s0[v]) <= 1e-12 * ncell * max(1.0, abs(U[v]).max()), (v, s0[v], s1[v])
+    assert d1 <= 1e-11
+    # fast build on the same problem stays within round-off of the exact build
+    f, _ = make_solver(ini, exact=False)
+    f.run(3)
+    close_per_cell(f.interior(), U, 1e-11)
+    f.close()
+    s.close()
+
+
+def test_error_paths():
+    g = np.load(f"{GOLDEN}/ot_16x12x8.npz")
+    ini = str(g["ini"])
+    p, _, _ = ppk.params_from_ini(ini.replace("riemann=hlld", "riemann=hll"))
+    with pytest.raises(ppk.PpkError, match="hlld"):
+        ppk.Mhd3d(p)
+    p, _, _ = ppk.params_from_ini(ini.replace("implementationVersion=0", "implementationVersion=2"))
+    with pytest.raises(ppk.PpkError, match="implementationVersion"):
+        ppk.Mhd3d(p)

@@ -1,0 +1,83 @@
+"""CPU: the C++ host layer (ConfigMap / HydroParams / initial conditions) and the C-ABI surface.
+No compute call is made here (there is no GPU on the CPU box)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, golden_cases
+
+import ppkmhd_b200 as ppk
+from ppkmhd_b200 import capi
+
+
+def test_library_exports_every_declared_symbol():
+    """Every function declared in include/*.h is exported by the shared library."""
+    declared = set()
+    for hdr in ("ppkmhd_b200.h", "ppkmhd_b200_host.h"):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        declared |= set(re.findall(r"\b(ppk_[a-z0-9_]+)\s*\(", text))
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+    L = C.CDLL(ppk.lib_path())
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} not exported"
+    assert b"sm_100a" in ppk.load_library().ppk_version_string()
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_params_match_oracle_and_float_parsing(case, oracle_mod):
+    ini = str(np.load(f"{GOLDEN}/{case}.npz")["ini"])
+    p, t_end, nstep = ppk.params_from_ini(ini)
+    o = oracle_mod.params_from_config(oracle_mod.Config(ini))
+    for f in ("nx", "ny", "nz", "dx", "dy", "dz", "xmin", "xmax", "ymin", "ymax", "zmin", "zmax",
+              "gamma0", "cfl", "slope_type", "smallr", "smallc", "smallp"):
+        assert getattr(p, f) == getattr(o, f), f
+    assert list(p.boundary_type) == list(o.bc)
+    assert p.gamma0 == 1.66600000858306884765625  # float-precision parse
+    assert p.ghost_width == 3 and p.riemann_solver == 4 and p.implementation_version == 0
+    assert t_end == 10.0 and nstep == int(np.load(f"{GOLDEN}/{case}.npz")["nsteps"])
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_initial_condition_bitwise(case, oracle_mod):
+    g = np.load(f"{GOLDEN}/{case}.npz")
+    ini = str(g["ini"])
+    U = ppk.init_condition_from_ini(ini)
+    assert np.array_equal(U[:, 3:-3, 3:-3, 3:-3], g["init"]), "differs from the reference's step-0 .vti"
+    orc = oracle_mod.Oracle(ini)
+    Uo = oracle_mod.init_problem(orc.p, orc.cfg)
+    assert np.array_equal(U, Uo), "ghost cells differ from the oracle's initial array"
+
+
+def test_slab_params(oracle_mod):
+    """[mpi] mz slabs: dz uses the global extent nz*mz (HydroParams.cpp:400-402); cell centres shift."""
+    ini = oracle_mod.make_ini("orszag_tang", (16, 12, 8), extra="[OrszagTang]\nkt=1\n", mz=2)
+    p0, _, _ = ppk.params_from_ini(ini, rank_z=0)
+    p1, _, _ = ppk.params_from_ini(ini, rank_z=1)
+    assert p0.mz == 2 and p1.rank_z == 1 and p0.dz == 1.0 / 16
+    U1 = ppk.init_condition_from_ini(ini, rank_z=1)
+    orc1 = oracle_mod.Oracle(ini, rank_pos=(0, 0, 1))
+    assert np.array_equal(U1, oracle_mod.init_problem(orc1.p, orc1.cfg))
+    # the two slabs are the two halves of the undecomposed 16x12x16 problem
+    whole = ppk.init_condition_from_ini(oracle_mod.make_ini("orszag_tang", (16, 12, 16), extra="[OrszagTang]\nkt=1\n"))
+    assert np.array_equal(U1[:, 3:-3, 3:-3, 3:-3], whole[:, 3 + 8:-3, 3:-3, 3:-3])
+
+
+def test_configmap_quirks():
+    ini = "[Run]\nTEND = 0.5 ; comment\nnstepmax=0x10\n[mesh]\nnx=8\nny=8\nnz=8\n# c\n[hydro]\nriemann=hlld\nproblem=FieldLoop\n"
+    p, t_end, nstep = ppk.params_from_ini("[run]\nsolver_name=MHD_Muscl_3D\n" + ini)
+    assert t_end == 0.5 and nstep == 16 and p.nx == 8
+    assert list(p.boundary_type) == [1] * 6  # default Dirichlet (HydroParams.cpp:145-156)
+
+
+def test_create_without_gpu_fails_loudly():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    p, _, _ = ppk.params_from_ini(str(np.load(f"{GOLDEN}/ot_16x12x8.npz")["ini"]))
+    with pytest.raises(ppk.PpkError):
+        ppk.Mhd3d(p)
