@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- Orszag-Tang 3-D fp64 MHD cell-updates/s (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 256] [--mode fast|exact]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU, z-slabs)
+  python bench.py --impl reference ...                                   (the reference on the host cores)
+
+A "step" is one full time step of the hot path (ghost fill / NCCL halo exchange, primitives + CFL
+reduction, edge E + face-B slopes, Hancock trace, HLLD fluxes x/y/z, edge EMFs z/y/x, conservative + CT
+update) over the rank's slab.  Workload at every N: Orszag-Tang 3-D with kt=1 (a genuinely 3-D flow),
+n^3 cells PER GPU (default 256^3 = BASELINE configs[1]; weak scaling: the domain grows along z with N).
+`value` counts interior cell-updates of all ranks per second with the state resident in HBM;
+`e2e` is the same metric through the C ABI with HOST buffers (pinned H2D of U before and D2H of U after
+every step inside the timed region).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Orszag-Tang 3D MHD fp64 Mcell-updates/s"
+UNIT = "Mcell-updates/s"
+ALGO_BYTES_PER_CELL = 128.0  # read 8 fp64 + write 8 fp64 per interior cell-update
+OT = "[OrszagTang]\nkt=1\n"
+
+
+def make_ini(n, mz, nstepmax, noutput=0):
+    """Orszag-Tang, kt=1, periodic, cubic cells, domain [0,1]x[0,1]x[0,mz]."""
+    bc = "\n".join(f"boundary_type_{f}=3" for f in ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax"))
+    return f"""[run]
+solver_name=MHD_Muscl_3D
+tEnd=1000000.0
+nStepmax={nstepmax}
+nOutput={noutput}
+nlog=1000000
+[mesh]
+nx={n}
+ny={n}
+nz={n}
+xmin=0.0
+xmax=1.0
+ymin=0.0
+ymax=1.0
+zmin=0.0
+zmax={float(mz)}
+{bc}
+[hydro]
+gamma0=1.666
+cfl=0.8
+niter_riemann=10
+iorder=2
+slope_type=2
+problem=orszag_tang
+riemann=hlld
+smallr=1e-8
+smallc=1e-8
+[mpi]
+mx=1
+my=1
+mz={mz}
+[output]
+outputPrefix=bench
+outputVtkAscii=false
+[other]
+implementationVersion=0
+{OT}"""
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the UNMODIFIED reference (oracle/_ref/ppkMHD) on the host cores
+# ---------------------------------------------------------------------------------------------
+def _run_ref_once(n, nsteps, threads):
+    from oracle import oracle as O
+
+    ini = make_ini(n, 1, nsteps)
+    if O.have_reference():
+        with tempfile.TemporaryDirectory() as tmp:
+            open(os.path.join(tmp, "run.ini"), "w").write(ini)
+            env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="spread", OMP_PLACES="threads")
+            out = subprocess.run([O.REF_BIN, "run.ini"], cwd=tmp, env=env, capture_output=True, text=True, check=True).stdout
+        return float(re.search(r"total\s+time\s*:\s*([0-9.]+)", out).group(1)), "reference"
+    # the reference did not travel: time the plain-C port (OpenMP) instead
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    orc = O.Oracle(ini)
+    t0 = time.time()
+    orc.run(nsteps)
+    return time.time() - t0, "port"
+
+
+def cpu_reference_throughput(n, steps, warmup, threads):
+    """interior Mcell-updates/s of the reference's own loop: (T(W+K) - T(W)) isolates K steps."""
+    t_w, kind = _run_ref_once(n, max(warmup, 1), threads)
+    t_wk, kind = _run_ref_once(n, max(warmup, 1) + steps, threads)
+    dt = max(t_wk - t_w, 1e-9)
+    return n ** 3 * steps / dt * 1e-6, kind, dt / steps
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.ref_n
+    steps = max(1, min(args.steps, 10))
+    warm = max(1, min(args.warmup, 2))
+    v, kind, spp = cpu_reference_throughput(n, steps, warm, threads)
+    sample = f"Orszag-Tang 3D kt=1 {n}^3, {steps} timed steps after {warm} warm-up steps (total-time difference of two runs), implementationVersion=0"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": spp * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": f"Orszag-Tang 3D kt=1 (bounded CPU sample {n}^3; GPU arm runs {args.n}^3 per GPU)",
+                                        "hlld": True, "implementationVersion": 0},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import ppkmhd_b200 as ppk
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, K, W = args.n, args.steps, max(args.warmup, 3)
+    exact = args.mode == "exact"
+
+    ini = make_ini(n, world, 10 ** 9)
+    p, t_end, _ = ppk.params_from_ini(ini, rank_z=rank, device=local, exact=exact)
+    solver = ppk.Mhd3d(p)
+    # a dedicated (non-default) torch stream: the C ABI launches on it, torch.cuda.Event records on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    solver.set_stream(stream.cuda_stream)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(ppk.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        solver.comm_init(bytes(idt.cpu().tolist()), world, rank)
+
+    # initial condition on the host (the reference's init functors use libm), pinned for the e2e leg
+    host = torch.empty(p.shape, dtype=torch.float64).pin_memory()
+    host.numpy()[...] = ppk.init_condition_from_ini(ini, rank_z=rank)
+    solver.upload(host.data_ptr())
+    solver.set_time(0.0, t_end, 0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident leg ------------------------------------------------------------------------
+    solver.run(W)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = solver.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    solver.run(K)
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = solver.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    cells = float(n) ** 3 * world
+    value = cells * K / (ms * 1e-3) * 1e-6
+    t_sim, dt_sim, it = solver.get_time()
+    sums, divb = solver.diagnostics()
+    if not np.all(np.isfinite(sums)):
+        raise SystemExit("non-finite state after the timed steps")
+
+    # ---- per-kernel timing (CUDA events around every launch, on the launch stream) ------------
+    solver.profile(True)
+    solver.kernel_times(reset=True)
+    PK = 3
+    solver.run(PK)
+    solver.synchronize()
+    kt = solver.kernel_times(reset=True)
+    solver.profile(False)
+    per_kernel = {k: {"ms_per_step": v[0] / PK, "launches_per_step": v[1] / PK} for k, v in kt.items() if v[1] > 0}
+    step_ms_prof = sum(v["ms_per_step"] for v in per_kernel.values())
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"] / max(per_kernel[k]["launches_per_step"], 1))
+    dom_ms = per_kernel[dom]["ms_per_step"] / per_kernel[dom]["launches_per_step"]
+    pk, pk_kind = peaks()
+    algo_bytes = ALGO_BYTES_PER_CELL * float(n) ** 3  # per launch: one launch sweeps the rank's n^3 cells
+    achieved = algo_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("kernel") == dom and tj.get("n") == n:
+            traffic = tj.get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind + " copy bandwidth",
+                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": dom_ms,
+                "whole_step": {"achieved": ALGO_BYTES_PER_CELL * cells / world * K / (ms * 1e-3) / 1e9,
+                               "frac": ALGO_BYTES_PER_CELL * cells / world * K / (ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
+                "note": "the path is FP64-pipe bound (see DESIGN.md / profiles): HBM fraction is low by construction"}
+
+    # ---- e2e leg: host buffers through the C ABI, H2D + step + D2H every step ------------------
+    Ke = max(2, min(K, args.e2e_steps))
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(Ke):
+        solver.upload(host.data_ptr())
+        solver.step()
+        solver.download(host.data_ptr())
+    f1.record(stream)
+    barrier()
+    ems = max_over_ranks(f0.elapsed_time(f1))
+    nbytes = int(np.prod(p.shape)) * 8
+    e2e = {"value": cells * Ke / (ems * 1e-3) * 1e-6, "unit": UNIT, "h2d_bytes_per_step": nbytes * world,
+           "d2h_bytes_per_step": nbytes * world, "steps": Ke,
+           "what": "ppk_mhd3d_upload(pinned host U) + ppk_mhd3d_step + ppk_mhd3d_download(host U) per step"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) -----------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, kind, spp = cpu_reference_throughput(args.ref_n, 6, 2, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"Orszag-Tang 3D kt=1 {args.ref_n}^3, 6 timed steps after 2 warm-up (difference of two runs of oracle/_ref/ppkMHD, "
+                         f"Kokkos-OpenMP, implementationVersion=0); {spp * 1e3:.0f} ms/step"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"Orszag-Tang 3D kt=1, {n}^3 cells per GPU (global {n}x{n}x{n * world}), z-slabs mz={world}, "
+                                   f"HLLD + CT, periodic, cfl 0.8, gamma 1.666, implementationVersion=0 semantics",
+                       "arithmetic": "fast (FMA contraction, within 1e-12 of the reference)" if not exact else "exact (--fmad=false, bit-identical)",
+                       "l2": "inputs larger than L2 (every array >= 1.1 GB vs 126 MB L2)",
+                       "cells_with_ghosts_per_gpu": int(np.prod(p.shape[1:])),
+                       "reference_style_value_with_ghosts": value * float(np.prod(p.shape[1:])) / float(n) ** 3},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "per_kernel_ms": {k: round(v["ms_per_step"], 4) for k, v in per_kernel.items()},
+            "profiled_step_ms": step_ms_prof,
+            "sim": {"t": t_sim, "dt": dt_sim, "iteration": it, "max_divB": divb, "device_GB": solver.device_bytes() / 1e9},
+        }
+        print(json.dumps(line))
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=256, help="cells per axis per GPU")
+    ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--ref-n", type=int, default=128, help="grid of the bounded CPU sample")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
