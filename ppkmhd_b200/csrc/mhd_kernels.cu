@@ -59,6 +59,116 @@ DEV double fast_speed_dir(double c2, double d2, double d, double n) {
   return sqrt(d2 + sqrt(d2 * d2 - c2 * n * n / d));
 }
 
+#if !PPK_EXACT
+// Fast-arithmetic variant of riemann_hlld (same algebra as RiemannSolvers_MHD.h:133-367, evaluated with
+// shared reciprocals: fp64 '/' and sqrt cost ~10 FP64-pipe instructions each and were 3/4 of the kernel).
+// 34 divisions+square roots become 15. Differences to the reference are a few ulp per operation, far
+// inside the 1e-12 per-cell tolerance (tests/test_gpu_parity.py::test_fast_mode_*).
+DEV void riemann_hlld_fast(double gamma0, double rl, double pl, double ul, double vl, double wl, double al, double bl,
+                           double cl, double rr, double pr, double ur, double vr, double wr, double ar, double br,
+                           double cr, double &f_d, double &f_p, double &f_u, double &f_v, double &f_w) {
+  const double entho = 1.0 / (gamma0 - 1.0);
+  const double a = 0.5 * (al + ar);
+  const double a2 = a * a;
+  const double sgnm = (a >= 0) ? 1.0 : -1.0;
+
+  const double ecinl = 0.5 * (ul * ul + vl * vl + wl * wl) * rl;
+  const double emagl = 0.5 * (a2 + bl * bl + cl * cl);
+  const double etotl = pl * entho + ecinl + emagl;
+  const double ptotl = pl + emagl;
+  const double vdotbl = ul * a + vl * bl + wl * cl;
+  const double ecinr = 0.5 * (ur * ur + vr * vr + wr * wr) * rr;
+  const double emagr = 0.5 * (a2 + br * br + cr * cr);
+  const double etotr = pr * entho + ecinr + emagr;
+  const double ptotr = pr + emagr;
+  const double vdotbr = ur * a + vr * br + wr * cr;
+
+  // fast magnetosonic speeds: max(sqrt(x),sqrt(y)) = sqrt(max(x,y))
+  const double irl = 1.0 / rl, irr = 1.0 / rr;
+  const double c2l = gamma0 * pl * irl, d2l = 0.5 * (2.0 * emagl * irl + c2l);
+  const double c2r = gamma0 * pr * irr, d2r = 0.5 * (2.0 * emagr * irr + c2r);
+  const double cf2l = d2l + sqrt(fmax(d2l * d2l - c2l * a2 * irl, 0.0));
+  const double cf2r = d2r + sqrt(fmax(d2r * d2r - c2r * a2 * irr, 0.0));
+  const double cfmax = sqrt(fmax(cf2l, cf2r));
+  const double sl = fmin(ul, ur) - cfmax;
+  const double sr = fmax(ul, ur) + cfmax;
+
+  const double rcl = rl * (ul - sl);
+  const double rcr = rr * (sr - ur);
+  const double irc = 1.0 / (rcr + rcl);
+  const double ustar = (rcr * ur + rcl * ul + (ptotl - ptotr)) * irc;
+  const double ptotstar = (rcr * ptotl + rcl * ptotr + rcl * rcr * (ul - ur)) * irc;
+
+  // left star region
+  const double isl = 1.0 / (sl - ustar);
+  const double rstarl = rl * (sl - ul) * isl;
+  double estar = rl * (sl - ul) * (sl - ustar) - a2;
+  const double el = rl * (sl - ul) * (sl - ul) - a2;
+  double vstarl, wstarl, bstarl, cstarl;
+  if (a2 > 0 && fabs(estar - a2) <= 1e-8 * a2) {  // |estar/a^2 - 1| <= 1e-8
+    vstarl = vl; bstarl = bl; wstarl = wl; cstarl = cl;
+  } else {
+    const double ie = 1.0 / estar;
+    const double k1 = a * (ustar - ul) * ie, k2 = el * ie;
+    vstarl = vl - bl * k1; bstarl = bl * k2;
+    wstarl = wl - cl * k1; cstarl = cl * k2;
+  }
+  const double vdotbstarl = ustar * a + vstarl * bstarl + wstarl * cstarl;
+  const double etotstarl = ((sl - ul) * etotl - ptotl * ul + ptotstar * ustar + a * (vdotbl - vdotbstarl)) * isl;
+  const double rsql = rsqrt(rstarl);
+  const double sqrrstarl = rstarl * rsql;
+  const double sal = ustar - fabs(a) * rsql;
+
+  // right star region
+  const double isr = 1.0 / (sr - ustar);
+  const double rstarr = rr * (sr - ur) * isr;
+  estar = rr * (sr - ur) * (sr - ustar) - a2;
+  const double er = rr * (sr - ur) * (sr - ur) - a2;
+  double vstarr, wstarr, bstarr, cstarr;
+  if (a2 > 0 && fabs(estar - a2) <= 1e-8 * a2) {
+    vstarr = vr; bstarr = br; wstarr = wr; cstarr = cr;
+  } else {
+    const double ie = 1.0 / estar;
+    const double k1 = a * (ustar - ur) * ie, k2 = er * ie;
+    vstarr = vr - br * k1; bstarr = br * k2;
+    wstarr = wr - cr * k1; cstarr = cr * k2;
+  }
+  const double vdotbstarr = ustar * a + vstarr * bstarr + wstarr * cstarr;
+  const double etotstarr = ((sr - ur) * etotr - ptotr * ur + ptotstar * ustar + a * (vdotbr - vdotbstarr)) * isr;
+  const double rsqr = rsqrt(rstarr);
+  const double sqrrstarr = rstarr * rsqr;
+  const double sar = ustar + fabs(a) * rsqr;
+
+  // sample the fan at x/t = 0 (the double-star state is only built when it is selected)
+  double ro, uo, vo, wo, bo, co, ptoto, etoto, vdotbo;
+  if (sl > 0) {
+    ro = rl; uo = ul; vo = vl; wo = wl; bo = bl; co = cl; ptoto = ptotl; etoto = etotl; vdotbo = vdotbl;
+  } else if (sal > 0) {
+    ro = rstarl; uo = ustar; vo = vstarl; wo = wstarl; bo = bstarl; co = cstarl; ptoto = ptotstar; etoto = etotstarl; vdotbo = vdotbstarl;
+  } else if (sar > 0) {
+    const double iss = 1.0 / (sqrrstarl + sqrrstarr);
+    const double ss = sgnm * sqrrstarl * sqrrstarr;
+    vo = (sqrrstarl * vstarl + sqrrstarr * vstarr + sgnm * (bstarr - bstarl)) * iss;
+    wo = (sqrrstarl * wstarl + sqrrstarr * wstarr + sgnm * (cstarr - cstarl)) * iss;
+    bo = (sqrrstarl * bstarr + sqrrstarr * bstarl + ss * (vstarr - vstarl)) * iss;
+    co = (sqrrstarl * cstarr + sqrrstarr * cstarl + ss * (wstarr - wstarl)) * iss;
+    vdotbo = ustar * a + vo * bo + wo * co;
+    uo = ustar; ptoto = ptotstar;
+    if (ustar > 0) { ro = rstarl; etoto = etotstarl - sgnm * sqrrstarl * (vdotbstarl - vdotbo); }
+    else { ro = rstarr; etoto = etotstarr + sgnm * sqrrstarr * (vdotbstarr - vdotbo); }
+  } else if (sr > 0) {
+    ro = rstarr; uo = ustar; vo = vstarr; wo = wstarr; bo = bstarr; co = cstarr; ptoto = ptotstar; etoto = etotstarr; vdotbo = vdotbstarr;
+  } else {
+    ro = rr; uo = ur; vo = vr; wo = wr; bo = br; co = cr; ptoto = ptotr; etoto = etotr; vdotbo = vdotbr;
+  }
+  f_d = ro * uo;
+  f_p = (etoto + ptoto) * uo - a * vdotbo;
+  f_u = ro * uo * uo - a2 + ptoto;
+  f_v = ro * uo * vo - a * bo;
+  f_w = ro * uo * wo - a * co;
+}
+#endif
+
 // riemann_hlld, RiemannSolvers_MHD.h:133-367. Inputs are in the frame of the face normal
 // (un,bn normal; t1,t2 transverse). Only the 5 hydro fluxes are produced: the induction part of
 // the reference's flux vector is never used (the field is advanced by the edge EMFs).
@@ -183,6 +293,90 @@ DEV double max5(double a0, double a1, double a2, double a3, double a4) {
 // One corner state of the 2-D magnetic Riemann problem: r,p, the two in-plane velocities and the
 // three field components in the (d1,d2,e) frame. (The out-of-plane velocity is never read.)
 struct Corner { double r, p, u, v, a, b, c; };
+
+#if !PPK_EXACT
+// Fast-arithmetic variant of mag_riemann2d_hlld (RiemannSolvers_MHD.h:398-630): identical algebra with
+//  * one reciprocal per distinct denominator (1/rho, 1/(S-ustar), 1/(S-vstar), 1/(SAR-SAL), 1/(SAT-SAB)),
+//  * max_i sqrt(x_i) evaluated as sqrt(max_i x_i) for the fast and Alfven speeds,
+//  * |Astar|/sqrt(rstar) = (|a|/sqrt(rstar_x)) * sqrt(gy) folded into the squared comparison,
+//  * the upwind selection as a branch.
+// 98 divisions + square roots become 34.
+struct CornerAux { double gx, gy, igx, igy; };
+DEV double mag_riemann2d_hlld_fast(double gamma0, double smallc, const Corner &LL, const Corner &RL, const Corner &LR,
+                                   const Corner &RR, double ELL, double ERL, double ELR, double ERR) {
+  const double iLL = 1.0 / LL.r, iLR = 1.0 / LR.r, iRL = 1.0 / RL.r, iRR = 1.0 / RR.r;
+  auto mag2 = [](const Corner &q) { return q.a * q.a + q.b * q.b + q.c * q.c; };
+  const double m2LL = mag2(LL), m2LR = mag2(LR), m2RL = mag2(RL), m2RR = mag2(RR);
+  // squared fast speeds along x (normal field a) and y (normal field b)
+  auto cf2 = [&](const Corner &q, double ir, double m2, double &cx2, double &cy2) {
+    const double c2 = gamma0 * q.p * ir;
+    const double d2 = 0.5 * (m2 * ir + c2);
+    const double dd = d2 * d2, k = c2 * ir;
+    cx2 = d2 + sqrt(fmax(dd - k * q.a * q.a, 0.0));
+    cy2 = d2 + sqrt(fmax(dd - k * q.b * q.b, 0.0));
+  };
+  double xLL, yLL, xLR, yLR, xRL, yRL, xRR, yRR;
+  cf2(LL, iLL, m2LL, xLL, yLL); cf2(LR, iLR, m2LR, xLR, yLR); cf2(RL, iRL, m2RL, xRL, yRL); cf2(RR, iRR, m2RR, xRR, yRR);
+  const double cxmax = sqrt(max4(xLL, xLR, xRL, xRR));
+  const double cymax = sqrt(max4(yLL, yLR, yRL, yRR));
+  const double SL = min4(LL.u, LR.u, RL.u, RR.u) - cxmax;
+  const double SR = max4(LL.u, LR.u, RL.u, RR.u) + cxmax;
+  const double SB = min4(LL.v, LR.v, RL.v, RR.v) - cymax;
+  const double ST = max4(LL.v, LR.v, RL.v, RR.v) + cymax;
+
+  const double PtotLL = LL.p + 0.5 * m2LL, PtotLR = LR.p + 0.5 * m2LR, PtotRL = RL.p + 0.5 * m2RL, PtotRR = RR.p + 0.5 * m2RR;
+  const double rcLLx = LL.r * (LL.u - SL), rcRLx = RL.r * (SR - RL.u), rcLRx = LR.r * (LR.u - SL), rcRRx = RR.r * (SR - RR.u);
+  const double rcLLy = LL.r * (LL.v - SB), rcLRy = LR.r * (ST - LR.v), rcRLy = RL.r * (RL.v - SB), rcRRy = RR.r * (ST - RR.v);
+  const double ustar = (rcLLx * LL.u + rcLRx * LR.u + rcRLx * RL.u + rcRRx * RR.u + (PtotLL - PtotRL + PtotLR - PtotRR)) /
+                       (rcLLx + rcLRx + rcRLx + rcRRx);
+  const double vstar = (rcLLy * LL.v + rcLRy * LR.v + rcRLy * RL.v + rcRRy * RR.v + (PtotLL - PtotLR + PtotRL - PtotRR)) /
+                       (rcLLy + rcLRy + rcRLy + rcRRy);
+
+  // compression factors g = (S - u)/(S - u*) of every corner in x and y, and their inverses
+  const double iSL = 1.0 / (SL - ustar), iSR = 1.0 / (SR - ustar), iSB = 1.0 / (SB - vstar), iST = 1.0 / (ST - vstar);
+  const double gxLL = (SL - LL.u) * iSL, gxLR = (SL - LR.u) * iSL, gxRL = (SR - RL.u) * iSR, gxRR = (SR - RR.u) * iSR;
+  const double gyLL = (SB - LL.v) * iSB, gyRL = (SB - RL.v) * iSB, gyLR = (ST - LR.v) * iST, gyRR = (ST - RR.v) * iST;
+  const double BstarLL = LL.b * gxLL, BstarLR = LR.b * gxLR, BstarRL = RL.b * gxRL, BstarRR = RR.b * gxRR;
+  const double AstarLL = LL.a * gyLL, AstarLR = LR.a * gyLR, AstarRL = RL.a * gyRL, AstarRR = RR.a * gyRR;
+
+  // squared Alfven speeds: a^2/rstar_x = a^2 /(r gx), Astar^2/rstar = (a^2/(r gx)) gy ; same for b with x<->y
+  const double axLL = LL.a * LL.a * iLL / gxLL, axLR = LR.a * LR.a * iLR / gxLR, axRL = RL.a * RL.a * iRL / gxRL, axRR = RR.a * RR.a * iRR / gxRR;
+  const double byLL = LL.b * LL.b * iLL / gyLL, byLR = LR.b * LR.b * iLR / gyLR, byRL = RL.b * RL.b * iRL / gyRL, byRR = RR.b * RR.b * iRR / gyRR;
+  const double sc2 = smallc * smallc;
+  const double calfvenL = sqrt(max5(axLR, axLR * gyLR, axLL, axLL * gyLL, sc2));
+  const double calfvenR = sqrt(max5(axRR, axRR * gyRR, axRL, axRL * gyRL, sc2));
+  const double calfvenB = sqrt(max5(byLL, byLL * gxLL, byRL, byRL * gxRL, sc2));
+  const double calfvenT = sqrt(max5(byLR, byLR * gxLR, byRR, byRR * gxRR, sc2));
+
+  const double SAL = fmin(ustar - calfvenL, 0.0);
+  const double SAR = fmax(ustar + calfvenR, 0.0);
+  const double SAB = fmin(vstar - calfvenB, 0.0);
+  const double SAT = fmax(vstar + calfvenT, 0.0);
+
+  const bool SB_pos = !signbit(SB), ST_pos = !signbit(ST), SL_pos = !signbit(SL), SR_pos = !signbit(SR);
+  if (SB_pos) {
+    if (SL_pos) return ELL;
+    if (!SR_pos) return ERL;
+    return (SAR * (ustar * BstarLL - LL.v * LL.a) - SAL * (ustar * BstarRL - RL.v * RL.a) + SAR * SAL * (RL.b - LL.b)) / (SAR - SAL);
+  }
+  if (!ST_pos) {
+    if (SL_pos) return ELR;
+    if (!SR_pos) return ERR;
+    return (SAR * (ustar * BstarLR - LR.v * LR.a) - SAL * (ustar * BstarRR - RR.v * RR.a) + SAR * SAL * (RR.b - LR.b)) / (SAR - SAL);
+  }
+  if (SL_pos) return (SAT * (LL.u * LL.b - vstar * AstarLL) - SAB * (LR.u * LR.b - vstar * AstarLR) - SAT * SAB * (LR.a - LL.a)) / (SAT - SAB);
+  if (!SR_pos) return (SAT * (RL.u * RL.b - vstar * AstarRL) - SAB * (RR.u * RR.b - vstar * AstarRR) - SAT * SAB * (RR.a - RL.a)) / (SAT - SAB);
+  const double iA = 1.0 / (SAR - SAL), iB = 1.0 / (SAT - SAB);
+  const double AstarT = (SAR * AstarRR - SAL * AstarLR) * iA;
+  const double AstarB = (SAR * AstarRL - SAL * AstarLL) * iA;
+  const double BstarR = (SAT * BstarRR - SAB * BstarRL) * iB;
+  const double BstarL = (SAT * BstarLR - SAB * BstarLL) * iB;
+  const double EstarLL = ustar * BstarLL - vstar * AstarLL, EstarLR = ustar * BstarLR - vstar * AstarLR;
+  const double EstarRL = ustar * BstarRL - vstar * AstarRL, EstarRR = ustar * BstarRR - vstar * AstarRR;
+  return (SAL * SAB * EstarRR - SAL * SAT * EstarRL - SAR * SAB * EstarLR + SAR * SAT * EstarLL) * iA * iB -
+         SAT * SAB * iB * (AstarT - AstarB) + SAR * SAL * iA * (BstarR - BstarL);
+}
+#endif
 
 // mag_riemann2d_hlld, RiemannSolvers_MHD.h:398-630
 DEV double mag_riemann2d_hlld(double gamma0, double smallc, const Corner &LL, const Corner &RL, const Corner &LR,
@@ -610,7 +804,11 @@ __global__ void __launch_bounds__(128) k_flux(const GridParams g, const double *
   const double b2r = BR_[(BQ + IA + T2) * N] - BR_[(SB + slope_b(D, T2)) * N];
 
   double fd, fp, fu, fv, fw;
+#if PPK_EXACT
   riemann_hlld(g.gamma0, rl, pl, unl, t1l, t2l, bnl, b1l, b2l, rr, pr, unr, t1r, t2r, bnr, b1r, b2r, fd, fp, fu, fv, fw);
+#else
+  riemann_hlld_fast(g.gamma0, rl, pl, unl, t1l, t2l, bnl, b1l, b2l, rr, pr, unr, t1r, t2r, bnr, b1r, b2r, fd, fp, fu, fv, fw);
+#endif
   double *Fo = F + cR;
   Fo[0 * N] = fd; Fo[1 * N] = fp; Fo[2 * N] = fu; Fo[3 * N] = fv; Fo[4 * N] = fw;
 }
@@ -690,7 +888,11 @@ __global__ void __launch_bounds__(128) k_emf(const GridParams g, const double *_
   const double ERL = RL.u * RL.b - RL.v * RL.a;
   const double ELR = LR.u * LR.b - LR.v * LR.a;
   const double ERR = RR.u * RR.b - RR.v * RR.a;
+#if PPK_EXACT
   EMF[c + (2 - E) * N] = mag_riemann2d_hlld(g.gamma0, g.smallc, LL, RL, LR, RR, ELL, ERL, ELR, ERR);
+#else
+  EMF[c + (2 - E) * N] = mag_riemann2d_hlld_fast(g.gamma0, g.smallc, LL, RL, LR, RR, ELL, ERL, ELR, ERR);
+#endif
 }
 
 // Kokkos::deep_copy(data_out, data_in) (SolverMHDMuscl.cpp:477) + UpdateFunctor3D_MHD
