@@ -110,6 +110,22 @@ int ppk_mhd3d_diagnostics(ppk_mhd3d *handle, double sums[8], double *max_divb);
 int ppk_nccl_get_unique_id(void *unique_id_128_bytes);
 int ppk_mhd3d_comm_init(ppk_mhd3d *handle, const void *unique_id_128_bytes, int nranks, int rank);
 
+/* The message list of one z-halo exchange for the slab described by `params` (pure host function, no GPU,
+ * no handle): offsets are in doubles from the start of the conservative array; `count` doubles each.
+ * These are the offsets of CopyDataArray_To_BorderBuf<ZMIN/ZMAX> / CopyBorderBuf_To_DataArray
+ * (mpiBorderUtils.h:117-123, 286-292) expressed on the array itself: send k in [gw,2gw) down and
+ * k in [nz,nz+gw) up, receive into k in [nz+gw,nz+2gw) and [0,gw). Returns the number of messages
+ * (0 for mz == 1; faces with a physical, non-periodic BC are not exchanged) or -1 on bad arguments;
+ * at most `capacity` entries are written. The engine posts exactly this list inside one NCCL group. */
+typedef struct ppk_halo_msg {
+  int peer;           /* rank_z of the neighbour slab */
+  int is_send;        /* 1: send, 0: receive */
+  int var;            /* variable plane 0..7 */
+  long long offset;   /* in doubles from U[0] */
+  long long count;    /* doubles */
+} ppk_halo_msg;
+int ppk_mhd3d_halo_plan(const ppk_mhd3d_params *params, int capacity, ppk_halo_msg *msgs);
+
 /* ---- plumbing ----------------------------------------------------------------------------- */
 /* Run on a caller-owned stream (a cudaStream_t, e.g. torch's current stream) instead of the
  * handle's own non-blocking stream. */
@@ -127,6 +143,10 @@ long ppk_mhd3d_launch_count(ppk_mhd3d *handle);
 int ppk_mhd3d_debug_array(ppk_mhd3d *handle, const char *name, double *host_out, int *ncomp);
 /* Bytes of device memory held by the handle. */
 long long ppk_mhd3d_device_bytes(ppk_mhd3d *handle);
+
+/* Evaluate the fast build's reciprocal / sqrt / rsqrt primitives (MUFU seed + one cubic Newton step) on n
+ * host values (device 0 / current device); tests compare them with IEEE results (<= 2 ulp). */
+int ppk_selftest_fastmath(int n, const double *x_host, double *rcp_out, double *sqrt_out, double *rsqrt_out);
 
 const char *ppk_last_error_string(void);
 const char *ppk_version_string(void);

@@ -7,6 +7,8 @@ from .capi import (  # noqa: F401
     Params,
     PpkError,
     build_library,
+    halo_plan,
+    selftest_fastmath,
     init_condition_from_ini,
     lib_path,
     load_library,
@@ -16,5 +18,5 @@ from .capi import (  # noqa: F401
 
 __all__ = [
     "Mhd3d", "Params", "PpkError", "lib_path", "load_library", "build_library",
-    "params_from_ini", "init_condition_from_ini", "nccl_unique_id",
+    "params_from_ini", "init_condition_from_ini", "nccl_unique_id", "halo_plan", "selftest_fastmath",
 ]

@@ -48,6 +48,12 @@ class Params(C.Structure):
         return (8, self.nz + 6, self.ny + 6, self.nx + 6)
 
 
+class HaloMsg(C.Structure):
+    """struct ppk_halo_msg"""
+
+    _fields_ = [("peer", C.c_int), ("is_send", C.c_int), ("var", C.c_int), ("offset", C.c_longlong), ("count", C.c_longlong)]
+
+
 _lib = None
 
 # every symbol include/*.h declares (tests/test_abi.py checks the library exports them all)
@@ -57,6 +63,7 @@ EXPORTS = [
     "ppk_mhd3d_synchronize", "ppk_mhd3d_diagnostics", "ppk_nccl_get_unique_id", "ppk_mhd3d_comm_init",
     "ppk_mhd3d_set_stream", "ppk_mhd3d_profile", "ppk_mhd3d_kernel_times", "ppk_mhd3d_launch_count",
     "ppk_mhd3d_debug_array", "ppk_mhd3d_device_bytes", "ppk_last_error_string", "ppk_version_string",
+    "ppk_mhd3d_halo_plan", "ppk_selftest_fastmath",
     "ppk_params_from_ini", "ppk_init_condition_from_ini", "ppk_run_ini",
 ]
 
@@ -93,6 +100,8 @@ def load_library():
     L.ppk_mhd3d_debug_array.argtypes = [vp, C.c_char_p, vp, ip]
     L.ppk_mhd3d_device_bytes.argtypes = [vp]
     L.ppk_mhd3d_device_bytes.restype = C.c_longlong
+    L.ppk_mhd3d_halo_plan.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(HaloMsg)]
+    L.ppk_selftest_fastmath.argtypes = [C.c_int, vp, vp, vp, vp]
     L.ppk_last_error_string.restype = C.c_char_p
     L.ppk_version_string.restype = C.c_char_p
     L.ppk_params_from_ini.argtypes = [C.c_char_p, C.c_int, C.POINTER(Params), dp, ip]
@@ -235,6 +244,23 @@ class Mhd3d:
         out = np.empty((nc.value,) + self.shape[1:], dtype=np.float64)
         _check(self.L.ppk_mhd3d_debug_array(self.h, name.encode(), out.ctypes.data, C.byref(nc)))
         return out
+
+
+def halo_plan(params: Params):
+    """ppk_mhd3d_halo_plan: list of (peer, is_send, var, offset, count) of one z-halo exchange."""
+    L = load_library()
+    msgs = (HaloMsg * 32)()
+    n = L.ppk_mhd3d_halo_plan(C.byref(params), 32, msgs)
+    if n < 0:
+        raise PpkError("ppk_mhd3d_halo_plan: bad arguments")
+    return [(m.peer, bool(m.is_send), m.var, m.offset, m.count) for m in msgs[:n]]
+
+
+def selftest_fastmath(x: np.ndarray):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = [np.empty_like(x) for _ in range(3)]
+    _check(load_library().ppk_selftest_fastmath(x.size, x.ctypes.data, *(o.ctypes.data for o in out)))
+    return out
 
 
 def nccl_unique_id() -> bytes:

@@ -191,18 +191,16 @@ int alloc_doubles(ppk_mhd3d *h, double **p, long long n) {
 // z ghost planes through NCCL: replaces CopyDataArray_To_BorderBuf + MPI_Sendrecv + CopyBorderBuf_To_DataArray
 // (SolverBase.cpp:842-925, mpiBorderUtils.h:36-330). In the (i fastest, variable slowest) layout the 3 ghost
 // planes of one variable are contiguous, so no pack/unpack kernel exists: 8 sends + 8 receives per face.
+// The message list is ppk_mhd3d_halo_plan (a pure host function, also driven over gloo by the CPU tests).
 int halo_exchange_z(ppk_mhd3d *h, double *U, cudaStream_t s) {
-  const GridParams &g = h->g;
-  const size_t plane = (size_t)g.isize * g.jsize;
-  const size_t cnt = plane * g.gw;
+  ppk_halo_msg msgs[4 * NBVAR];
+  const int n = ppk_mhd3d_halo_plan(&h->params, 4 * NBVAR, msgs);
+  if (n < 0) return fail(PPK_ERR_STATE, "halo plan failed");
   Scope sc(h, KK_HALO, s);
   NCCL_TRY(g_nccl.GroupStart());
-  for (int v = 0; v < NBVAR; ++v) {
-    double *base = U + (size_t)v * g.ncell;
-    if (h->exch_lo) NCCL_TRY(g_nccl.Send(base + plane * g.gw, cnt, ncclDouble, h->zlo, h->comm, s));
-    if (h->exch_hi) NCCL_TRY(g_nccl.Recv(base + plane * (g.nz + g.gw), cnt, ncclDouble, h->zhi, h->comm, s));
-    if (h->exch_hi) NCCL_TRY(g_nccl.Send(base + plane * g.nz, cnt, ncclDouble, h->zhi, h->comm, s));
-    if (h->exch_lo) NCCL_TRY(g_nccl.Recv(base, cnt, ncclDouble, h->zlo, h->comm, s));
+  for (int m = 0; m < n; ++m) {
+    if (msgs[m].is_send) NCCL_TRY(g_nccl.Send(U + msgs[m].offset, (size_t)msgs[m].count, ncclDouble, msgs[m].peer, h->comm, s));
+    else NCCL_TRY(g_nccl.Recv(U + msgs[m].offset, (size_t)msgs[m].count, ncclDouble, msgs[m].peer, h->comm, s));
   }
   NCCL_TRY(g_nccl.GroupEnd());
   return 0;
@@ -300,6 +298,7 @@ int ppk_mhd3d_create(const ppk_mhd3d_params *p, ppk_mhd3d **out) {
   g.isize = p->nx + 2 * g.gw; g.jsize = p->ny + 2 * g.gw; g.ksize = p->nz + 2 * g.gw;
   g.ncell = (long long)g.isize * g.jsize * g.ksize;
   g.dx = p->dx; g.dy = p->dy; g.dz = p->dz;
+  g.idx = 1.0 / p->dx; g.idy = 1.0 / p->dy; g.idz = 1.0 / p->dz;
   g.gamma0 = p->gamma0; g.cfl = p->cfl; g.slope_type = p->slope_type;
   g.smallr = p->smallr; g.smallc = p->smallc; g.smallp = p->smallp;
   for (int f = 0; f < 6; ++f) g.bc[f] = p->boundary_type[f];
@@ -448,6 +447,45 @@ int ppk_mhd3d_diagnostics(ppk_mhd3d *h, double sums[8], double *max_divb) {
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   if (sums) memcpy(sums, out, 8 * sizeof(double));
   if (max_divb) *max_divb = out[8];
+  return 0;
+}
+
+int ppk_mhd3d_halo_plan(const ppk_mhd3d_params *p, int capacity, ppk_halo_msg *msgs) {
+  if (!p || (capacity > 0 && !msgs)) return -1;
+  if (p->mz <= 1) return 0;
+  const long long gw = p->ghost_width;
+  const long long isize = p->nx + 2 * gw, jsize = p->ny + 2 * gw, ksize = p->nz + 2 * gw;
+  const long long plane = isize * jsize, ncell = plane * ksize, cnt = plane * gw;
+  const bool lo_outer = p->rank_z == 0, hi_outer = p->rank_z == p->mz - 1;
+  const bool exch_lo = !lo_outer || p->boundary_type[4] == PPK_BC_PERIODIC;
+  const bool exch_hi = !hi_outer || p->boundary_type[5] == PPK_BC_PERIODIC;
+  const int zlo = (p->rank_z - 1 + p->mz) % p->mz, zhi = (p->rank_z + 1) % p->mz;
+  int n = 0;
+  auto add = [&](int peer, int is_send, int var, long long off) {
+    if (n < capacity) msgs[n] = ppk_halo_msg{peer, is_send, var, var * ncell + off, cnt};
+    ++n;
+  };
+  for (int v = 0; v < PPK_NBVAR; ++v) {
+    // same order on every rank: (send down, recv from up, send up, recv from down) per variable
+    if (exch_lo) add(zlo, 1, v, plane * gw);              // first interior planes k in [gw, 2gw) go down
+    if (exch_hi) add(zhi, 0, v, plane * (p->nz + gw));    // upper ghost planes k in [nz+gw, nz+2gw)
+    if (exch_hi) add(zhi, 1, v, plane * p->nz);           // last interior planes k in [nz, nz+gw) go up
+    if (exch_lo) add(zlo, 0, v, 0);                       // lower ghost planes k in [0, gw)
+  }
+  return n;
+}
+
+int ppk_selftest_fastmath(int n, const double *x_host, double *rcp_out, double *sqrt_out, double *rsqrt_out) {
+  if (n <= 0 || !x_host || !rcp_out || !sqrt_out || !rsqrt_out) return fail(PPK_ERR_INVALID_ARGUMENT, "bad argument");
+  double *d = nullptr;
+  CUDA_TRY(cudaMalloc((void **)&d, (size_t)4 * n * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(d, x_host, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+  kernel_table_fast()->fastmath_selftest(n, d, d + n, d + 2 * (size_t)n, d + 3 * (size_t)n, nullptr);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(rcp_out, d + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(sqrt_out, d + 2 * (size_t)n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(rsqrt_out, d + 3 * (size_t)n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaFree(d));
   return 0;
 }
 

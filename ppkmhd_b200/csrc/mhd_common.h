@@ -29,6 +29,7 @@ struct GridParams {
   int isize, jsize, ksize;
   long long ncell;  // isize*jsize*ksize
   double dx, dy, dz;
+  double idx, idy, idz;  // 1/dx, 1/dy, 1/dz (fast-arithmetic build only)
   double gamma0, cfl, slope_type, smallr, smallc, smallp;
   int bc[6];  // effective BC of this slab's faces (BC_COPY on faces owned by the halo exchange)
 };
@@ -38,6 +39,7 @@ struct StepState {
   double t;
   double t_end;
   double dt;
+  double dtdx, dtdy, dtdz;         // dt/dx, dt/dy, dt/dz of the current step (SolverMHDMuscl.cpp:490-492)
   unsigned long long inv_dt_bits;  // max over cells of sum_d (c_f,d + |v_d|)/dx_d as ordered bits
   long long iteration;
 };
@@ -63,6 +65,7 @@ struct KernelTable {
   void (*update)(const GridParams &g, const StepState *st, const double *Uin, double *Uout, const double *Fx,
                  const double *Fy, const double *Fz, const double *EMF, cudaStream_t s);
   void (*diagnostics)(const GridParams &g, const double *U, double *out9, cudaStream_t s);
+  void (*fastmath_selftest)(int n, const double *x, double *rcp, double *sq, double *rsq, cudaStream_t s);
 };
 
 const KernelTable *kernel_table_exact();

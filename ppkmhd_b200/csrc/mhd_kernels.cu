@@ -60,6 +60,29 @@ DEV double fast_speed_dir(double c2, double d2, double d, double n) {
 }
 
 #if !PPK_EXACT
+// ---- fast-arithmetic primitives ---------------------------------------------------------------------
+// nvcc expands an fp64 '/' or sqrt() into MUFU seed + Newton steps + a guarded slow path (~10-14 FP64-pipe
+// instructions, a branch and a CALL). The physical quantities here are normal, finite and non-zero, so the
+// fast build uses the 20-bit MUFU seed followed by ONE cubically convergent step (error e -> e^3 = 2^-60,
+// i.e. the result is within ~1 ulp): 1 MUFU + 3 (rcp) or 5 (rsqrt) FP64 instructions, no branch.
+DEV double frcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(y, t, y);
+}
+DEV double frsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double t = x * y;
+  const double e = fma(-t, y, 1.0);           // 1 - x y^2
+  const double p = fma(e, 0.375, 0.5) * e;    // e/2 + 3 e^2/8
+  return fma(y, p, y);
+}
+// sqrt for x >= 0 (x == 0 must give 0: the clamped discriminant of the fast speed can vanish)
+DEV double fsqrt(double x) { return x * frsqrt(fmax(x, 1e-300)); }
+
 // Fast-arithmetic variant of riemann_hlld (same algebra as RiemannSolvers_MHD.h:133-367, evaluated with
 // shared reciprocals: fp64 '/' and sqrt cost ~10 FP64-pipe instructions each and were 3/4 of the kernel).
 // 34 divisions+square roots become 15. Differences to the reference are a few ulp per operation, far
@@ -67,7 +90,7 @@ DEV double fast_speed_dir(double c2, double d2, double d, double n) {
 DEV void riemann_hlld_fast(double gamma0, double rl, double pl, double ul, double vl, double wl, double al, double bl,
                            double cl, double rr, double pr, double ur, double vr, double wr, double ar, double br,
                            double cr, double &f_d, double &f_p, double &f_u, double &f_v, double &f_w) {
-  const double entho = 1.0 / (gamma0 - 1.0);
+  const double entho = frcp(gamma0 - 1.0);
   const double a = 0.5 * (al + ar);
   const double a2 = a * a;
   const double sgnm = (a >= 0) ? 1.0 : -1.0;
@@ -83,24 +106,24 @@ DEV void riemann_hlld_fast(double gamma0, double rl, double pl, double ul, doubl
   const double ptotr = pr + emagr;
   const double vdotbr = ur * a + vr * br + wr * cr;
 
-  // fast magnetosonic speeds: max(sqrt(x),sqrt(y)) = sqrt(max(x,y))
-  const double irl = 1.0 / rl, irr = 1.0 / rr;
+  // fast magnetosonic speeds: max(fsqrt(x),fsqrt(y)) = fsqrt(max(x,y))
+  const double irl = frcp(rl), irr = frcp(rr);
   const double c2l = gamma0 * pl * irl, d2l = 0.5 * (2.0 * emagl * irl + c2l);
   const double c2r = gamma0 * pr * irr, d2r = 0.5 * (2.0 * emagr * irr + c2r);
-  const double cf2l = d2l + sqrt(fmax(d2l * d2l - c2l * a2 * irl, 0.0));
-  const double cf2r = d2r + sqrt(fmax(d2r * d2r - c2r * a2 * irr, 0.0));
-  const double cfmax = sqrt(fmax(cf2l, cf2r));
+  const double cf2l = d2l + fsqrt(fmax(d2l * d2l - c2l * a2 * irl, 0.0));
+  const double cf2r = d2r + fsqrt(fmax(d2r * d2r - c2r * a2 * irr, 0.0));
+  const double cfmax = fsqrt(fmax(cf2l, cf2r));
   const double sl = fmin(ul, ur) - cfmax;
   const double sr = fmax(ul, ur) + cfmax;
 
   const double rcl = rl * (ul - sl);
   const double rcr = rr * (sr - ur);
-  const double irc = 1.0 / (rcr + rcl);
+  const double irc = frcp(rcr + rcl);
   const double ustar = (rcr * ur + rcl * ul + (ptotl - ptotr)) * irc;
   const double ptotstar = (rcr * ptotl + rcl * ptotr + rcl * rcr * (ul - ur)) * irc;
 
   // left star region
-  const double isl = 1.0 / (sl - ustar);
+  const double isl = frcp(sl - ustar);
   const double rstarl = rl * (sl - ul) * isl;
   double estar = rl * (sl - ul) * (sl - ustar) - a2;
   const double el = rl * (sl - ul) * (sl - ul) - a2;
@@ -108,19 +131,19 @@ DEV void riemann_hlld_fast(double gamma0, double rl, double pl, double ul, doubl
   if (a2 > 0 && fabs(estar - a2) <= 1e-8 * a2) {  // |estar/a^2 - 1| <= 1e-8
     vstarl = vl; bstarl = bl; wstarl = wl; cstarl = cl;
   } else {
-    const double ie = 1.0 / estar;
+    const double ie = frcp(estar);
     const double k1 = a * (ustar - ul) * ie, k2 = el * ie;
     vstarl = vl - bl * k1; bstarl = bl * k2;
     wstarl = wl - cl * k1; cstarl = cl * k2;
   }
   const double vdotbstarl = ustar * a + vstarl * bstarl + wstarl * cstarl;
   const double etotstarl = ((sl - ul) * etotl - ptotl * ul + ptotstar * ustar + a * (vdotbl - vdotbstarl)) * isl;
-  const double rsql = rsqrt(rstarl);
+  const double rsql = frsqrt(rstarl);
   const double sqrrstarl = rstarl * rsql;
   const double sal = ustar - fabs(a) * rsql;
 
   // right star region
-  const double isr = 1.0 / (sr - ustar);
+  const double isr = frcp(sr - ustar);
   const double rstarr = rr * (sr - ur) * isr;
   estar = rr * (sr - ur) * (sr - ustar) - a2;
   const double er = rr * (sr - ur) * (sr - ur) - a2;
@@ -128,14 +151,14 @@ DEV void riemann_hlld_fast(double gamma0, double rl, double pl, double ul, doubl
   if (a2 > 0 && fabs(estar - a2) <= 1e-8 * a2) {
     vstarr = vr; bstarr = br; wstarr = wr; cstarr = cr;
   } else {
-    const double ie = 1.0 / estar;
+    const double ie = frcp(estar);
     const double k1 = a * (ustar - ur) * ie, k2 = er * ie;
     vstarr = vr - br * k1; bstarr = br * k2;
     wstarr = wr - cr * k1; cstarr = cr * k2;
   }
   const double vdotbstarr = ustar * a + vstarr * bstarr + wstarr * cstarr;
   const double etotstarr = ((sr - ur) * etotr - ptotr * ur + ptotstar * ustar + a * (vdotbr - vdotbstarr)) * isr;
-  const double rsqr = rsqrt(rstarr);
+  const double rsqr = frsqrt(rstarr);
   const double sqrrstarr = rstarr * rsqr;
   const double sar = ustar + fabs(a) * rsqr;
 
@@ -146,7 +169,7 @@ DEV void riemann_hlld_fast(double gamma0, double rl, double pl, double ul, doubl
   } else if (sal > 0) {
     ro = rstarl; uo = ustar; vo = vstarl; wo = wstarl; bo = bstarl; co = cstarl; ptoto = ptotstar; etoto = etotstarl; vdotbo = vdotbstarl;
   } else if (sar > 0) {
-    const double iss = 1.0 / (sqrrstarl + sqrrstarr);
+    const double iss = frcp(sqrrstarl + sqrrstarr);
     const double ss = sgnm * sqrrstarl * sqrrstarr;
     vo = (sqrrstarl * vstarl + sqrrstarr * vstarr + sgnm * (bstarr - bstarl)) * iss;
     wo = (sqrrstarl * wstarl + sqrrstarr * wstarr + sgnm * (cstarr - cstarl)) * iss;
@@ -304,7 +327,7 @@ struct Corner { double r, p, u, v, a, b, c; };
 struct CornerAux { double gx, gy, igx, igy; };
 DEV double mag_riemann2d_hlld_fast(double gamma0, double smallc, const Corner &LL, const Corner &RL, const Corner &LR,
                                    const Corner &RR, double ELL, double ERL, double ELR, double ERR) {
-  const double iLL = 1.0 / LL.r, iLR = 1.0 / LR.r, iRL = 1.0 / RL.r, iRR = 1.0 / RR.r;
+  const double iLL = frcp(LL.r), iLR = frcp(LR.r), iRL = frcp(RL.r), iRR = frcp(RR.r);
   auto mag2 = [](const Corner &q) { return q.a * q.a + q.b * q.b + q.c * q.c; };
   const double m2LL = mag2(LL), m2LR = mag2(LR), m2RL = mag2(RL), m2RR = mag2(RR);
   // squared fast speeds along x (normal field a) and y (normal field b)
@@ -312,13 +335,13 @@ DEV double mag_riemann2d_hlld_fast(double gamma0, double smallc, const Corner &L
     const double c2 = gamma0 * q.p * ir;
     const double d2 = 0.5 * (m2 * ir + c2);
     const double dd = d2 * d2, k = c2 * ir;
-    cx2 = d2 + sqrt(fmax(dd - k * q.a * q.a, 0.0));
-    cy2 = d2 + sqrt(fmax(dd - k * q.b * q.b, 0.0));
+    cx2 = d2 + fsqrt(fmax(dd - k * q.a * q.a, 0.0));
+    cy2 = d2 + fsqrt(fmax(dd - k * q.b * q.b, 0.0));
   };
   double xLL, yLL, xLR, yLR, xRL, yRL, xRR, yRR;
   cf2(LL, iLL, m2LL, xLL, yLL); cf2(LR, iLR, m2LR, xLR, yLR); cf2(RL, iRL, m2RL, xRL, yRL); cf2(RR, iRR, m2RR, xRR, yRR);
-  const double cxmax = sqrt(max4(xLL, xLR, xRL, xRR));
-  const double cymax = sqrt(max4(yLL, yLR, yRL, yRR));
+  const double cxmax = fsqrt(max4(xLL, xLR, xRL, xRR));
+  const double cymax = fsqrt(max4(yLL, yLR, yRL, yRR));
   const double SL = min4(LL.u, LR.u, RL.u, RR.u) - cxmax;
   const double SR = max4(LL.u, LR.u, RL.u, RR.u) + cxmax;
   const double SB = min4(LL.v, LR.v, RL.v, RR.v) - cymax;
@@ -327,26 +350,28 @@ DEV double mag_riemann2d_hlld_fast(double gamma0, double smallc, const Corner &L
   const double PtotLL = LL.p + 0.5 * m2LL, PtotLR = LR.p + 0.5 * m2LR, PtotRL = RL.p + 0.5 * m2RL, PtotRR = RR.p + 0.5 * m2RR;
   const double rcLLx = LL.r * (LL.u - SL), rcRLx = RL.r * (SR - RL.u), rcLRx = LR.r * (LR.u - SL), rcRRx = RR.r * (SR - RR.u);
   const double rcLLy = LL.r * (LL.v - SB), rcLRy = LR.r * (ST - LR.v), rcRLy = RL.r * (RL.v - SB), rcRRy = RR.r * (ST - RR.v);
-  const double ustar = (rcLLx * LL.u + rcLRx * LR.u + rcRLx * RL.u + rcRRx * RR.u + (PtotLL - PtotRL + PtotLR - PtotRR)) /
-                       (rcLLx + rcLRx + rcRLx + rcRRx);
-  const double vstar = (rcLLy * LL.v + rcLRy * LR.v + rcRLy * RL.v + rcRRy * RR.v + (PtotLL - PtotLR + PtotRL - PtotRR)) /
-                       (rcLLy + rcLRy + rcRLy + rcRRy);
+  const double ustar = (rcLLx * LL.u + rcLRx * LR.u + rcRLx * RL.u + rcRRx * RR.u + (PtotLL - PtotRL + PtotLR - PtotRR)) *
+                       frcp(rcLLx + rcLRx + rcRLx + rcRRx);
+  const double vstar = (rcLLy * LL.v + rcLRy * LR.v + rcRLy * RL.v + rcRRy * RR.v + (PtotLL - PtotLR + PtotRL - PtotRR)) *
+                       frcp(rcLLy + rcLRy + rcRLy + rcRRy);
 
   // compression factors g = (S - u)/(S - u*) of every corner in x and y, and their inverses
-  const double iSL = 1.0 / (SL - ustar), iSR = 1.0 / (SR - ustar), iSB = 1.0 / (SB - vstar), iST = 1.0 / (ST - vstar);
+  const double iSL = frcp(SL - ustar), iSR = frcp(SR - ustar), iSB = frcp(SB - vstar), iST = frcp(ST - vstar);
   const double gxLL = (SL - LL.u) * iSL, gxLR = (SL - LR.u) * iSL, gxRL = (SR - RL.u) * iSR, gxRR = (SR - RR.u) * iSR;
   const double gyLL = (SB - LL.v) * iSB, gyRL = (SB - RL.v) * iSB, gyLR = (ST - LR.v) * iST, gyRR = (ST - RR.v) * iST;
   const double BstarLL = LL.b * gxLL, BstarLR = LR.b * gxLR, BstarRL = RL.b * gxRL, BstarRR = RR.b * gxRR;
   const double AstarLL = LL.a * gyLL, AstarLR = LR.a * gyLR, AstarRL = RL.a * gyRL, AstarRR = RR.a * gyRR;
 
   // squared Alfven speeds: a^2/rstar_x = a^2 /(r gx), Astar^2/rstar = (a^2/(r gx)) gy ; same for b with x<->y
-  const double axLL = LL.a * LL.a * iLL / gxLL, axLR = LR.a * LR.a * iLR / gxLR, axRL = RL.a * RL.a * iRL / gxRL, axRR = RR.a * RR.a * iRR / gxRR;
-  const double byLL = LL.b * LL.b * iLL / gyLL, byLR = LR.b * LR.b * iLR / gyLR, byRL = RL.b * RL.b * iRL / gyRL, byRR = RR.b * RR.b * iRR / gyRR;
+  const double axLL = LL.a * LL.a * iLL * frcp(gxLL), axLR = LR.a * LR.a * iLR * frcp(gxLR);
+  const double axRL = RL.a * RL.a * iRL * frcp(gxRL), axRR = RR.a * RR.a * iRR * frcp(gxRR);
+  const double byLL = LL.b * LL.b * iLL * frcp(gyLL), byLR = LR.b * LR.b * iLR * frcp(gyLR);
+  const double byRL = RL.b * RL.b * iRL * frcp(gyRL), byRR = RR.b * RR.b * iRR * frcp(gyRR);
   const double sc2 = smallc * smallc;
-  const double calfvenL = sqrt(max5(axLR, axLR * gyLR, axLL, axLL * gyLL, sc2));
-  const double calfvenR = sqrt(max5(axRR, axRR * gyRR, axRL, axRL * gyRL, sc2));
-  const double calfvenB = sqrt(max5(byLL, byLL * gxLL, byRL, byRL * gxRL, sc2));
-  const double calfvenT = sqrt(max5(byLR, byLR * gxLR, byRR, byRR * gxRR, sc2));
+  const double calfvenL = fsqrt(max5(axLR, axLR * gyLR, axLL, axLL * gyLL, sc2));
+  const double calfvenR = fsqrt(max5(axRR, axRR * gyRR, axRL, axRL * gyRL, sc2));
+  const double calfvenB = fsqrt(max5(byLL, byLL * gxLL, byRL, byRL * gxRL, sc2));
+  const double calfvenT = fsqrt(max5(byLR, byLR * gxLR, byRR, byRR * gxRR, sc2));
 
   const double SAL = fmin(ustar - calfvenL, 0.0);
   const double SAR = fmax(ustar + calfvenR, 0.0);
@@ -357,16 +382,16 @@ DEV double mag_riemann2d_hlld_fast(double gamma0, double smallc, const Corner &L
   if (SB_pos) {
     if (SL_pos) return ELL;
     if (!SR_pos) return ERL;
-    return (SAR * (ustar * BstarLL - LL.v * LL.a) - SAL * (ustar * BstarRL - RL.v * RL.a) + SAR * SAL * (RL.b - LL.b)) / (SAR - SAL);
+    return (SAR * (ustar * BstarLL - LL.v * LL.a) - SAL * (ustar * BstarRL - RL.v * RL.a) + SAR * SAL * (RL.b - LL.b)) * frcp(SAR - SAL);
   }
   if (!ST_pos) {
     if (SL_pos) return ELR;
     if (!SR_pos) return ERR;
-    return (SAR * (ustar * BstarLR - LR.v * LR.a) - SAL * (ustar * BstarRR - RR.v * RR.a) + SAR * SAL * (RR.b - LR.b)) / (SAR - SAL);
+    return (SAR * (ustar * BstarLR - LR.v * LR.a) - SAL * (ustar * BstarRR - RR.v * RR.a) + SAR * SAL * (RR.b - LR.b)) * frcp(SAR - SAL);
   }
-  if (SL_pos) return (SAT * (LL.u * LL.b - vstar * AstarLL) - SAB * (LR.u * LR.b - vstar * AstarLR) - SAT * SAB * (LR.a - LL.a)) / (SAT - SAB);
-  if (!SR_pos) return (SAT * (RL.u * RL.b - vstar * AstarRL) - SAB * (RR.u * RR.b - vstar * AstarRR) - SAT * SAB * (RR.a - RL.a)) / (SAT - SAB);
-  const double iA = 1.0 / (SAR - SAL), iB = 1.0 / (SAT - SAB);
+  if (SL_pos) return (SAT * (LL.u * LL.b - vstar * AstarLL) - SAB * (LR.u * LR.b - vstar * AstarLR) - SAT * SAB * (LR.a - LL.a)) * frcp(SAT - SAB);
+  if (!SR_pos) return (SAT * (RL.u * RL.b - vstar * AstarRL) - SAB * (RR.u * RR.b - vstar * AstarRR) - SAT * SAB * (RR.a - RL.a)) * frcp(SAT - SAB);
+  const double iA = frcp(SAR - SAL), iB = frcp(SAT - SAB);
   const double AstarT = (SAR * AstarRR - SAL * AstarLR) * iA;
   const double AstarB = (SAR * AstarRL - SAL * AstarLL) * iA;
   const double BstarR = (SAT * BstarRR - SAB * BstarRL) * iB;
@@ -583,22 +608,39 @@ __global__ void __launch_bounds__(256) k_prim_dt(const GridParams g, const doubl
     const double fb1 = U[c + g.isize + IB * N];
     const double fc1 = U[c + (long long)g.isize * g.jsize + IC * N];
     const double r = fmax(ur, g.smallr);
+#if PPK_EXACT
     const double u = mu / r, v = mv / r, w = mw / r;
+#else
+    const double ir = frcp(r);
+    const double u = mu * ir, v = mv * ir, w = mw * ir;
+#endif
     const double A = 0.5 * (fa + fa1), B = 0.5 * (fb + fb1), C = 0.5 * (fc + fc1);
     const double eken = 0.5 * (u * u + v * v + w * w);
     const double emag = 0.5 * (A * A + B * B + C * C);
+#if PPK_EXACT
     const double eint = (ue - emag) / r - eken;
+#else
+    const double eint = (ue - emag) * ir - eken;
+#endif
     const double p = fmax((g.gamma0 - 1.0) * r * eint, r * g.smallp);
     Q[c + ID * N] = r; Q[c + IP * N] = p; Q[c + IU * N] = u; Q[c + IV * N] = v; Q[c + IW * N] = w;
     Q[c + IA * N] = A; Q[c + IB * N] = B; Q[c + IC * N] = C;
     const int gw = g.gw;
     if ((int)i >= gw && (int)i < g.isize - gw && (int)j >= gw && (int)j < g.jsize - gw && k >= gw && k < g.ksize - gw) {
+#if PPK_EXACT
       double c2, d2;
       fast_speed_common(g.gamma0, r, p, A, B, C, c2, d2);
       const double vx = fast_speed_dir(c2, d2, r, A) + fabs(u);
       const double vy = fast_speed_dir(c2, d2, r, B) + fabs(v);
       const double vz = fast_speed_dir(c2, d2, r, C) + fabs(w);
       inv = vx / g.dx + vy / g.dy + vz / g.dz;
+#else
+      const double c2 = g.gamma0 * p * ir, d2 = 0.5 * (2.0 * emag * ir + c2), dd = d2 * d2, kk = c2 * ir;
+      const double vx = fsqrt(d2 + fsqrt(fmax(dd - kk * A * A, 0.0))) + fabs(u);
+      const double vy = fsqrt(d2 + fsqrt(fmax(dd - kk * B * B, 0.0))) + fabs(v);
+      const double vz = fsqrt(d2 + fsqrt(fmax(dd - kk * C * C, 0.0))) + fabs(w);
+      inv = vx * g.idx + vy * g.idy + vz * g.idz;
+#endif
     }
   }
   // NaN-safe like fmax(invDt, x) in the reference: fmax drops NaNs
@@ -620,6 +662,7 @@ __global__ void k_finalize_dt(const GridParams g, StepState *st) {
   double dt = g.cfl / inv;
   if (st->t + dt > st->t_end) dt = st->t_end - st->t;
   st->dt = dt;
+  st->dtdx = dt / g.dx; st->dtdy = dt / g.dy; st->dtdz = dt / g.dz;
   st->inv_dt_bits = 0ull;
 }
 // ++m_iteration; m_t += m_dt (SolverBase.cpp:216-218)
@@ -687,8 +730,7 @@ __global__ void __launch_bounds__(128) k_trace(const GridParams g, const StepSta
   if (j >= g.jsize - 2) return;
   const long long N = g.ncell, sj = g.isize, sk = (long long)g.isize * g.jsize;
   const long long c = cidx(g, i, j, k);
-  const double dt = stp->dt;
-  const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
+  const double dtdx = stp->dtdx, dtdy = stp->dtdy, dtdz = stp->dtdz;
   const double st = g.slope_type;
   const bool lim = (st == 1.0 || st == 2.0);
 
@@ -715,13 +757,20 @@ __global__ void __launch_bounds__(128) k_trace(const GridParams g, const StepSta
 
   const double gamma = g.gamma0;
   // source terms, MHDBaseFunctor3D.h:843-857
+#if PPK_EXACT
+#  define OVER_R(x) ((x) / r)
+#else
+  const double ir = frcp(r);
+#  define OVER_R(x) ((x) * ir)
+#endif
   const double sr0 = (-u * drx - dux * r) * dtdx + (-v * dry - dvy * r) * dtdy + (-w * drz - dwz * r) * dtdz;
-  const double su0 = (-u * dux - (dpx + B * dBx + C * dCx) / r) * dtdx + (-v * duy + B * dAy / r) * dtdy +
-                     (-w * duz + C * dAz / r) * dtdz;
-  const double sv0 = (-u * dvx + A * dBx / r) * dtdx + (-v * dvy - (dpy + A * dAy + C * dCy) / r) * dtdy +
-                     (-w * dvz + C * dBz / r) * dtdz;
-  const double sw0 = (-u * dwx + A * dCx / r) * dtdx + (-v * dwy + B * dCy / r) * dtdy +
-                     (-w * dwz - (dpz + A * dAz + B * dBz) / r) * dtdz;
+  const double su0 = (-u * dux - OVER_R(dpx + B * dBx + C * dCx)) * dtdx + (-v * duy + OVER_R(B * dAy)) * dtdy +
+                     (-w * duz + OVER_R(C * dAz)) * dtdz;
+  const double sv0 = (-u * dvx + OVER_R(A * dBx)) * dtdx + (-v * dvy - OVER_R(dpy + A * dAy + C * dCy)) * dtdy +
+                     (-w * dvz + OVER_R(C * dBz)) * dtdz;
+  const double sw0 = (-u * dwx + OVER_R(A * dCx)) * dtdx + (-v * dwy + OVER_R(B * dCy)) * dtdy +
+                     (-w * dwz - OVER_R(dpz + A * dAz + B * dBz)) * dtdz;
+#undef OVER_R
   const double sp0 = (-u * dpx - dux * gamma * p) * dtdx + (-v * dpy - dvy * gamma * p) * dtdy +
                      (-w * dpz - dwz * gamma * p) * dtdz;
   const double sA0 = (u * dBy + B * duy - v * dAy - A * dvy) * dtdy + (u * dCz + C * duz - w * dAz - A * dwz) * dtdz;
@@ -914,8 +963,7 @@ __global__ void __launch_bounds__(256) k_update(const GridParams g, const StepSt
   for (int v = 0; v < NBVAR; ++v) u[v] = Uin[c + v * N];
   const int gw = g.gw;
   if (i >= gw && i < g.isize - gw && j >= gw && j < g.jsize - gw && k >= gw && k < g.ksize - gw) {
-    const double dt = stp->dt;
-    const double dtdx = dt / g.dx, dtdy = dt / g.dy, dtdz = dt / g.dz;
+    const double dtdx = stp->dtdx, dtdy = stp->dtdy, dtdz = stp->dtdz;
     // x faces: (rho,E,mx,my,mz) <- (0,1,2,3,4)
     u[ID] += Fx[c + 0 * N] * dtdx; u[IP] += Fx[c + 1 * N] * dtdx; u[IU] += Fx[c + 2 * N] * dtdx;
     u[IV] += Fx[c + 3 * N] * dtdx; u[IW] += Fx[c + 4 * N] * dtdx;
@@ -986,6 +1034,17 @@ __global__ void __launch_bounds__(256) k_diagnostics(const GridParams g, const d
   }
 }
 
+// the reciprocal / square-root primitives of this build against which tests/ compare IEEE results
+__global__ void k_fastmath_selftest(int n, const double *x, double *rcp, double *sq, double *rsq) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+#if PPK_EXACT
+  rcp[t] = 1.0 / x[t]; sq[t] = sqrt(x[t]); rsq[t] = 1.0 / sqrt(x[t]);
+#else
+  rcp[t] = frcp(x[t]); sq[t] = fsqrt(x[t]); rsq[t] = frsqrt(x[t]);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
@@ -1046,13 +1105,17 @@ static void l_diagnostics(const GridParams &g, const double *U, double *out9, cu
   k_diagnostics<<<grid, bs, 0, s>>>(g, U, out9);
 }
 
+static void l_fastmath_selftest(int n, const double *x, double *rcp, double *sq, double *rsq, cudaStream_t s) {
+  k_fastmath_selftest<<<(n + 255) / 256, 256, 0, s>>>(n, x, rcp, sq, rsq);
+}
+
 static const KernelTable table = {
 #if PPK_EXACT
   "exact",
 #else
   "fast",
 #endif
-  l_boundary, l_prim_dt, l_finalize_dt, l_advance_time, l_elec_dbf, l_trace, l_flux, l_emf, l_update, l_diagnostics,
+  l_boundary, l_prim_dt, l_finalize_dt, l_advance_time, l_elec_dbf, l_trace, l_flux, l_emf, l_update, l_diagnostics, l_fastmath_selftest,
 };
 
 }  // namespace PPK_NS

@@ -191,3 +191,84 @@ def test_error_paths():
     p, _, _ = ppk.params_from_ini(ini.replace("implementationVersion=0", "implementationVersion=2"))
     with pytest.raises(ppk.PpkError, match="implementationVersion"):
         ppk.Mhd3d(p)
+
+
+def test_fast_math_primitives_within_2ulp():
+    """The fast build's rcp / sqrt / rsqrt (MUFU seed + one cubic Newton step) against IEEE results."""
+    rng = np.random.default_rng(7)
+    x = np.concatenate([10.0 ** rng.uniform(-30, 30, 200000), rng.uniform(0.5, 2.0, 100000), [1.0, 2.0, 4.0, 1e-8, 1.66600000858306884765625]])
+    rcp, sq, rsq = ppk.selftest_fastmath(x)
+    ulp = lambda got, want: np.abs(got - want) / np.spacing(np.abs(want))
+    assert ulp(rcp, 1.0 / x).max() <= 2.0, ulp(rcp, 1.0 / x).max()
+    assert ulp(sq, np.sqrt(x)).max() <= 2.0, ulp(sq, np.sqrt(x)).max()
+    assert ulp(rsq, 1.0 / np.sqrt(x)).max() <= 2.0, ulp(rsq, 1.0 / np.sqrt(x)).max()
+    # negative arguments of the reciprocal, and sqrt(0) == 0 (the clamped fast-speed discriminant can vanish)
+    rcp, _, _ = ppk.selftest_fastmath(-x[:1000])
+    assert ulp(rcp, -1.0 / x[:1000]).max() <= 2.0
+    _, sq0, _ = ppk.selftest_fastmath(np.zeros(4))
+    assert np.array_equal(sq0, np.zeros(4))
+
+
+def _slab_worker(rank, world, port, ini, nsteps, exact, out_dir):
+    import sys
+
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)  # CPU side channel for the 128-byte NCCL id only
+    import ppkmhd_b200 as P
+
+    p, t_end, _ = P.params_from_ini(ini, rank_z=rank, device=rank, exact=exact)
+    s = P.Mhd3d(p)
+    idt = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        idt = torch.tensor(list(P.nccl_unique_id()), dtype=torch.uint8)
+    dist.broadcast(idt, 0)
+    s.comm_init(bytes(idt.tolist()), world, rank)
+    s.upload(P.init_condition_from_ini(ini, rank_z=rank))
+    s.set_time(0.0, t_end, 0)
+    s.run(nsteps)
+    t, dt, it = s.get_time()
+    sums, divb = s.diagnostics()
+    np.save(os.path.join(out_dir, f"slab{rank}.npy"), s.interior())
+    np.save(os.path.join(out_dir, f"meta{rank}.npy"), np.array([t, dt, it, divb] + list(sums)))
+    s.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_z_slabs_bit_identical_to_single_gpu(tmp_path, world):
+    """Decomposition invariance: N z-slabs over NCCL == the undecomposed run, bit for bit, dt included."""
+    import socket
+
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from oracle import oracle as O  # ini text helper only
+
+    nsteps, nzl = 6, 12
+    kw = dict(nstepmax=nsteps, extra="[OrszagTang]\nkt=0.5\n", tend=10.0)
+    ini_n = O.make_ini("orszag_tang", (24, 20, nzl), mz=world, **kw)
+    ini_1 = O.make_ini("orszag_tang", (24, 20, nzl * world), **kw)
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    mp.spawn(_slab_worker, args=(world, port, ini_n, nsteps, True, str(tmp_path)), nprocs=world, join=True)
+    s, _ = make_solver(ini_1, exact=True)
+    s.run(nsteps)
+    t, dt, it = s.get_time()
+    sums, divb = s.diagnostics()
+    got = np.concatenate([np.load(tmp_path / f"slab{r}.npy") for r in range(world)], axis=1)
+    for r in range(world):
+        m = np.load(tmp_path / f"meta{r}.npy")
+        assert m[0] == t and m[1] == dt and m[2] == it, (r, m[:3], t, dt, it)
+    assert np.array_equal(got, s.interior()), "z-slab run differs from the single-GPU run"
+    tot = sum(np.load(tmp_path / f"meta{r}.npy")[4:] for r in range(world))
+    assert np.allclose(tot, sums, rtol=1e-12, atol=1e-12)
+    s.close()
