@@ -205,6 +205,7 @@ def run_ours(args):
     ini = make_ini(n, world, 10 ** 9)
     p, t_end, _ = ppk.params_from_ini(ini, rank_z=rank, device=local, exact=exact)
     solver = ppk.Mhd3d(p)
+    solver.set_pipeline(args.pipeline)
     # a dedicated (non-default) torch stream: the C ABI launches on it, torch.cuda.Event records on it
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -319,6 +320,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": f"Orszag-Tang 3D kt=1, {n}^3 cells per GPU (global {n}x{n}x{n * world}), z-slabs mz={world}, "
                                    f"HLLD + CT, periodic, cfl 0.8, gamma 1.666, implementationVersion=0 semantics",
+                       "pipeline": args.pipeline,
                        "arithmetic": "fast (FMA contraction, within 1e-12 of the reference)" if not exact else "exact (--fmad=false, bit-identical)",
                        "l2": "inputs larger than L2 (every array >= 1.1 GB vs 126 MB L2)",
                        "cells_with_ghosts_per_gpu": int(np.prod(p.shape[1:])),
@@ -342,6 +344,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=256, help="cells per axis per GPU")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--pipeline", default="fused", choices=["fused", "fused_split", "unfused"])
     ap.add_argument("--ref-n", type=int, default=128, help="grid of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")

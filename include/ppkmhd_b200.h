@@ -130,6 +130,15 @@ int ppk_mhd3d_halo_plan(const ppk_mhd3d_params *params, int capacity, ppk_halo_m
 /* Run on a caller-owned stream (a cudaStream_t, e.g. torch's current stream) instead of the
  * handle's own non-blocking stream. */
 int ppk_mhd3d_set_stream(ppk_mhd3d *handle, void *cuda_stream);
+/* Kernel schedule of one step (results are identical, bit for bit in exact mode):
+ *   PPK_PIPELINE_FUSED (default): ghost fill | primitives + CFL | edge E + face-B slopes | Hancock trace |
+ *       ONE consumer kernel = HLLD fluxes x,y,z + edge EMFs z,y,x + conservative and CT update (fluxes and EMFs
+ *       stay on chip);
+ *   PPK_PIPELINE_FUSED_SPLIT: the consumer as two kernels (fluxes + hydro update, EMFs + CT update);
+ *   PPK_PIPELINE_UNFUSED: one kernel per flux direction / EMF component + an update kernel, storing
+ *       Fluxes_x|y|z and Emf like the reference's v0 (what ppk_mhd3d_debug_array exposes). */
+enum ppk_pipeline { PPK_PIPELINE_UNFUSED = 0, PPK_PIPELINE_FUSED = 1, PPK_PIPELINE_FUSED_SPLIT = 2 };
+int ppk_mhd3d_set_pipeline(ppk_mhd3d *handle, int pipeline);
 /* Per-kernel CUDA-event timing (replaces the coarse timers of SolverBase.h:35-42 for profiling).
  * While enabled every kernel launch is bracketed by events on the launch stream. */
 int ppk_mhd3d_profile(ppk_mhd3d *handle, int enable);

@@ -63,7 +63,7 @@ EXPORTS = [
     "ppk_mhd3d_synchronize", "ppk_mhd3d_diagnostics", "ppk_nccl_get_unique_id", "ppk_mhd3d_comm_init",
     "ppk_mhd3d_set_stream", "ppk_mhd3d_profile", "ppk_mhd3d_kernel_times", "ppk_mhd3d_launch_count",
     "ppk_mhd3d_debug_array", "ppk_mhd3d_device_bytes", "ppk_last_error_string", "ppk_version_string",
-    "ppk_mhd3d_halo_plan", "ppk_selftest_fastmath",
+    "ppk_mhd3d_halo_plan", "ppk_selftest_fastmath", "ppk_mhd3d_set_pipeline",
     "ppk_params_from_ini", "ppk_init_condition_from_ini", "ppk_run_ini",
 ]
 
@@ -94,6 +94,7 @@ def load_library():
     L.ppk_mhd3d_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     L.ppk_mhd3d_set_stream.argtypes = [vp, vp]
     L.ppk_mhd3d_profile.argtypes = [vp, C.c_int]
+    L.ppk_mhd3d_set_pipeline.argtypes = [vp, C.c_int]
     L.ppk_mhd3d_kernel_times.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), dp, C.POINTER(C.c_long), C.c_int]
     L.ppk_mhd3d_launch_count.argtypes = [vp]
     L.ppk_mhd3d_launch_count.restype = C.c_long
@@ -218,6 +219,11 @@ class Mhd3d:
 
     def set_stream(self, stream_ptr):
         _check(self.L.ppk_mhd3d_set_stream(self.h, stream_ptr))
+
+    PIPELINES = {"unfused": 0, "fused": 1, "fused_split": 2}
+
+    def set_pipeline(self, name: str):
+        _check(self.L.ppk_mhd3d_set_pipeline(self.h, self.PIPELINES[name]))
 
     def profile(self, enable=True):
         _check(self.L.ppk_mhd3d_profile(self.h, 1 if enable else 0))

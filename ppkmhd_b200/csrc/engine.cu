@@ -86,7 +86,7 @@ int load_nccl() {
 
 const char *const kKernelNames[KK_COUNT] = {"boundary", "prim_dt", "finalize_dt", "elec_dbf", "trace",
                                             "flux_x", "flux_y", "flux_z", "emf_z", "emf_y", "emf_x",
-                                            "update", "diagnostics", "halo_exchange"};
+                                            "update", "diagnostics", "halo_exchange", "consume"};
 
 }  // namespace
 
@@ -101,6 +101,7 @@ struct ppk_mhd3d {
   double *Q = nullptr, *E = nullptr, *DBF = nullptr, *BASIS = nullptr, *F[3] = {nullptr, nullptr, nullptr}, *EMF = nullptr;
   StepState *st = nullptr;
   double *diag = nullptr;
+  void *tma = nullptr;  // tensor maps for the TMA-staged flux / EMF kernels
   long long bytes = 0;
   long launches = 0;
   long host_iteration = 0;  // parity selects U / U2 like SolverMHDMuscl::godunov_unsplit (SolverMHDMuscl.h:793-805)
@@ -115,6 +116,7 @@ struct ppk_mhd3d {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0, zlo = 0, zhi = 0;
   bool exch_lo = false, exch_hi = false;  // z faces filled by the halo exchange
+  int pipeline = PPK_PIPELINE_FUSED;
 
   double *cur() { return U[host_iteration & 1]; }
   double *nxt() { return U[(host_iteration + 1) & 1]; }
@@ -251,13 +253,19 @@ int enqueue_step(ppk_mhd3d *h) {
   if (int rc = boundaries_and_primitives(h, Uin, true)) return rc;
   { Scope sc(h, KK_ELEC_DBF, s); h->kt->elec_dbf(g, Uin, h->Q, h->E, h->DBF, s); }
   { Scope sc(h, KK_TRACE, s); h->kt->trace(g, h->st, Uin, h->Q, h->E, h->BASIS, s); }
-  { Scope sc(h, KK_FLUX_X, s); h->kt->flux(g, 0, h->BASIS, h->F[0], s); }
-  { Scope sc(h, KK_FLUX_Y, s); h->kt->flux(g, 1, h->BASIS, h->F[1], s); }
-  { Scope sc(h, KK_FLUX_Z, s); h->kt->flux(g, 2, h->BASIS, h->F[2], s); }
-  { Scope sc(h, KK_EMF_Z, s); h->kt->emf(g, 2, h->BASIS, h->DBF, h->EMF, s); }
-  { Scope sc(h, KK_EMF_Y, s); h->kt->emf(g, 1, h->BASIS, h->DBF, h->EMF, s); }
-  { Scope sc(h, KK_EMF_X, s); h->kt->emf(g, 0, h->BASIS, h->DBF, h->EMF, s); }
-  { Scope sc(h, KK_UPDATE, s); h->kt->update(g, h->st, Uin, Uout, h->F[0], h->F[1], h->F[2], h->EMF, s); }
+  if (h->pipeline == PPK_PIPELINE_UNFUSED) {
+    { Scope sc(h, KK_FLUX_X, s); h->kt->flux(g, 0, h->BASIS, h->F[0], h->tma, s); }
+    { Scope sc(h, KK_FLUX_Y, s); h->kt->flux(g, 1, h->BASIS, h->F[1], h->tma, s); }
+    { Scope sc(h, KK_FLUX_Z, s); h->kt->flux(g, 2, h->BASIS, h->F[2], h->tma, s); }
+    { Scope sc(h, KK_EMF_Z, s); h->kt->emf(g, 2, h->BASIS, h->DBF, h->EMF, h->tma, s); }
+    { Scope sc(h, KK_EMF_Y, s); h->kt->emf(g, 1, h->BASIS, h->DBF, h->EMF, h->tma, s); }
+    { Scope sc(h, KK_EMF_X, s); h->kt->emf(g, 0, h->BASIS, h->DBF, h->EMF, h->tma, s); }
+    { Scope sc(h, KK_UPDATE, s); h->kt->update(g, h->st, Uin, Uout, h->F[0], h->F[1], h->F[2], h->EMF, s); }
+  } else {
+    Scope sc(h, KK_CONSUME, s);
+    h->kt->consume(g, h->st, h->BASIS, h->DBF, Uin, Uout, h->pipeline == PPK_PIPELINE_FUSED_SPLIT, s);
+    if (h->pipeline == PPK_PIPELINE_FUSED_SPLIT) h->launches += 1;
+  }
   h->kt->advance_time(h->st, s);
   h->launches += 1;
   h->host_iteration += 1;
@@ -324,12 +332,11 @@ int ppk_mhd3d_create(const ppk_mhd3d_params *p, ppk_mhd3d **out) {
   if ((rc = alloc_doubles(h, &h->U[0], NBVAR * n)) || (rc = alloc_doubles(h, &h->U[1], NBVAR * n)) ||
       (rc = alloc_doubles(h, &h->Q, NBVAR * n)) || (rc = alloc_doubles(h, &h->E, NELEC * n)) ||
       (rc = alloc_doubles(h, &h->DBF, NDBF * n)) || (rc = alloc_doubles(h, &h->BASIS, NBASIS * n)) ||
-      (rc = alloc_doubles(h, &h->F[0], NFLUX * n)) || (rc = alloc_doubles(h, &h->F[1], NFLUX * n)) ||
-      (rc = alloc_doubles(h, &h->F[2], NFLUX * n)) || (rc = alloc_doubles(h, &h->EMF, NEMF * n)) ||
       (rc = alloc_doubles(h, &h->diag, 16))) {
     ppk_mhd3d_destroy(h);
     return rc;
   }
+  h->tma = h->kt->tma_create(g, h->BASIS, h->DBF);
   CUDA_TRY(cudaMalloc((void **)&h->st, sizeof(StepState)));
   StepState st0{};
   st0.t = 0.0; st0.t_end = 1e300; st0.dt = 0.0; st0.inv_dt_bits = 0ull; st0.iteration = 0;
@@ -347,6 +354,7 @@ int ppk_mhd3d_destroy(ppk_mhd3d *h) {
   for (double *p : {h->U[0], h->U[1], h->Q, h->E, h->DBF, h->BASIS, h->F[0], h->F[1], h->F[2], h->EMF, h->diag})
     if (p) cudaFree(p);
   if (h->st) cudaFree(h->st);
+  if (h->tma && h->kt) h->kt->tma_destroy(h->tma);
   for (auto &p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : h->pool) cudaEventDestroy(e);
   if (h->ev_xy) cudaEventDestroy(h->ev_xy);
@@ -521,6 +529,21 @@ int ppk_mhd3d_set_stream(ppk_mhd3d *h, void *cuda_stream) {
   return 0;
 }
 
+int ppk_mhd3d_set_pipeline(ppk_mhd3d *h, int pipeline) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  if (pipeline < PPK_PIPELINE_UNFUSED || pipeline > PPK_PIPELINE_FUSED_SPLIT) return fail(PPK_ERR_INVALID_ARGUMENT, "unknown pipeline");
+  DeviceGuard guard(h->device);
+  if (pipeline == PPK_PIPELINE_UNFUSED && !h->F[0]) {  // flux / EMF arrays exist only for the unfused pipeline
+    int rc = 0;
+    const long long n = h->g.ncell;
+    if ((rc = alloc_doubles(h, &h->F[0], NFLUX * n)) || (rc = alloc_doubles(h, &h->F[1], NFLUX * n)) ||
+        (rc = alloc_doubles(h, &h->F[2], NFLUX * n)) || (rc = alloc_doubles(h, &h->EMF, NEMF * n)))
+      return rc;
+  }
+  h->pipeline = pipeline;
+  return 0;
+}
+
 int ppk_mhd3d_profile(ppk_mhd3d *h, int enable) {
   if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
   DeviceGuard guard(h->device);
@@ -564,6 +587,7 @@ int ppk_mhd3d_debug_array(ppk_mhd3d *h, const char *name, double *host_out, int 
   else if (s == "Fluxes_z") { src = h->F[2]; nc = NFLUX; }
   else if (s == "Emf") { src = h->EMF; nc = NEMF; }
   else return fail(PPK_ERR_INVALID_ARGUMENT, "unknown array name " + s);
+  if (!src) return fail(PPK_ERR_STATE, s + " exists only in the unfused pipeline (ppk_mhd3d_set_pipeline)");
   if (ncomp) *ncomp = nc;
   if (host_out) {
     CUDA_TRY(cudaMemcpyAsync(host_out, src, (size_t)nc * h->g.ncell * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

@@ -47,7 +47,7 @@ struct StepState {
 // kernel kinds, for the per-kernel timers
 enum KernelKind {
   KK_BOUNDARY = 0, KK_PRIM_DT, KK_FINALIZE_DT, KK_ELEC_DBF, KK_TRACE,
-  KK_FLUX_X, KK_FLUX_Y, KK_FLUX_Z, KK_EMF_Z, KK_EMF_Y, KK_EMF_X, KK_UPDATE, KK_DIAG, KK_HALO, KK_COUNT
+  KK_FLUX_X, KK_FLUX_Y, KK_FLUX_Z, KK_EMF_Z, KK_EMF_Y, KK_EMF_X, KK_UPDATE, KK_DIAG, KK_HALO, KK_CONSUME, KK_COUNT
 };
 
 // Launchers exported by each arithmetic build (mhd_kernels.cu compiled twice).
@@ -60,12 +60,19 @@ struct KernelTable {
   void (*elec_dbf)(const GridParams &g, const double *U, const double *Q, double *E, double *DBF, cudaStream_t s);
   void (*trace)(const GridParams &g, const StepState *st, const double *U, const double *Q, const double *E,
                 double *BASIS, cudaStream_t s);
-  void (*flux)(const GridParams &g, int dir, const double *BASIS, double *F, cudaStream_t s);
-  void (*emf)(const GridParams &g, int edir, const double *BASIS, const double *DBF, double *EMF, cudaStream_t s);
+  // `tma`: context from tma_create (TMA-staged tiles) or nullptr (plain loads)
+  void (*flux)(const GridParams &g, int dir, const double *BASIS, double *F, const void *tma, cudaStream_t s);
+  void (*emf)(const GridParams &g, int edir, const double *BASIS, const double *DBF, double *EMF, const void *tma, cudaStream_t s);
   void (*update)(const GridParams &g, const StepState *st, const double *Uin, double *Uout, const double *Fx,
                  const double *Fy, const double *Fz, const double *EMF, cudaStream_t s);
   void (*diagnostics)(const GridParams &g, const double *U, double *out9, cudaStream_t s);
   void (*fastmath_selftest)(int n, const double *x, double *rcp, double *sq, double *rsq, cudaStream_t s);
+  // fused fluxes + EMFs + update; split != 0: two launches (hydro part, CT part)
+  void (*consume)(const GridParams &g, const StepState *st, const double *BASIS, const double *DBF, const double *Uin,
+                  double *Uout, int split, cudaStream_t s);
+  // tensor maps of the basis / face-slope arrays for the TMA-staged kernels (nullptr: not applicable)
+  void *(*tma_create)(const GridParams &g, const double *BASIS, const double *DBF);
+  void (*tma_destroy)(void *ctx);
 };
 
 const KernelTable *kernel_table_exact();

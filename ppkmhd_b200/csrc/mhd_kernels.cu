@@ -13,7 +13,9 @@
 // (each state component is an exact 1- or 2-addition combination of basis numbers).
 #include "mhd_common.h"
 
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
 #include <math.h>
+#include <stdlib.h>
 
 #ifndef PPK_EXACT
 #  error "compile with -DPPK_EXACT=0 or 1"
@@ -810,24 +812,16 @@ __global__ void __launch_bounds__(128) k_trace(const GridParams g, const StepSta
 DEV constexpr int slope_b(int D, int m) { return 5 + (m > D ? m - 1 : m); }
 DEV constexpr int slope_base(int D) { return D == 0 ? BSX : (D == 1 ? BSY : BSZ); }
 
-// ComputeFluxesAndStoreFunctor3D_MHD (MHDRunFunctors3D.h:1783-1909), one direction per launch.
-// Face (i,j,k) = lower D-face of cell (i,j,k): left state = qm_D of cell - e_D, right state = qp_D of
+// ComputeFluxesAndStoreFunctor3D_MHD (MHDRunFunctors3D.h:1783-1909), one face.
+// Face cR = lower D-face of cell cR: left state = qm_D of cell cR - e_D, right state = qp_D of
 // the cell (MHDBaseFunctor3D.h:898-968), rotated into the face frame exactly like the swapValues calls
-// of the reference (y: u<->v, A<->B ; z: u<->w, A<->C). Only faces the update reads are computed:
-// normal index in [gw, n+gw], transverse indices interior. Stores (rho, E, normal, t1, t2) fluxes.
+// of the reference (y: u<->v, A<->B ; z: u<->w, A<->C). Produces (rho, E, normal, t1, t2) fluxes.
 template <int D>
-__global__ void __launch_bounds__(128) k_flux(const GridParams g, const double *__restrict__ BASIS, double *__restrict__ F) {
-  const int gw = g.gw;
-  const int k = gw + blockIdx.y;
-  const unsigned ni = g.nx + (D == 0 ? 1 : 0);
-  const unsigned nj = g.ny + (D == 1 ? 1 : 0);
-  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned jj = t / ni;
-  if (jj >= nj) return;
-  const int i = gw + (int)(t - jj * ni), j = gw + (int)jj;
+DEV void flux_face(const GridParams &g, const double *__restrict__ BASIS, long long cR, double &fd, double &fp,
+                   double &fu, double &fv, double &fw) {
   const long long N = g.ncell;
   const long long sD = D == 0 ? 1 : (D == 1 ? (long long)g.isize : (long long)g.isize * g.jsize);
-  const long long cR = cidx(g, i, j, k), cL = cR - sD;
+  const long long cL = cR - sD;
   constexpr int T1 = D == 0 ? 1 : (D == 1 ? 0 : 1);  // frame after the reference's swaps
   constexpr int T2 = D == 0 ? 2 : (D == 1 ? 2 : 0);
   constexpr int SB = slope_base(D);
@@ -852,12 +846,30 @@ __global__ void __launch_bounds__(128) k_flux(const GridParams g, const double *
   const double b1r = BR_[(BQ + IA + T1) * N] - BR_[(SB + slope_b(D, T1)) * N];
   const double b2r = BR_[(BQ + IA + T2) * N] - BR_[(SB + slope_b(D, T2)) * N];
 
-  double fd, fp, fu, fv, fw;
 #if PPK_EXACT
   riemann_hlld(g.gamma0, rl, pl, unl, t1l, t2l, bnl, b1l, b2l, rr, pr, unr, t1r, t2r, bnr, b1r, b2r, fd, fp, fu, fv, fw);
 #else
   riemann_hlld_fast(g.gamma0, rl, pl, unl, t1l, t2l, bnl, b1l, b2l, rr, pr, unr, t1r, t2r, bnr, b1r, b2r, fd, fp, fu, fv, fw);
 #endif
+}
+
+// One direction per launch (the unfused pipeline). Only faces the update reads are computed:
+// normal index in [gw, n+gw], transverse indices interior.
+template <int D, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_flux(const GridParams g, const double *__restrict__ BASIS, double *__restrict__ F,
+                                                    int ib, unsigned ni) {
+  // faces i in [gw+ib, gw+ib+ni): the whole range, or the columns left over by the TMA-tiled kernel
+  const int gw = g.gw;
+  const int k = gw + blockIdx.y;
+  const unsigned nj = g.ny + (D == 1 ? 1 : 0);
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned jj = t / ni;
+  if (jj >= nj) return;
+  const int i = gw + ib + (int)(t - jj * ni), j = gw + (int)jj;
+  const long long N = g.ncell;
+  const long long cR = cidx(g, i, j, k);
+  double fd, fp, fu, fv, fw;
+  flux_face<D>(g, BASIS, cR, fd, fp, fu, fv, fw);
   double *Fo = F + cR;
   Fo[0 * N] = fd; Fo[1 * N] = fp; Fo[2 * N] = fu; Fo[3 * N] = fv; Fo[4 * N] = fw;
 }
@@ -901,33 +913,9 @@ DEV Corner edge_state(const GridParams &g, const double *__restrict__ BASIS, con
   return o;
 }
 
-// ComputeEmfAndStoreFunctor3D (MHDRunFunctors3D.h:2100-2238) + compute_emf<dir>
-// (RiemannSolvers_MHD.h:651-874), one edge direction per launch. With the cyclic frame
-// (d1,d2) = Z:(x,y) X:(y,z) Y:(z,x) the reference's three cases (including its RB/LT swap for EMF_y)
-// are one pattern: RT from c-e1-e2, RB from c-e1, LT from c-e2, LB from c.
-template <int E>
-__global__ void __launch_bounds__(128) k_emf(const GridParams g, const double *__restrict__ BASIS,
-                                             const double *__restrict__ DBF, double *__restrict__ EMF) {
-  constexpr int D1 = (E + 1) % 3, D2 = (E + 2) % 3;
-  const int gw = g.gw;
-  const int k = gw + blockIdx.y;
-  const unsigned ni = g.nx + (E == 0 ? 0 : 1);
-  const unsigned nj = g.ny + (E == 1 ? 0 : 1);
-  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned jj = t / ni;
-  if (jj >= nj) return;
-  const int i = gw + (int)(t - jj * ni), j = gw + (int)jj;
-  const long long N = g.ncell;
-  const long long st1 = D1 == 0 ? 1 : (D1 == 1 ? (long long)g.isize : (long long)g.isize * g.jsize);
-  const long long st2 = D2 == 0 ? 1 : (D2 == 1 ? (long long)g.isize : (long long)g.isize * g.jsize);
-  const long long c = cidx(g, i, j, k);
-
-  const Corner RT = edge_state<E>(g, BASIS, DBF, c - st1 - st2, true, true);
-  const Corner RB = edge_state<E>(g, BASIS, DBF, c - st1, true, false);
-  const Corner LT = edge_state<E>(g, BASIS, DBF, c - st2, false, true);
-  const Corner LB = edge_state<E>(g, BASIS, DBF, c, false, false);
-
-  // compute_emf: LL<-RT, RL<-LT, LR<-RB, RR<-LB ; in-plane field averaged across the edge
+// compute_emf<dir> (RiemannSolvers_MHD.h:651-874) from the four edge states around an edge:
+// LL<-RT, RL<-LT, LR<-RB, RR<-LB ; in-plane field averaged across the edge
+DEV double emf_from_corners(const GridParams &g, const Corner &RT, const Corner &RB, const Corner &LT, const Corner &LB) {
   Corner LL = RT, RL = LT, LR = RB, RR = LB;
   const double a_top = 0.5 * (RT.a + LT.a), a_bot = 0.5 * (RB.a + LB.a);
   const double b_rgt = 0.5 * (RT.b + RB.b), b_lft = 0.5 * (LT.b + LB.b);
@@ -938,10 +926,248 @@ __global__ void __launch_bounds__(128) k_emf(const GridParams g, const double *_
   const double ELR = LR.u * LR.b - LR.v * LR.a;
   const double ERR = RR.u * RR.b - RR.v * RR.a;
 #if PPK_EXACT
-  EMF[c + (2 - E) * N] = mag_riemann2d_hlld(g.gamma0, g.smallc, LL, RL, LR, RR, ELL, ERL, ELR, ERR);
+  return mag_riemann2d_hlld(g.gamma0, g.smallc, LL, RL, LR, RR, ELL, ERL, ELR, ERR);
 #else
-  EMF[c + (2 - E) * N] = mag_riemann2d_hlld_fast(g.gamma0, g.smallc, LL, RL, LR, RR, ELL, ERL, ELR, ERR);
+  return mag_riemann2d_hlld_fast(g.gamma0, g.smallc, LL, RL, LR, RR, ELL, ERL, ELR, ERR);
 #endif
+}
+
+
+// ComputeEmfAndStoreFunctor3D (MHDRunFunctors3D.h:2100-2238) + compute_emf<dir>
+// (RiemannSolvers_MHD.h:651-874), one edge. With the cyclic frame
+// (d1,d2) = Z:(x,y) X:(y,z) Y:(z,x) the reference's three cases (including its RB/LT swap for EMF_y)
+// are one pattern: RT from c-e1-e2, RB from c-e1, LT from c-e2, LB from c.
+template <int E>
+DEV double emf_edge(const GridParams &g, const double *__restrict__ BASIS, const double *__restrict__ DBF, long long c) {
+  constexpr int D1 = (E + 1) % 3, D2 = (E + 2) % 3;
+  const long long st1 = D1 == 0 ? 1 : (D1 == 1 ? (long long)g.isize : (long long)g.isize * g.jsize);
+  const long long st2 = D2 == 0 ? 1 : (D2 == 1 ? (long long)g.isize : (long long)g.isize * g.jsize);
+
+  const Corner RT = edge_state<E>(g, BASIS, DBF, c - st1 - st2, true, true);
+  const Corner RB = edge_state<E>(g, BASIS, DBF, c - st1, true, false);
+  const Corner LT = edge_state<E>(g, BASIS, DBF, c - st2, false, true);
+  const Corner LB = edge_state<E>(g, BASIS, DBF, c, false, false);
+  return emf_from_corners(g, RT, RB, LT, LB);
+}
+
+// One edge direction per launch (the unfused pipeline).
+template <int E, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_emf(const GridParams g, const double *__restrict__ BASIS,
+                                                   const double *__restrict__ DBF, double *__restrict__ EMF, int ib,
+                                                   unsigned ni) {
+  const int gw = g.gw;
+  const int k = gw + blockIdx.y;
+  const unsigned nj = g.ny + (E == 1 ? 0 : 1);
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned jj = t / ni;
+  if (jj >= nj) return;
+  const int i = gw + ib + (int)(t - jj * ni), j = gw + (int)jj;
+  const long long c = cidx(g, i, j, k);
+  EMF[c + (2 - E) * g.ncell] = emf_edge<E>(g, BASIS, DBF, c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA-staged variants of the flux / EMF kernels.
+//
+// The basis is a 4-D tensor (x, y, z, component) in the reference's SoA layout, so the cells one CTA needs
+// of one component are a 3-D box: one `cp.async.bulk.tensor.4d` (SASS UTMALDG) per component, issued by a
+// single thread, lands the box in shared memory and signals an mbarrier. The Riemann problems then read
+// their 2 (face) or 4 (edge) cells from shared memory at compile-time offsets: no per-load 64-bit address
+// arithmetic, no long-scoreboard stall in the middle of the FP64 chains, and the loads of the CTA that is
+// waiting overlap the arithmetic of the other CTAs resident on the SM.
+// Needs an even isize (16-byte global strides); otherwise, and for the x-columns beyond the last full
+// 32-wide tile, the plain kernels above are used.
+// ---------------------------------------------------------------------------------------------
+DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+DEV void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+DEV void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEV void mbar_wait(unsigned long long *bar, unsigned parity) {
+  asm volatile(
+    "{\n"
+    ".reg .pred P1;\n"
+    "LAB_WAIT:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+    "@P1 bra DONE;\n"
+    "bra LAB_WAIT;\n"
+    "DONE:\n"
+    "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+DEV void tma_load_box(double *dst, const CUtensorMap *map, int x, int y, int z, int comp, unsigned long long *bar) {
+  asm volatile(
+    "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+      smem_u32(dst)),
+    "l"(map), "r"(x), "r"(y), "r"(z), "r"(comp), "r"(smem_u32(bar))
+    : "memory");
+}
+
+// tile geometry of one TMA-staged kernel: TX x TY x TZ faces/edges per CTA, HX/HY/HZ lower halo cells.
+// A box must start on a 16-byte boundary of the innermost dimension, i.e. at an EVEN x index for fp64: tiles
+// start at i0 = gw + 32*bx (odd, gw = 3), so every configuration takes HX = 1 (box from i0-1, 34 wide) whether
+// or not its stencil reaches into x.
+template <int TY_, int TZ_, int HX_, int HY_, int HZ_, int NSLOT_>
+struct TileCfg {
+  static constexpr int TX = 32, TY = TY_, TZ = TZ_, HX = HX_, HY = HY_, HZ = HZ_, NSLOT = NSLOT_;
+  static constexpr int XB = TX + 2 * HX;  // x extent padded to a 16-byte multiple (one unused column when HX = 1)
+  static constexpr int YB = TY + HY, ZB = TZ + HZ;
+  static constexpr int BOX = XB * YB * ZB;                          // doubles per component box
+  static constexpr int SLOT = (BOX * 8 + 127) / 128 * 16;           // slot stride in doubles (128-byte aligned)
+  static constexpr int SMEM_BYTES = NSLOT * SLOT * 8;
+  static constexpr int THREADS = TX * TY * TZ;
+};
+template <int E> struct EmfCfg;  // edge direction E: halo of one cell along d1 and d2
+template <> struct EmfCfg<2> : TileCfg<8, 1, 1, 1, 0, 21> {};
+template <> struct EmfCfg<0> : TileCfg<4, 2, 1, 1, 1, 21> {};
+template <> struct EmfCfg<1> : TileCfg<4, 2, 1, 0, 1, 21> {};
+template <int D> struct FluxCfg;  // face direction D: halo of one cell along D
+template <> struct FluxCfg<0> : TileCfg<8, 1, 1, 0, 0, 16> {};
+template <> struct FluxCfg<1> : TileCfg<8, 1, 1, 1, 0, 16> {};
+template <> struct FluxCfg<2> : TileCfg<4, 2, 1, 0, 1, 16> {};
+
+// component (row of the 4-D tensor) staged in slot s of the EMF kernel; slots 19,20 come from DBF
+template <int E>
+DEV constexpr int emf_slot_comp(int s) {
+  constexpr int D1 = (E + 1) % 3, D2 = (E + 2) % 3;
+  constexpr int S1 = slope_base(D1), S2 = slope_base(D2);
+  const int q[5] = {BQ + ID, BQ + IP, BQ + IU + D1, BQ + IU + D2, BQ + IA + E};
+  const int i1[5] = {0, 1, 2 + D1, 2 + D2, slope_b(D1, E)};
+  const int i2[5] = {0, 1, 2 + D1, 2 + D2, slope_b(D2, E)};
+  if (s < 5) return q[s];
+  if (s < 10) return S1 + i1[s - 5];
+  if (s < 15) return S2 + i2[s - 10];
+  if (s < 19) return BFACE + 2 * (s < 17 ? D1 : D2) + ((s - 15) & 1);
+  return s == 19 ? dbf_idx(D1, D2) : dbf_idx(D2, D1);
+}
+
+// edge_state<E> reading the staged tile; `o` = offset of the cell inside a component box
+template <int E, class Cfg>
+DEV Corner edge_state_smem(const GridParams &g, const double *__restrict__ sm, int o, const bool s1p, const bool s2p) {
+  constexpr int D1 = (E + 1) % 3, D2 = (E + 2) % 3;
+  constexpr int st[3] = {1, Cfg::XB, Cfg::XB * Cfg::YB};
+  constexpr int S = Cfg::SLOT;
+  auto comb = [&](int sq) {
+    const double a = sm[(sq + 5) * S + o], b = sm[(sq + 10) * S + o];
+    return sm[sq * S + o] + ((s1p ? a : -a) + (s2p ? b : -b));
+  };
+  Corner c;
+  c.r = fmax(g.smallr, comb(0));
+  c.p = fmax(g.smallp, comb(1));
+  c.u = comb(2);
+  c.v = comb(3);
+  {
+    const double face = sm[(15 + (s1p ? 1 : 0)) * S + o];
+    const double h = 0.5 * sm[19 * S + (s1p ? o + st[D1] : o)];
+    c.a = face + (s2p ? h : -h);
+  }
+  {
+    const double face = sm[(17 + (s2p ? 1 : 0)) * S + o];
+    const double h = 0.5 * sm[20 * S + (s2p ? o + st[D2] : o)];
+    c.b = face + (s1p ? h : -h);
+  }
+  c.c = comb(4);
+  return c;
+}
+
+template <int E>
+__global__ void __launch_bounds__(EmfCfg<E>::THREADS, 2)
+  k_emf_tma(const GridParams g, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapD,
+            double *__restrict__ EMF) {
+  using Cfg = EmfCfg<E>;
+  constexpr int D1 = (E + 1) % 3, D2 = (E + 2) % 3;
+  extern __shared__ __align__(128) double sm[];
+  __shared__ unsigned long long bar;
+  const int tid = threadIdx.x;
+  const int tx = tid % Cfg::TX, ty = (tid / Cfg::TX) % Cfg::TY, tz = tid / (Cfg::TX * Cfg::TY);
+  const int i0 = g.gw + blockIdx.x * Cfg::TX, j0 = g.gw + blockIdx.y * Cfg::TY, k0 = g.gw + blockIdx.z * Cfg::TZ;
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, Cfg::NSLOT * Cfg::BOX * 8);
+#pragma unroll
+    for (int s = 0; s < Cfg::NSLOT; ++s)
+      tma_load_box(sm + s * Cfg::SLOT, s < 19 ? &mapB : &mapD, i0 - Cfg::HX, j0 - Cfg::HY, k0 - Cfg::HZ, emf_slot_comp<E>(s), &bar);
+  }
+  mbar_wait(&bar, 0);
+  const int i = i0 + tx, j = j0 + ty, k = k0 + tz;
+  // edges the CT update reads: index <= n+gw along d1 and d2, interior along the edge direction
+  const int nj = g.ny + (E == 1 ? 0 : 1), nk = g.nz + (E == 2 ? 0 : 1);
+  if (j >= g.gw + nj || k >= g.gw + nk) return;  // (the x range is tiled exactly by the launcher)
+  constexpr int st[3] = {1, Cfg::XB, Cfg::XB * Cfg::YB};
+  const int o = (tx + Cfg::HX) + Cfg::XB * ((ty + Cfg::HY) + Cfg::YB * (tz + Cfg::HZ));
+  const Corner RT = edge_state_smem<E, Cfg>(g, sm, o - st[D1] - st[D2], true, true);
+  const Corner RB = edge_state_smem<E, Cfg>(g, sm, o - st[D1], true, false);
+  const Corner LT = edge_state_smem<E, Cfg>(g, sm, o - st[D2], false, true);
+  const Corner LB = edge_state_smem<E, Cfg>(g, sm, o, false, false);
+  EMF[cidx(g, i, j, k) + (2 - E) * g.ncell] = emf_from_corners(g, RT, RB, LT, LB);
+}
+
+// component staged in slot s of the flux kernel: 0-6 q (r,p,un,t1,t2,b1,b2), 7-13 their slopes along D,
+// 14 lower-face normal field (right state), 15 upper-face normal field (left state)
+template <int D>
+DEV constexpr int flux_slot_comp(int s) {
+  constexpr int T1 = D == 0 ? 1 : (D == 1 ? 0 : 1), T2 = D == 0 ? 2 : (D == 1 ? 2 : 0);
+  constexpr int SB = slope_base(D);
+  const int q[7] = {BQ + ID, BQ + IP, BQ + IU + D, BQ + IU + T1, BQ + IU + T2, BQ + IA + T1, BQ + IA + T2};
+  const int sl[7] = {0, 1, 2 + D, 2 + T1, 2 + T2, slope_b(D, T1), slope_b(D, T2)};
+  if (s < 7) return q[s];
+  if (s < 14) return SB + sl[s - 7];
+  return BFACE + 2 * D + (s - 14);
+}
+
+template <int D>
+__global__ void __launch_bounds__(FluxCfg<D>::THREADS, 3)
+  k_flux_tma(const GridParams g, const __grid_constant__ CUtensorMap mapB, double *__restrict__ F) {
+  using Cfg = FluxCfg<D>;
+  extern __shared__ __align__(128) double sm[];
+  __shared__ unsigned long long bar;
+  const int tid = threadIdx.x;
+  const int tx = tid % Cfg::TX, ty = (tid / Cfg::TX) % Cfg::TY, tz = tid / (Cfg::TX * Cfg::TY);
+  const int i0 = g.gw + blockIdx.x * Cfg::TX, j0 = g.gw + blockIdx.y * Cfg::TY, k0 = g.gw + blockIdx.z * Cfg::TZ;
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, Cfg::NSLOT * Cfg::BOX * 8);
+#pragma unroll
+    for (int s = 0; s < Cfg::NSLOT; ++s)
+      tma_load_box(sm + s * Cfg::SLOT, &mapB, i0 - Cfg::HX, j0 - Cfg::HY, k0 - Cfg::HZ, flux_slot_comp<D>(s), &bar);
+  }
+  mbar_wait(&bar, 0);
+  const int i = i0 + tx, j = j0 + ty, k = k0 + tz;
+  const int nj = g.ny + (D == 1 ? 1 : 0), nk = g.nz + (D == 2 ? 1 : 0);
+  if (j >= g.gw + nj || k >= g.gw + nk) return;
+  constexpr int st[3] = {1, Cfg::XB, Cfg::XB * Cfg::YB};
+  constexpr int S = Cfg::SLOT;
+  const int oR = (tx + Cfg::HX) + Cfg::XB * ((ty + Cfg::HY) + Cfg::YB * (tz + Cfg::HZ)), oL = oR - st[D];
+  // left state: q + slope (qm) of the cell below the face; right state: q - slope (qp) of the cell above
+  const double rl = fmax(g.smallr, sm[0 * S + oL] + sm[7 * S + oL]);
+  const double pl = fmax(g.smallp, sm[1 * S + oL] + sm[8 * S + oL]);
+  const double unl = sm[2 * S + oL] + sm[9 * S + oL];
+  const double t1l = sm[3 * S + oL] + sm[10 * S + oL];
+  const double t2l = sm[4 * S + oL] + sm[11 * S + oL];
+  const double bnl = sm[15 * S + oL];
+  const double b1l = sm[5 * S + oL] + sm[12 * S + oL];
+  const double b2l = sm[6 * S + oL] + sm[13 * S + oL];
+  const double rr = fmax(g.smallr, sm[0 * S + oR] - sm[7 * S + oR]);
+  const double pr = fmax(g.smallp, sm[1 * S + oR] - sm[8 * S + oR]);
+  const double unr = sm[2 * S + oR] - sm[9 * S + oR];
+  const double t1r = sm[3 * S + oR] - sm[10 * S + oR];
+  const double t2r = sm[4 * S + oR] - sm[11 * S + oR];
+  const double bnr = sm[14 * S + oR];
+  const double b1r = sm[5 * S + oR] - sm[12 * S + oR];
+  const double b2r = sm[6 * S + oR] - sm[13 * S + oR];
+  double fd, fp, fu, fv, fw;
+#if PPK_EXACT
+  riemann_hlld(g.gamma0, rl, pl, unl, t1l, t2l, bnl, b1l, b2l, rr, pr, unr, t1r, t2r, bnr, b1r, b2r, fd, fp, fu, fv, fw);
+#else
+  riemann_hlld_fast(g.gamma0, rl, pl, unl, t1l, t2l, bnl, b1l, b2l, rr, pr, unr, t1r, t2r, bnr, b1r, b2r, fd, fp, fu, fv, fw);
+#endif
+  const long long N = g.ncell;
+  double *Fo = F + cidx(g, i, j, k);
+  Fo[0 * N] = fd; Fo[1 * N] = fp; Fo[2 * N] = fu; Fo[3 * N] = fv; Fo[4 * N] = fw;
 }
 
 // Kokkos::deep_copy(data_out, data_in) (SolverMHDMuscl.cpp:477) + UpdateFunctor3D_MHD
@@ -991,6 +1217,123 @@ __global__ void __launch_bounds__(256) k_update(const GridParams g, const StepSt
   }
 #pragma unroll
   for (int v = 0; v < NBVAR; ++v) Uout[c + v * N] = u[v];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused consumer: ComputeFluxesAndStore (x,y,z) + ComputeEmfAndStore (z,y,x) + UpdateFunctor3D_MHD +
+// UpdateEmfFunctor3D (MHDRunFunctors3D.h:1783-1909, 2100-2238, 2430-2544, 2549-2628) in ONE kernel that
+// never writes a flux or an EMF to HBM.
+//
+// A CTA owns a (CBX-1) x (CBY-1) tile of (i,j) columns and marches upwards in k. Thread (tx,ty) solves the
+// Riemann problems on the three LOWER faces and the three LOWER edges of cell (i,j,k); the upper-face /
+// upper-edge values a cell needs come from its +x / +y neighbours in the tile through shared memory (the
+// last row and column of threads exist only to provide them: tiles overlap by one), and from the same
+// thread one plane later in z. The reference's update order per cell
+//     x-lo, x-hi, y-lo, y-hi, z-lo | z-hi          and for CT   Ez-terms, in-plane C terms | Ey/Ex(k+1) terms
+// is exactly "everything of plane k, then the z-hi terms when plane k+1 has been solved", so the partially
+// updated cell waits in registers for one iteration and the result is bit-identical to the unfused order.
+// Ghost cells of Uout are not written: every step begins by refilling all ghost layers of its input array.
+// ---------------------------------------------------------------------------------------------
+constexpr int CBX = 32, CBY = 8;
+
+template <bool HYDRO, bool CT>
+__global__ void __launch_bounds__(CBX *CBY, 2)
+  k_consume(const GridParams g, const StepState *__restrict__ stp, const double *__restrict__ BASIS,
+            const double *__restrict__ DBF, const double *__restrict__ Uin, double *__restrict__ Uout, int zchunk) {
+  __shared__ double sF[2][NFLUX][CBY][CBX];  // x- and y-face fluxes of the current plane
+  __shared__ double sE[3][CBY][CBX];         // Ez, Ey, Ex of the current plane
+  const int gw = g.gw;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i = gw + blockIdx.x * (CBX - 1) + tx;
+  const int j = gw + blockIdx.y * (CBY - 1) + ty;
+  const bool in_i = i <= gw + g.nx, in_j = j <= gw + g.ny;  // faces and edges exist up to index n+gw inclusive
+  const bool cell_i = i < gw + g.nx, cell_j = j < gw + g.ny;
+  const bool own = tx < CBX - 1 && ty < CBY - 1 && cell_i && cell_j;
+  // the solves an owner of this tile consumes from this thread
+  const bool do_fx = HYDRO && in_i && cell_j && ty < CBY - 1;
+  const bool do_fy = HYDRO && cell_i && in_j && tx < CBX - 1;
+  const bool do_fz = HYDRO && own;
+  const bool do_ez = CT && in_i && in_j && !(tx == CBX - 1 && ty == CBY - 1);
+  const bool do_ey = CT && in_i && cell_j && ty < CBY - 1;
+  const bool do_ex = CT && cell_i && in_j && tx < CBX - 1;
+
+  const long long N = g.ncell, sk = (long long)g.isize * g.jsize;
+  const double dtdx = stp->dtdx, dtdy = stp->dtdy, dtdz = stp->dtdz;
+  // this CTA marches over cells k0 .. k1-1 (blockIdx.z selects the z-chunk; chunks only exist to give the grid
+  // enough CTAs) and additionally solves the z-coupled problems of plane k1 to close its last cells
+  const int k0 = gw + blockIdx.z * zchunk;
+  const int k1 = min(k0 + zchunk, gw + g.nz);
+  long long c = cidx(g, i, j, k0);
+  double u[NBVAR];
+  double ey_prev = 0.0, ex_prev = 0.0;
+#pragma unroll
+  for (int v = 0; v < NBVAR; ++v) u[v] = 0.0;
+
+  for (int k = k0; k <= k1; ++k, c += sk) {
+    // the plane above is first touched one iteration from now: start its DRAM -> L2 transfer now (the row and
+    // column of cells below the tile are prefetched by the neighbouring CTAs' threads)
+    if (k < k1 && in_i && in_j) {
+      const double *nb = BASIS + c + sk, *nd = DBF + c + sk;
+#pragma unroll
+      for (int v = 0; v < NBASIS; ++v) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + v * N));
+#pragma unroll
+      for (int v = 0; v < NDBF; ++v) asm volatile("prefetch.global.L2 [%0];" ::"l"(nd + v * N));
+    }
+    double fz[NFLUX] = {0, 0, 0, 0, 0}, ey = 0.0, ex = 0.0;
+    if (do_fz) flux_face<2>(g, BASIS, c, fz[0], fz[1], fz[2], fz[3], fz[4]);
+    if (do_ey) ey = emf_edge<1>(g, BASIS, DBF, c);
+    if (do_ex) ex = emf_edge<0>(g, BASIS, DBF, c);
+    if (own && k > k0) {  // cell k-1 receives its z-hi terms and is complete
+      const long long cp = c - sk;
+      if (HYDRO) {
+        u[ID] -= fz[0] * dtdz; u[IP] -= fz[1] * dtdz; u[IU] -= fz[4] * dtdz; u[IV] -= fz[3] * dtdz; u[IW] -= fz[2] * dtdz;
+        Uout[cp + ID * N] = u[ID]; Uout[cp + IP * N] = u[IP]; Uout[cp + IU * N] = u[IU];
+        Uout[cp + IV * N] = u[IV]; Uout[cp + IW * N] = u[IW];
+      }
+      if (CT) {
+        u[IA] -= (ey - ey_prev) * dtdz;
+        u[IB] += (ex - ex_prev) * dtdz;
+        Uout[cp + IA * N] = u[IA]; Uout[cp + IB * N] = u[IB]; Uout[cp + IC * N] = u[IC];
+      }
+    }
+    if (k == k1) break;  // uniform: the top plane only closes the last cells
+
+    double fx[NFLUX] = {0, 0, 0, 0, 0}, fy[NFLUX] = {0, 0, 0, 0, 0}, ez = 0.0;
+    if (do_fx) flux_face<0>(g, BASIS, c, fx[0], fx[1], fx[2], fx[3], fx[4]);
+    if (do_fy) flux_face<1>(g, BASIS, c, fy[0], fy[1], fy[2], fy[3], fy[4]);
+    if (do_ez) ez = emf_edge<2>(g, BASIS, DBF, c);
+    if (HYDRO) {
+#pragma unroll
+      for (int v = 0; v < NFLUX; ++v) { sF[0][v][ty][tx] = fx[v]; sF[1][v][ty][tx] = fy[v]; }
+    }
+    if (CT) { sE[0][ty][tx] = ez; sE[1][ty][tx] = ey; sE[2][ty][tx] = ex; }
+    __syncthreads();
+    if (own) {
+      if (HYDRO) {
+        u[ID] = Uin[c + ID * N]; u[IP] = Uin[c + IP * N]; u[IU] = Uin[c + IU * N]; u[IV] = Uin[c + IV * N]; u[IW] = Uin[c + IW * N];
+        // x faces: (rho,E,mx,my,mz) <- (0,1,2,3,4)
+        u[ID] += fx[0] * dtdx; u[IP] += fx[1] * dtdx; u[IU] += fx[2] * dtdx; u[IV] += fx[3] * dtdx; u[IW] += fx[4] * dtdx;
+        u[ID] -= sF[0][0][ty][tx + 1] * dtdx; u[IP] -= sF[0][1][ty][tx + 1] * dtdx; u[IU] -= sF[0][2][ty][tx + 1] * dtdx;
+        u[IV] -= sF[0][3][ty][tx + 1] * dtdx; u[IW] -= sF[0][4][ty][tx + 1] * dtdx;
+        // y faces, rotated frame: normal=my (2), t1=mx (3), t2=mz (4)
+        u[ID] += fy[0] * dtdy; u[IP] += fy[1] * dtdy; u[IU] += fy[3] * dtdy; u[IV] += fy[2] * dtdy; u[IW] += fy[4] * dtdy;
+        u[ID] -= sF[1][0][ty + 1][tx] * dtdy; u[IP] -= sF[1][1][ty + 1][tx] * dtdy; u[IU] -= sF[1][3][ty + 1][tx] * dtdy;
+        u[IV] -= sF[1][2][ty + 1][tx] * dtdy; u[IW] -= sF[1][4][ty + 1][tx] * dtdy;
+        // z-lo face: normal=mz (2), t1=my (3), t2=mx (4)
+        u[ID] += fz[0] * dtdz; u[IP] += fz[1] * dtdz; u[IU] += fz[4] * dtdz; u[IV] += fz[3] * dtdz; u[IW] += fz[2] * dtdz;
+      }
+      if (CT) {
+        u[IA] = Uin[c + IA * N]; u[IB] = Uin[c + IB * N]; u[IC] = Uin[c + IC * N];
+        // expression order of MHDRunFunctors3D.h:2602-2616; the two Ey/Ex(k+1) terms follow one plane later
+        u[IA] += (sE[0][ty + 1][tx] - ez) * dtdy;
+        u[IB] -= (sE[0][ty][tx + 1] - ez) * dtdx;
+        u[IC] += (sE[1][ty][tx + 1] - ey) * dtdx;
+        u[IC] -= (sE[2][ty + 1][tx] - ex) * dtdy;
+        ey_prev = ey; ex_prev = ex;
+      }
+    }
+    __syncthreads();
+  }
 }
 
 // Diagnostics: per-variable sums over the interior and max |div B| (needs filled upper ghosts).
@@ -1077,27 +1420,122 @@ static void l_trace(const GridParams &g, const StepState *st, const double *U, c
   dim3 grid(cdiv((long long)(g.isize - 4) * (g.jsize - 4), bs), g.ksize - 4);
   k_trace<<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS);
 }
-static void l_flux(const GridParams &g, int dir, const double *BASIS, double *F, cudaStream_t s) {
-  const int bs = 128;
-  const long long ni = g.nx + (dir == 0), nj = g.ny + (dir == 1), nk = g.nz + (dir == 2);
-  dim3 grid(cdiv(ni * nj, bs), (unsigned)nk);
-  if (dir == 0) k_flux<0><<<grid, bs, 0, s>>>(g, BASIS, F);
-  else if (dir == 1) k_flux<1><<<grid, bs, 0, s>>>(g, BASIS, F);
-  else k_flux<2><<<grid, bs, 0, s>>>(g, BASIS, F);
+// ---- TMA tensor maps (host) ---------------------------------------------------------------------
+struct TmaCtx {
+  CUtensorMap emfB[3], emfD[3], fluxB[3];
+};
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool encode_map(EncodeTiledFn enc, CUtensorMap *m, const GridParams &g, const double *base, int ncomp, int xb, int yb, int zb) {
+  const cuuint64_t dims[4] = {(cuuint64_t)g.isize, (cuuint64_t)g.jsize, (cuuint64_t)g.ksize, (cuuint64_t)ncomp};
+  const cuuint64_t strides[3] = {(cuuint64_t)g.isize * 8, (cuuint64_t)g.isize * g.jsize * 8, (cuuint64_t)g.ncell * 8};
+  const cuuint32_t box[4] = {(cuuint32_t)xb, (cuuint32_t)yb, (cuuint32_t)zb, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-static void l_emf(const GridParams &g, int e, const double *BASIS, const double *DBF, double *EMF, cudaStream_t s) {
-  const int bs = 128;
-  const long long ni = g.nx + (e != 0), nj = g.ny + (e != 1), nk = g.nz + (e != 2);
-  dim3 grid(cdiv(ni * nj, bs), (unsigned)nk);
-  if (e == 0) k_emf<0><<<grid, bs, 0, s>>>(g, BASIS, DBF, EMF);
-  else if (e == 1) k_emf<1><<<grid, bs, 0, s>>>(g, BASIS, DBF, EMF);
-  else k_emf<2><<<grid, bs, 0, s>>>(g, BASIS, DBF, EMF);
+template <class Cfg> static bool encode_cfg(EncodeTiledFn enc, CUtensorMap *m, const GridParams &g, const double *base, int ncomp) {
+  return encode_map(enc, m, g, base, ncomp, Cfg::XB, Cfg::YB, Cfg::ZB);
+}
+// returns nullptr when TMA staging cannot be used (odd isize => global strides not 16-byte multiples, or
+// PPK_TMA=0): the plain kernels then do all the work
+static void *l_tma_create(const GridParams &g, const double *BASIS, const double *DBF) {
+  if (getenv("PPK_TMA") && atoi(getenv("PPK_TMA")) == 0) return nullptr;
+  if ((g.isize & 1) || g.nx < 32) return nullptr;
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return nullptr;
+  EncodeTiledFn enc = (EncodeTiledFn)fn;
+  TmaCtx *c = new TmaCtx();
+  bool ok = encode_cfg<EmfCfg<0>>(enc, &c->emfB[0], g, BASIS, NBASIS) && encode_cfg<EmfCfg<1>>(enc, &c->emfB[1], g, BASIS, NBASIS) &&
+            encode_cfg<EmfCfg<2>>(enc, &c->emfB[2], g, BASIS, NBASIS) && encode_cfg<EmfCfg<0>>(enc, &c->emfD[0], g, DBF, NDBF) &&
+            encode_cfg<EmfCfg<1>>(enc, &c->emfD[1], g, DBF, NDBF) && encode_cfg<EmfCfg<2>>(enc, &c->emfD[2], g, DBF, NDBF) &&
+            encode_cfg<FluxCfg<0>>(enc, &c->fluxB[0], g, BASIS, NBASIS) && encode_cfg<FluxCfg<1>>(enc, &c->fluxB[1], g, BASIS, NBASIS) &&
+            encode_cfg<FluxCfg<2>>(enc, &c->fluxB[2], g, BASIS, NBASIS);
+  ok = ok && cudaFuncSetAttribute(k_emf_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, EmfCfg<0>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_emf_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, EmfCfg<1>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_emf_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, EmfCfg<2>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_flux_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<0>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_flux_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<1>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_flux_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<2>::SMEM_BYTES) == cudaSuccess;
+  if (!ok) { delete c; return nullptr; }
+  return c;
+}
+static void l_tma_destroy(void *ctx) { delete (TmaCtx *)ctx; }
+
+template <int D>
+static void launch_flux(const GridParams &g, const double *BASIS, double *F, const TmaCtx *tma, cudaStream_t s) {
+  static const int minb = getenv("PPK_FLUX_MINB") ? atoi(getenv("PPK_FLUX_MINB")) : 5;
+  const int ni = g.nx + (D == 0), nj = g.ny + (D == 1), nk = g.nz + (D == 2);
+  int done = 0;  // x-columns covered by full TMA tiles
+  if (tma) {
+    using Cfg = FluxCfg<D>;
+    const int ntx = ni / Cfg::TX;
+    done = ntx * Cfg::TX;
+    dim3 grid(ntx, cdiv(nj, Cfg::TY), cdiv(nk, Cfg::TZ));
+    k_flux_tma<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(g, tma->fluxB[D], F);
+  }
+  if (done < ni) {
+    const int bs = 128;
+    dim3 grid(cdiv((long long)(ni - done) * nj, bs), (unsigned)nk);
+    if (minb == 4) k_flux<D, 4><<<grid, bs, 0, s>>>(g, BASIS, F, done, ni - done);
+    else if (minb == 6) k_flux<D, 6><<<grid, bs, 0, s>>>(g, BASIS, F, done, ni - done);
+    else k_flux<D, 5><<<grid, bs, 0, s>>>(g, BASIS, F, done, ni - done);
+  }
+}
+static void l_flux(const GridParams &g, int dir, const double *BASIS, double *F, const void *tma, cudaStream_t s) {
+  if (dir == 0) launch_flux<0>(g, BASIS, F, (const TmaCtx *)tma, s);
+  else if (dir == 1) launch_flux<1>(g, BASIS, F, (const TmaCtx *)tma, s);
+  else launch_flux<2>(g, BASIS, F, (const TmaCtx *)tma, s);
+}
+template <int E>
+static void launch_emf(const GridParams &g, const double *BASIS, const double *DBF, double *EMF, const TmaCtx *tma, cudaStream_t s) {
+  static const int minb = getenv("PPK_EMF_MINB") ? atoi(getenv("PPK_EMF_MINB")) : 5;
+  const int ni = g.nx + (E != 0), nj = g.ny + (E != 1), nk = g.nz + (E != 2);
+  int done = 0;
+  if (tma) {
+    using Cfg = EmfCfg<E>;
+    const int ntx = ni / Cfg::TX;
+    done = ntx * Cfg::TX;
+    dim3 grid(ntx, cdiv(nj, Cfg::TY), cdiv(nk, Cfg::TZ));
+    k_emf_tma<E><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(g, tma->emfB[E], tma->emfD[E], EMF);
+  }
+  if (done < ni) {
+    const int bs = 128;
+    dim3 grid(cdiv((long long)(ni - done) * nj, bs), (unsigned)nk);
+    if (minb == 4) k_emf<E, 4><<<grid, bs, 0, s>>>(g, BASIS, DBF, EMF, done, ni - done);
+    else if (minb == 6) k_emf<E, 6><<<grid, bs, 0, s>>>(g, BASIS, DBF, EMF, done, ni - done);
+    else k_emf<E, 5><<<grid, bs, 0, s>>>(g, BASIS, DBF, EMF, done, ni - done);
+  }
+}
+static void l_emf(const GridParams &g, int e, const double *BASIS, const double *DBF, double *EMF, const void *tma, cudaStream_t s) {
+  if (e == 0) launch_emf<0>(g, BASIS, DBF, EMF, (const TmaCtx *)tma, s);
+  else if (e == 1) launch_emf<1>(g, BASIS, DBF, EMF, (const TmaCtx *)tma, s);
+  else launch_emf<2>(g, BASIS, DBF, EMF, (const TmaCtx *)tma, s);
 }
 static void l_update(const GridParams &g, const StepState *st, const double *Uin, double *Uout, const double *Fx,
                      const double *Fy, const double *Fz, const double *EMF, cudaStream_t s) {
   const int bs = 256;
   dim3 grid(cdiv((long long)g.isize * g.jsize, bs), g.ksize);
   k_update<<<grid, bs, 0, s>>>(g, st, Uin, Uout, Fx, Fy, Fz, EMF);
+}
+static void l_consume(const GridParams &g, const StepState *st, const double *BASIS, const double *DBF, const double *Uin,
+                      double *Uout, int split, cudaStream_t s) {
+  dim3 block(CBX, CBY);
+  // z-chunks: as few as give >= ~8 waves of CTAs on 148 SMs x 2 CTAs (each chunk re-solves one plane of z-problems)
+  const long long tiles = (long long)cdiv(g.nx, CBX - 1) * cdiv(g.ny, CBY - 1);
+  int nchunk = (int)((8LL * 296 + tiles - 1) / tiles);
+  const int max_chunks = g.nz / 16 > 0 ? g.nz / 16 : 1;
+  if (nchunk > max_chunks) nchunk = max_chunks;
+  if (nchunk < 1) nchunk = 1;
+  const int zchunk = (g.nz + nchunk - 1) / nchunk;
+  dim3 grid(cdiv(g.nx, CBX - 1), cdiv(g.ny, CBY - 1), cdiv(g.nz, zchunk));
+  if (!split) k_consume<true, true><<<grid, block, 0, s>>>(g, st, BASIS, DBF, Uin, Uout, zchunk);
+  else {
+    k_consume<true, false><<<grid, block, 0, s>>>(g, st, BASIS, DBF, Uin, Uout, zchunk);
+    k_consume<false, true><<<grid, block, 0, s>>>(g, st, BASIS, DBF, Uin, Uout, zchunk);
+  }
 }
 static void l_diagnostics(const GridParams &g, const double *U, double *out9, cudaStream_t s) {
   const int bs = 256;
@@ -1115,7 +1553,7 @@ static const KernelTable table = {
 #else
   "fast",
 #endif
-  l_boundary, l_prim_dt, l_finalize_dt, l_advance_time, l_elec_dbf, l_trace, l_flux, l_emf, l_update, l_diagnostics, l_fastmath_selftest,
+  l_boundary, l_prim_dt, l_finalize_dt, l_advance_time, l_elec_dbf, l_trace, l_flux, l_emf, l_update, l_diagnostics, l_fastmath_selftest, l_consume, l_tma_create, l_tma_destroy,
 };
 
 }  // namespace PPK_NS

@@ -23,9 +23,10 @@ OT = "[OrszagTang]\nkt=1\n"
 BLAST = "[blast]\nradius=0.25\ndensity_in=1.0\ndensity_out=1.2\npressure_in=10.0\npressure_out=0.1\n"
 
 
-def make_solver(ini, exact=True):
+def make_solver(ini, exact=True, pipeline="fused"):
     p, t_end, nstep = ppk.params_from_ini(ini, exact=exact)
     s = ppk.Mhd3d(p)
+    s.set_pipeline(pipeline)
     s.upload(ppk.init_condition_from_ini(ini))
     s.set_time(0.0, t_end, 0)
     return s, nstep
@@ -41,10 +42,11 @@ def close_per_cell(a, b, rtol=1e-12):
         assert not bad.any(), f"var {v}: max abs diff {np.abs(a[v] - b[v]).max():.3e} (field max {np.abs(b[v]).max():.3e})"
 
 
+@pytest.mark.parametrize("pipeline", ["fused", "fused_split", "unfused"])
 @pytest.mark.parametrize("case", golden_cases())
-def test_exact_mode_bit_identical_to_reference(case):
+def test_exact_mode_bit_identical_to_reference(case, pipeline):
     g = np.load(f"{GOLDEN}/{case}.npz")
-    s, nstep = make_solver(str(g["ini"]), exact=True)
+    s, nstep = make_solver(str(g["ini"]), exact=True, pipeline=pipeline)
     assert np.array_equal(s.interior(), g["init"])
     s.step()
     t, dt, it = s.get_time()
@@ -57,10 +59,11 @@ def test_exact_mode_bit_identical_to_reference(case):
     s.close()
 
 
+@pytest.mark.parametrize("pipeline", ["fused", "unfused"])
 @pytest.mark.parametrize("case", golden_cases())
-def test_fast_mode_within_1e12_of_reference(case):
+def test_fast_mode_within_1e12_of_reference(case, pipeline):
     g = np.load(f"{GOLDEN}/{case}.npz")
-    s, nstep = make_solver(str(g["ini"]), exact=False)
+    s, nstep = make_solver(str(g["ini"]), exact=False, pipeline=pipeline)
     s.step()
     close_per_cell(s.interior(), g["step1"], 1e-12)
     s.run(nstep - 1)
@@ -78,10 +81,13 @@ def test_exact_mode_vs_oracle_with_intermediates(problem, n, extra, bounds, cfl,
     O = oracle_mod
     ini = O.make_ini(problem, n, nstepmax=4, extra=extra, bounds=bounds, cfl=cfl, tend=10.0)
     orc = O.Oracle(ini)
-    s, _ = make_solver(ini, exact=True)
+    s, _ = make_solver(ini, exact=True, pipeline="unfused")   # the pipeline that stores Fluxes_* and Emf
+    f, _ = make_solver(ini, exact=True, pipeline="fused")
     for step in range(4):
         orc.step()
         s.step()
+        f.step()
+        assert np.array_equal(f.interior(), orc.interior()), f"fused pipeline differs at step {step + 1}"
         t, dt, it = s.get_time()
         assert dt == orc.dt and t == orc.t, f"dt/t differ at step {step}: {dt} vs {orc.dt}"
         if step == 0:
@@ -108,6 +114,7 @@ def test_exact_mode_vs_oracle_with_intermediates(problem, n, extra, bounds, cfl,
     assert np.allclose(sums, so, rtol=1e-11, atol=1e-9), (sums, so)  # different summation order
     assert abs(divb - do) <= 1e-18 + 1e-12 * do, (divb, do)
     s.close()
+    f.close()
 
 
 def test_hundred_steps_conserved_sums_and_divb(oracle_mod):
