@@ -274,18 +274,33 @@ def run_ours(args):
     pk, pk_kind = peaks()
     algo_bytes = ALGO_BYTES_PER_CELL * float(n) ** 3  # per launch: one launch sweeps the rank's n^3 cells
     achieved = algo_bytes / (dom_ms * 1e-3) / 1e9
+    # DRAM bytes of the dominant kernel from the committed ncu --set full capture (same n), per launch
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "kernel_dram_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if tj.get("kernel") == dom and tj.get("n") == n:
-            traffic = tj.get("dram_bytes_per_launch")
+        if tj.get("n") == n:
+            traffic = tj.get("dram_bytes_per_launch", {}).get(dom)
+    # second roofline of this path: the FP64 pipe. Instructions per cell-update from the SASS of the
+    # kernels timed here (profiles/sass_counts.json), pipe peak measured on this pool's B200 by
+    # profiles/microbench/fp64_pipe.cu (17.0 T thread-instructions/s = 34 TFLOP/s)
+    fp64 = None
+    spath = os.path.join(ROOT, "profiles", "sass_counts.json")
+    if os.path.exists(spath):
+        per_cell = json.load(open(spath))["per_cell_update"]
+        rate = per_cell["fp64_pipe"] * cells / world * K / (ms * 1e-3)
+        fp64 = {"fp64_pipe_inst_per_cell_update": per_cell["fp64_pipe"], "all_inst_per_cell_update": per_cell["instructions"],
+                "achieved_Tinst_s": rate / 1e12, "peak_Tinst_s": 17.0, "frac": rate / 17.0e12,
+                "peak_source": "profiles/microbench/fp64_pipe.cu measured on B200 (DFMA, 16 warps/SM, ILP 4)"}
+    step_gbs = ALGO_BYTES_PER_CELL * cells / world * K / (ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind + " copy bandwidth",
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind + " copy bandwidth (burst)",
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": dom_ms,
-                "whole_step": {"achieved": ALGO_BYTES_PER_CELL * cells / world * K / (ms * 1e-3) / 1e9,
-                               "frac": ALGO_BYTES_PER_CELL * cells / world * K / (ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
-                "note": "the path is FP64-pipe bound (see DESIGN.md / profiles): HBM fraction is low by construction"}
+                "whole_step": {"achieved": step_gbs, "frac": step_gbs / pk["hbm_gbs"]},
+                "fp64_pipe": fp64,
+                "note": "128 algorithmic B per cell-update (read U^n, write U^n+1). The step needs ~3.0k FP64-pipe "
+                        "instructions per cell-update, so the FP64 pipe bounds it at ~5.7 Gcell/s = 11% of the HBM roofline; "
+                        "see DESIGN.md"}
 
     # ---- e2e leg: host buffers through the C ABI, H2D + step + D2H every step ------------------
     Ke = max(2, min(K, args.e2e_steps))
@@ -344,7 +359,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=256, help="cells per axis per GPU")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
-    ap.add_argument("--pipeline", default="fused", choices=["fused", "fused_split", "unfused"])
+    ap.add_argument("--pipeline", default="unfused", choices=["fused", "fused_split", "unfused"])
     ap.add_argument("--ref-n", type=int, default=128, help="grid of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")

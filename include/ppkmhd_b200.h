@@ -131,12 +131,13 @@ int ppk_mhd3d_halo_plan(const ppk_mhd3d_params *params, int capacity, ppk_halo_m
  * handle's own non-blocking stream. */
 int ppk_mhd3d_set_stream(ppk_mhd3d *handle, void *cuda_stream);
 /* Kernel schedule of one step (results are identical, bit for bit in exact mode):
- *   PPK_PIPELINE_FUSED (default): ghost fill | primitives + CFL | edge E + face-B slopes | Hancock trace |
- *       ONE consumer kernel = HLLD fluxes x,y,z + edge EMFs z,y,x + conservative and CT update (fluxes and EMFs
- *       stay on chip);
- *   PPK_PIPELINE_FUSED_SPLIT: the consumer as two kernels (fluxes + hydro update, EMFs + CT update);
- *   PPK_PIPELINE_UNFUSED: one kernel per flux direction / EMF component + an update kernel, storing
- *       Fluxes_x|y|z and Emf like the reference's v0 (what ppk_mhd3d_debug_array exposes). */
+ *   PPK_PIPELINE_UNFUSED (default, the fastest measured on B200): ghost fill | primitives + CFL | edge E +
+ *       face-B slopes | Hancock trace | one TMA-staged kernel per flux direction and EMF component | update;
+ *       stores Fluxes_x|y|z and Emf like the reference's v0 (what ppk_mhd3d_debug_array exposes);
+ *   PPK_PIPELINE_FUSED: after the trace, ONE z-marching consumer kernel = HLLD fluxes x,y,z + edge EMFs z,y,x +
+ *       conservative and CT update; fluxes and EMFs never reach HBM (2.2x less DRAM traffic for that part, but
+ *       slower today: see DESIGN.md);
+ *   PPK_PIPELINE_FUSED_SPLIT: that consumer as two kernels (fluxes + hydro update, EMFs + CT update). */
 enum ppk_pipeline { PPK_PIPELINE_UNFUSED = 0, PPK_PIPELINE_FUSED = 1, PPK_PIPELINE_FUSED_SPLIT = 2 };
 int ppk_mhd3d_set_pipeline(ppk_mhd3d *handle, int pipeline);
 /* Per-kernel CUDA-event timing (replaces the coarse timers of SolverBase.h:35-42 for profiling).
@@ -148,7 +149,7 @@ int ppk_mhd3d_kernel_times(ppk_mhd3d *handle, int capacity, const char **names, 
 /* Total number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 long ppk_mhd3d_launch_count(ppk_mhd3d *handle);
 /* Copy an internal device array to the host for tests: "U","U2","Q" (8 comps), "ElecField" (3),
- * "dbf" (6), "basis" (35), "Fluxes_x|y|z" (5), "Emf" (3). Returns the number of components. */
+ * "dbf" (6), "basis" (32), "Fluxes_x|y|z" (5), "Emf" (3). Returns the number of components. */
 int ppk_mhd3d_debug_array(ppk_mhd3d *handle, const char *name, double *host_out, int *ncomp);
 /* Bytes of device memory held by the handle. */
 long long ppk_mhd3d_device_bytes(ppk_mhd3d *handle);

@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path() -> str:
-    return os.path.join(HERE, "lib", "libppkmhd_b200.so")
+    # PPKMHD_B200_LIB: an alternative build of the same library (kernel-tuning experiments)
+    return os.environ.get("PPKMHD_B200_LIB") or os.path.join(HERE, "lib", "libppkmhd_b200.so")
 
 
 def build_library(verbose: bool = False) -> str:

@@ -116,7 +116,7 @@ struct ppk_mhd3d {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0, zlo = 0, zhi = 0;
   bool exch_lo = false, exch_hi = false;  // z faces filled by the halo exchange
-  int pipeline = PPK_PIPELINE_FUSED;
+  int pipeline = PPK_PIPELINE_UNFUSED;
 
   double *cur() { return U[host_iteration & 1]; }
   double *nxt() { return U[(host_iteration + 1) & 1]; }
@@ -254,6 +254,9 @@ int enqueue_step(ppk_mhd3d *h) {
   { Scope sc(h, KK_ELEC_DBF, s); h->kt->elec_dbf(g, Uin, h->Q, h->E, h->DBF, s); }
   { Scope sc(h, KK_TRACE, s); h->kt->trace(g, h->st, Uin, h->Q, h->E, h->BASIS, s); }
   if (h->pipeline == PPK_PIPELINE_UNFUSED) {
+    if (!h->F[0]) {  // flux / EMF arrays are allocated on first use of this pipeline
+      if (int rc = ppk_mhd3d_set_pipeline(h, PPK_PIPELINE_UNFUSED)) return rc;
+    }
     { Scope sc(h, KK_FLUX_X, s); h->kt->flux(g, 0, h->BASIS, h->F[0], h->tma, s); }
     { Scope sc(h, KK_FLUX_Y, s); h->kt->flux(g, 1, h->BASIS, h->F[1], h->tma, s); }
     { Scope sc(h, KK_FLUX_Z, s); h->kt->flux(g, 2, h->BASIS, h->F[2], h->tma, s); }

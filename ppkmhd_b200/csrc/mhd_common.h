@@ -10,15 +10,16 @@ enum { BC_UNDEFINED = 0, BC_DIRICHLET = 1, BC_NEUMANN = 2, BC_PERIODIC = 3, BC_C
 
 // "Trace basis": what ComputeTraceFunctor3D_MHD (MHDRunFunctors3D.h:543-856) would expand into
 // 18 stored states (144 doubles per cell). Every one of those states is an exact 1- or 2-addition
-// combination of these 35 numbers (MHDBaseFunctor3D.h:898-1112), so we store the 35 and rebuild a
+// combination of these 32 numbers (+ the 3 lower-face values of the +1 neighbours) (MHDBaseFunctor3D.h:898-1112), so we store the 32 and rebuild a
 // state in registers where a Riemann problem needs it.
 enum {
   BQ = 0,       // 8: half-step-updated cell-centred primitives r,p,u,v,w,A,B,C (order ID..IC)
   BSX = 8,      // 7: halved x-slopes  r,p,u,v,w,B,C
   BSY = 15,     // 7: halved y-slopes  r,p,u,v,w,A,C
   BSZ = 22,     // 7: halved z-slopes  r,p,u,v,w,A,B
-  BFACE = 29,   // 6: half-step-updated face fields AL,AR,BL,BR,CL,CR
-  NBASIS = 35
+  BFACE = 29,   // 3: half-step-updated LOWER-face fields AL,BL,CL (a cell's upper-face value is bitwise its +1
+                //    neighbour's lower-face value, so it is not stored)
+  NBASIS = 32
 };
 // limited transverse slopes of the face-centred field (DeltaA/B/C of the reference, only the
 // 6 non-trivial ones): dA/dy, dA/dz, dB/dx, dB/dz, dC/dx, dC/dy

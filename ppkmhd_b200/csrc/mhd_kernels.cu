@@ -8,7 +8,7 @@
 //   -DPPK_EXACT=0              : same source, FMA contraction allowed, the EMF upwind blend is a
 //                                branch instead of a 0/1-weighted sum of all branches.
 // Not a port of the Kokkos functors: the reference stores 18 reconstructed states per cell
-// (1152 B) between its trace and Riemann kernels; here the trace kernel stores a 35-number
+// (1152 B) between its trace and Riemann kernels; here the trace kernel stores a 32-number
 // "basis" per cell and the face-flux / edge-EMF kernels rebuild the states they need in registers
 // (each state component is an exact 1- or 2-addition combination of basis numbers).
 #include "mhd_common.h"
@@ -720,10 +720,11 @@ __global__ void __launch_bounds__(256) k_elec_dbf(const GridParams g, const doub
 
 // ComputeTraceFunctor3D_MHD (MHDRunFunctors3D.h:543-856): hydro slopes (slope_unsplit_hydro_3d,
 // MHDBaseFunctor3D.h:362-495) + Hancock half step (trace_unsplit_mhd_3d_simpler, :688-896).
-// Writes the 35-number basis on [2,size-2)^3 (the cells whose states a face or an edge consumes).
-__global__ void __launch_bounds__(128) k_trace(const GridParams g, const StepState *__restrict__ stp,
-                                               const double *__restrict__ U, const double *__restrict__ Q,
-                                               const double *__restrict__ E, double *__restrict__ BASIS) {
+// Writes the 32-number basis on [2,size-2)^3 (the cells whose states a face or an edge consumes).
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_trace(const GridParams g, const StepState *__restrict__ stp,
+                                                     const double *__restrict__ U, const double *__restrict__ Q,
+                                                     const double *__restrict__ E, double *__restrict__ BASIS) {
   const int k = 2 + blockIdx.y;
   const unsigned ni = g.isize - 4;
   const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -752,9 +753,8 @@ __global__ void __launch_bounds__(128) k_trace(const GridParams g, const StepSta
   const double dry = sy[ID], dpy = sy[IP], duy = sy[IU], dvy = sy[IV], dwy = sy[IW], dAy = sy[IA], dCy = sy[IC];
   const double drz = sz[ID], dpz = sz[IP], duz = sz[IU], dvz = sz[IV], dwz = sz[IW], dAz = sz[IA], dBz = sz[IB];
 
-  double AL = U[c + IA * N], AR = U[c + 1 + IA * N];
-  double BL = U[c + IB * N], BR = U[c + sj + IB * N];
-  double CL = U[c + IC * N], CR = U[c + sk + IC * N];
+  double AL = U[c + IA * N], BL = U[c + IB * N], CL = U[c + IC * N];
+  const double AR = U[c + 1 + IA * N], BR = U[c + sj + IB * N], CR = U[c + sk + IC * N];
   const double dAx = 0.5 * (AR - AL), dBy = 0.5 * (BR - BL), dCz = 0.5 * (CR - CL);
 
   const double gamma = g.gamma0;
@@ -781,18 +781,18 @@ __global__ void __launch_bounds__(128) k_trace(const GridParams g, const StepSta
 
   // face-centred field from the edge electric field, :872-877
   const double *Ex = E, *Ey = E + N, *Ez = E + 2 * N;
-  const double ELL = Ex[c], ELR = Ex[c + sk], ERL = Ex[c + sj], ERR = Ex[c + sj + sk];
-  const double FLL = Ey[c], FLR = Ey[c + sk], FRL = Ey[c + 1], FRR = Ey[c + 1 + sk];
-  const double GLL = Ez[c], GLR = Ez[c + sj], GRL = Ez[c + 1], GRR = Ez[c + 1 + sj];
+  // Only the three LOWER face values are produced: the upper-face value of a cell (AR = U_A(c+1) + sAR0 etc.)
+  // is the same expression on the same operands as the lower-face value of its +1 neighbour, hence the same bits,
+  // and the face / edge kernels read it there.
+  const double ELL = Ex[c], ELR = Ex[c + sk], ERL = Ex[c + sj];
+  const double FLL = Ey[c], FLR = Ey[c + sk], FRL = Ey[c + 1];
+  const double GLL = Ez[c], GLR = Ez[c + sj], GRL = Ez[c + 1];
   const double sAL0 = +(GLR - GLL) * dtdy * 0.5 - (FLR - FLL) * dtdz * 0.5;
-  const double sAR0 = +(GRR - GRL) * dtdy * 0.5 - (FRR - FRL) * dtdz * 0.5;
   const double sBL0 = -(GRL - GLL) * dtdx * 0.5 + (ELR - ELL) * dtdz * 0.5;
-  const double sBR0 = -(GRR - GLR) * dtdx * 0.5 + (ERR - ERL) * dtdz * 0.5;
   const double sCL0 = +(FRL - FLL) * dtdx * 0.5 - (ERL - ELL) * dtdy * 0.5;
-  const double sCR0 = +(FRR - FLR) * dtdx * 0.5 - (ERR - ELR) * dtdy * 0.5;
 
   r = r + sr0; u = u + su0; v = v + sv0; w = w + sw0; p = p + sp0; A = A + sA0; B = B + sB0; C = C + sC0;
-  AL = AL + sAL0; AR = AR + sAR0; BL = BL + sBL0; BR = BR + sBR0; CL = CL + sCL0; CR = CR + sCR0;
+  AL = AL + sAL0; BL = BL + sBL0; CL = CL + sCL0;
 
   double *Bs = BASIS + c;
   Bs[(BQ + ID) * N] = r; Bs[(BQ + IP) * N] = p; Bs[(BQ + IU) * N] = u; Bs[(BQ + IV) * N] = v; Bs[(BQ + IW) * N] = w;
@@ -803,8 +803,7 @@ __global__ void __launch_bounds__(128) k_trace(const GridParams g, const StepSta
   Bs[(BSY + 5) * N] = dAy; Bs[(BSY + 6) * N] = dCy;
   Bs[(BSZ + 0) * N] = drz; Bs[(BSZ + 1) * N] = dpz; Bs[(BSZ + 2) * N] = duz; Bs[(BSZ + 3) * N] = dvz; Bs[(BSZ + 4) * N] = dwz;
   Bs[(BSZ + 5) * N] = dAz; Bs[(BSZ + 6) * N] = dBz;
-  Bs[(BFACE + 0) * N] = AL; Bs[(BFACE + 1) * N] = AR; Bs[(BFACE + 2) * N] = BL; Bs[(BFACE + 3) * N] = BR;
-  Bs[(BFACE + 4) * N] = CL; Bs[(BFACE + 5) * N] = CR;
+  Bs[(BFACE + 0) * N] = AL; Bs[(BFACE + 1) * N] = BL; Bs[(BFACE + 2) * N] = CL;
 }
 
 // index, inside the 7 slopes of direction D, of field component m (m != D): r,p,u,v,w then the two
@@ -833,7 +832,7 @@ DEV void flux_face(const GridParams &g, const double *__restrict__ BASIS, long l
   const double unl = BL_[(BQ + IU + D) * N] + BL_[(SB + 2 + D) * N];
   const double t1l = BL_[(BQ + IU + T1) * N] + BL_[(SB + 2 + T1) * N];
   const double t2l = BL_[(BQ + IU + T2) * N] + BL_[(SB + 2 + T2) * N];
-  const double bnl = BL_[(BFACE + 2 * D + 1) * N];
+  const double bnl = BR_[(BFACE + D) * N];  // upper face of the left cell == lower face of the right cell
   const double b1l = BL_[(BQ + IA + T1) * N] + BL_[(SB + slope_b(D, T1)) * N];
   const double b2l = BL_[(BQ + IA + T2) * N] + BL_[(SB + slope_b(D, T2)) * N];
   // right state: q - slope (qp), normal field = lower-face value of the right cell
@@ -842,7 +841,7 @@ DEV void flux_face(const GridParams &g, const double *__restrict__ BASIS, long l
   const double unr = BR_[(BQ + IU + D) * N] - BR_[(SB + 2 + D) * N];
   const double t1r = BR_[(BQ + IU + T1) * N] - BR_[(SB + 2 + T1) * N];
   const double t2r = BR_[(BQ + IU + T2) * N] - BR_[(SB + 2 + T2) * N];
-  const double bnr = BR_[(BFACE + 2 * D) * N];
+  const double bnr = BR_[(BFACE + D) * N];
   const double b1r = BR_[(BQ + IA + T1) * N] - BR_[(SB + slope_b(D, T1)) * N];
   const double b2r = BR_[(BQ + IA + T2) * N] - BR_[(SB + slope_b(D, T2)) * N];
 
@@ -900,12 +899,12 @@ DEV Corner edge_state(const GridParams &g, const double *__restrict__ BASIS, con
   o.v = comb(BQ + IU + D2, 2 + D2, 2 + D2);
   // field component normal to d1: face value on side s1, plus/minus half its limited slope along d2
   {
-    const double face = Bc[(BFACE + 2 * D1 + (s1p ? 1 : 0)) * N];
+    const double face = Bc[(s1p ? st1 : 0) + (BFACE + D1) * N];  // upper face = lower face of the +d1 neighbour
     const double h = 0.5 * DBF[(s1p ? c + st1 : c) + dbf_idx(D1, D2) * N];
     o.a = face + (s2p ? h : -h);
   }
   {
-    const double face = Bc[(BFACE + 2 * D2 + (s2p ? 1 : 0)) * N];
+    const double face = Bc[(s2p ? st2 : 0) + (BFACE + D2) * N];
     const double h = 0.5 * DBF[(s2p ? c + st2 : c) + dbf_idx(D2, D1) * N];
     o.b = face + (s1p ? h : -h);
   }
@@ -1009,9 +1008,10 @@ DEV void tma_load_box(double *dst, const CUtensorMap *map, int x, int y, int z, 
 // A box must start on a 16-byte boundary of the innermost dimension, i.e. at an EVEN x index for fp64: tiles
 // start at i0 = gw + 32*bx (odd, gw = 3), so every configuration takes HX = 1 (box from i0-1, 34 wide) whether
 // or not its stencil reaches into x.
-template <int TY_, int TZ_, int HX_, int HY_, int HZ_, int NSLOT_>
+template <int TY_, int TZ_, int HX_, int HY_, int HZ_, int NSLOT_, int MINB_>
 struct TileCfg {
   static constexpr int TX = 32, TY = TY_, TZ = TZ_, HX = HX_, HY = HY_, HZ = HZ_, NSLOT = NSLOT_;
+  static constexpr int MINB = MINB_;  // CTAs per SM the register allocation aims at (measured best per kernel)
   static constexpr int XB = TX + 2 * HX;  // x extent padded to a 16-byte multiple (one unused column when HX = 1)
   static constexpr int YB = TY + HY, ZB = TZ + HZ;
   static constexpr int BOX = XB * YB * ZB;                          // doubles per component box
@@ -1019,16 +1019,20 @@ struct TileCfg {
   static constexpr int SMEM_BYTES = NSLOT * SLOT * 8;
   static constexpr int THREADS = TX * TY * TZ;
 };
+// Measured on B200 at 256^3 (profiles/r1_tuning_notes.md): the staged EMF kernels gain from more resident CTAs
+// (z-edges: 128-thread CTAs x5 at 96 registers 0.73 ms vs 0.92 ms for 256 x2; y-edges 256 x3 at 80 registers
+// 0.78 vs 0.91 ms); the x-edge tile (z halo + the alignment column) only fits twice in shared memory.
 template <int E> struct EmfCfg;  // edge direction E: halo of one cell along d1 and d2
-template <> struct EmfCfg<2> : TileCfg<8, 1, 1, 1, 0, 21> {};
-template <> struct EmfCfg<0> : TileCfg<4, 2, 1, 1, 1, 21> {};
-template <> struct EmfCfg<1> : TileCfg<4, 2, 1, 0, 1, 21> {};
+template <> struct EmfCfg<2> : TileCfg<4, 1, 1, 1, 0, 19, 5> {};
+template <> struct EmfCfg<0> : TileCfg<4, 2, 1, 1, 1, 19, 3> {};
+template <> struct EmfCfg<1> : TileCfg<4, 2, 1, 0, 1, 19, 3> {};
 template <int D> struct FluxCfg;  // face direction D: halo of one cell along D
-template <> struct FluxCfg<0> : TileCfg<8, 1, 1, 0, 0, 16> {};
-template <> struct FluxCfg<1> : TileCfg<8, 1, 1, 1, 0, 16> {};
-template <> struct FluxCfg<2> : TileCfg<4, 2, 1, 0, 1, 16> {};
+template <> struct FluxCfg<0> : TileCfg<8, 1, 1, 0, 0, 15, 3> {};
+template <> struct FluxCfg<1> : TileCfg<8, 1, 1, 1, 0, 15, 3> {};
+template <> struct FluxCfg<2> : TileCfg<4, 2, 1, 0, 1, 15, 3> {};
 
-// component (row of the 4-D tensor) staged in slot s of the EMF kernel; slots 19,20 come from DBF
+// component (row of the 4-D tensor) staged in slot s of the EMF kernel: 0-4 q, 5-9 slopes along d1, 10-14 slopes
+// along d2, 15/16 lower-face field normal to d1/d2; slots 17,18 come from DBF
 template <int E>
 DEV constexpr int emf_slot_comp(int s) {
   constexpr int D1 = (E + 1) % 3, D2 = (E + 2) % 3;
@@ -1039,8 +1043,8 @@ DEV constexpr int emf_slot_comp(int s) {
   if (s < 5) return q[s];
   if (s < 10) return S1 + i1[s - 5];
   if (s < 15) return S2 + i2[s - 10];
-  if (s < 19) return BFACE + 2 * (s < 17 ? D1 : D2) + ((s - 15) & 1);
-  return s == 19 ? dbf_idx(D1, D2) : dbf_idx(D2, D1);
+  if (s < 17) return BFACE + (s == 15 ? D1 : D2);
+  return s == 17 ? dbf_idx(D1, D2) : dbf_idx(D2, D1);
 }
 
 // edge_state<E> reading the staged tile; `o` = offset of the cell inside a component box
@@ -1059,13 +1063,13 @@ DEV Corner edge_state_smem(const GridParams &g, const double *__restrict__ sm, i
   c.u = comb(2);
   c.v = comb(3);
   {
-    const double face = sm[(15 + (s1p ? 1 : 0)) * S + o];
-    const double h = 0.5 * sm[19 * S + (s1p ? o + st[D1] : o)];
+    const double face = sm[15 * S + (s1p ? o + st[D1] : o)];
+    const double h = 0.5 * sm[17 * S + (s1p ? o + st[D1] : o)];
     c.a = face + (s2p ? h : -h);
   }
   {
-    const double face = sm[(17 + (s2p ? 1 : 0)) * S + o];
-    const double h = 0.5 * sm[20 * S + (s2p ? o + st[D2] : o)];
+    const double face = sm[16 * S + (s2p ? o + st[D2] : o)];
+    const double h = 0.5 * sm[18 * S + (s2p ? o + st[D2] : o)];
     c.b = face + (s1p ? h : -h);
   }
   c.c = comb(4);
@@ -1073,7 +1077,7 @@ DEV Corner edge_state_smem(const GridParams &g, const double *__restrict__ sm, i
 }
 
 template <int E>
-__global__ void __launch_bounds__(EmfCfg<E>::THREADS, 2)
+__global__ void __launch_bounds__(EmfCfg<E>::THREADS, EmfCfg<E>::MINB)
   k_emf_tma(const GridParams g, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapD,
             double *__restrict__ EMF) {
   using Cfg = EmfCfg<E>;
@@ -1089,7 +1093,7 @@ __global__ void __launch_bounds__(EmfCfg<E>::THREADS, 2)
     mbar_expect_tx(&bar, Cfg::NSLOT * Cfg::BOX * 8);
 #pragma unroll
     for (int s = 0; s < Cfg::NSLOT; ++s)
-      tma_load_box(sm + s * Cfg::SLOT, s < 19 ? &mapB : &mapD, i0 - Cfg::HX, j0 - Cfg::HY, k0 - Cfg::HZ, emf_slot_comp<E>(s), &bar);
+      tma_load_box(sm + s * Cfg::SLOT, s < 17 ? &mapB : &mapD, i0 - Cfg::HX, j0 - Cfg::HY, k0 - Cfg::HZ, emf_slot_comp<E>(s), &bar);
   }
   mbar_wait(&bar, 0);
   const int i = i0 + tx, j = j0 + ty, k = k0 + tz;
@@ -1106,7 +1110,7 @@ __global__ void __launch_bounds__(EmfCfg<E>::THREADS, 2)
 }
 
 // component staged in slot s of the flux kernel: 0-6 q (r,p,un,t1,t2,b1,b2), 7-13 their slopes along D,
-// 14 lower-face normal field (right state), 15 upper-face normal field (left state)
+// 14 lower-face normal field of the right cell (= the upper-face value of the left cell)
 template <int D>
 DEV constexpr int flux_slot_comp(int s) {
   constexpr int T1 = D == 0 ? 1 : (D == 1 ? 0 : 1), T2 = D == 0 ? 2 : (D == 1 ? 2 : 0);
@@ -1115,11 +1119,11 @@ DEV constexpr int flux_slot_comp(int s) {
   const int sl[7] = {0, 1, 2 + D, 2 + T1, 2 + T2, slope_b(D, T1), slope_b(D, T2)};
   if (s < 7) return q[s];
   if (s < 14) return SB + sl[s - 7];
-  return BFACE + 2 * D + (s - 14);
+  return BFACE + D;
 }
 
 template <int D>
-__global__ void __launch_bounds__(FluxCfg<D>::THREADS, 3)
+__global__ void __launch_bounds__(FluxCfg<D>::THREADS, FluxCfg<D>::MINB)
   k_flux_tma(const GridParams g, const __grid_constant__ CUtensorMap mapB, double *__restrict__ F) {
   using Cfg = FluxCfg<D>;
   extern __shared__ __align__(128) double sm[];
@@ -1148,7 +1152,7 @@ __global__ void __launch_bounds__(FluxCfg<D>::THREADS, 3)
   const double unl = sm[2 * S + oL] + sm[9 * S + oL];
   const double t1l = sm[3 * S + oL] + sm[10 * S + oL];
   const double t2l = sm[4 * S + oL] + sm[11 * S + oL];
-  const double bnl = sm[15 * S + oL];
+  const double bnl = sm[14 * S + oR];
   const double b1l = sm[5 * S + oL] + sm[12 * S + oL];
   const double b2l = sm[6 * S + oL] + sm[13 * S + oL];
   const double rr = fmax(g.smallr, sm[0 * S + oR] - sm[7 * S + oR]);
@@ -1270,15 +1274,6 @@ __global__ void __launch_bounds__(CBX *CBY, 2)
   for (int v = 0; v < NBVAR; ++v) u[v] = 0.0;
 
   for (int k = k0; k <= k1; ++k, c += sk) {
-    // the plane above is first touched one iteration from now: start its DRAM -> L2 transfer now (the row and
-    // column of cells below the tile are prefetched by the neighbouring CTAs' threads)
-    if (k < k1 && in_i && in_j) {
-      const double *nb = BASIS + c + sk, *nd = DBF + c + sk;
-#pragma unroll
-      for (int v = 0; v < NBASIS; ++v) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + v * N));
-#pragma unroll
-      for (int v = 0; v < NDBF; ++v) asm volatile("prefetch.global.L2 [%0];" ::"l"(nd + v * N));
-    }
     double fz[NFLUX] = {0, 0, 0, 0, 0}, ey = 0.0, ex = 0.0;
     if (do_fz) flux_face<2>(g, BASIS, c, fz[0], fz[1], fz[2], fz[3], fz[4]);
     if (do_ey) ey = emf_edge<1>(g, BASIS, DBF, c);
@@ -1418,7 +1413,12 @@ static void l_trace(const GridParams &g, const StepState *st, const double *U, c
                     double *BASIS, cudaStream_t s) {
   const int bs = 128;
   dim3 grid(cdiv((long long)(g.isize - 4) * (g.jsize - 4), bs), g.ksize - 4);
-  k_trace<<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS);
+  static const int minb = getenv("PPK_TRACE_MINB") ? atoi(getenv("PPK_TRACE_MINB")) : 4;
+  if (minb == 5) k_trace<5><<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS);
+  else if (minb == 6) k_trace<6><<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS);
+  else if (minb == 8) k_trace<8><<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS);
+  else if (minb == 3) k_trace<3><<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS);
+  else k_trace<4><<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS);
 }
 // ---- TMA tensor maps (host) ---------------------------------------------------------------------
 struct TmaCtx {
@@ -1471,7 +1471,10 @@ static void launch_flux(const GridParams &g, const double *BASIS, double *F, con
   int done = 0;  // x-columns covered by full TMA tiles
   if (tma) {
     using Cfg = FluxCfg<D>;
-    const int ntx = ni / Cfg::TX;
+    // a remainder of a few columns would make the plain kernel fetch 32-byte sectors for 8 or 16 useful bytes:
+    // hand it a whole extra tile instead so that its rows stay coalesced
+    int ntx = ni / Cfg::TX;
+    if (ni % Cfg::TX != 0 && ni % Cfg::TX < 8 && ntx > 1) --ntx;
     done = ntx * Cfg::TX;
     dim3 grid(ntx, cdiv(nj, Cfg::TY), cdiv(nk, Cfg::TZ));
     k_flux_tma<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(g, tma->fluxB[D], F);
@@ -1496,7 +1499,8 @@ static void launch_emf(const GridParams &g, const double *BASIS, const double *D
   int done = 0;
   if (tma) {
     using Cfg = EmfCfg<E>;
-    const int ntx = ni / Cfg::TX;
+    int ntx = ni / Cfg::TX;
+    if (ni % Cfg::TX != 0 && ni % Cfg::TX < 8 && ntx > 1) --ntx;
     done = ntx * Cfg::TX;
     dim3 grid(ntx, cdiv(nj, Cfg::TY), cdiv(nk, Cfg::TZ));
     k_emf_tma<E><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(g, tma->emfB[E], tma->emfD[E], EMF);

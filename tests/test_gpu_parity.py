@@ -23,7 +23,7 @@ OT = "[OrszagTang]\nkt=1\n"
 BLAST = "[blast]\nradius=0.25\ndensity_in=1.0\ndensity_out=1.2\npressure_in=10.0\npressure_out=0.1\n"
 
 
-def make_solver(ini, exact=True, pipeline="fused"):
+def make_solver(ini, exact=True, pipeline="unfused"):
     p, t_end, nstep = ppk.params_from_ini(ini, exact=exact)
     s = ppk.Mhd3d(p)
     s.set_pipeline(pipeline)
