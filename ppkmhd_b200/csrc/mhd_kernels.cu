@@ -39,16 +39,26 @@ DEV long long cidx(const GridParams &g, int i, int j, int k) {
 // device math
 // ---------------------------------------------------------------------------------------------
 
+// min/max of the floors and limiters: the exact build keeps fmin/fmax (the reference's calls); the fast build uses
+// a comparison + select (3 instructions instead of the 6-7 of fmin/fmax with their NaN-quieting path on sm_100)
+#if PPK_EXACT
+DEV double vmax(double a, double b) { return fmax(a, b); }
+DEV double vmin(double a, double b) { return fmin(a, b); }
+#else
+DEV double vmax(double a, double b) { return a > b ? a : b; }
+DEV double vmin(double a, double b) { return a < b ? a : b; }
+#endif
+
 // TVD limited slope, MHDBaseFunctor3D.h:280-288 (hydro) and :605-665 (face B)
 DEV double limited_slope(double st, double q, double qplus, double qminus) {
   const double dlft = st * (q - qminus);
   const double drgt = st * (qplus - q);
   const double dcen = 0.5 * (qplus - qminus);
   const double dsgn = (dcen >= 0.0) ? 1.0 : -1.0;
-  const double slop = fmin(fabs(dlft), fabs(drgt));
+  const double slop = vmin(fabs(dlft), fabs(drgt));
   double dlim = slop;
   if ((dlft * drgt) <= 0.0) dlim = 0.0;
-  return dsgn * fmin(dlim, fabs(dcen));
+  return dsgn * vmin(dlim, fabs(dcen));
 }
 
 // find_speed_fast<dir>, mhd_utils.h:89-117; `n` is the field component normal to the direction
@@ -84,6 +94,37 @@ DEV double frsqrt(double x) {
 }
 // sqrt for x >= 0 (x == 0 must give 0: the clamped discriminant of the fast speed can vanish)
 DEV double fsqrt(double x) { return x * frsqrt(fmax(x, 1e-300)); }
+// Comparison-select min/max (DSETP + 2 SEL): fmin/fmax() cost 6-7 instructions each on sm_100 because of their
+// NaN-quieting path, and the fast build has ~60 of them per edge. Arguments here are never NaN.
+DEV double dmax(double a, double b) { return a > b ? a : b; }
+DEV double dmin(double a, double b) { return a < b ? a : b; }
+// sqrt of a quantity that is mathematically >= 0 but may come out <= 0 by round-off (the discriminant of the fast
+// speed): everything below the smallest normal, including negatives, is replaced by 2^-1000 (sqrt = 1e-150 ~ 0)
+// with 3 integer-pipe instructions on the high word, no FP64-pipe slot.
+DEV double fsqrt_clamped(double x) {
+  const int hi = __double2hiint(x);
+  const bool tiny = hi < 0x00100000;  // negative doubles have a negative high word
+  const double xc = __hiloint2double(tiny ? 0x01700000 : hi, tiny ? 0 : __double2loint(x));
+  return xc * frsqrt(xc);
+}
+// max of POSITIVE doubles on the integer pipe (positive doubles order like their bit patterns): keeps the
+// comparison chains of the squared wave speeds off the FP64 pipe, which bounds the EMF kernels
+DEV double pmax(double a, double b) { return __double_as_longlong(a) > __double_as_longlong(b) ? a : b; }
+DEV double pmax4(double a0, double a1, double a2, double a3) { return pmax(pmax(a0, a1), pmax(a2, a3)); }
+DEV double pmax5(double a0, double a1, double a2, double a3, double a4) { return pmax(pmax4(a0, a1, a2, a3), a4); }
+// sqrt of a strictly positive normal number
+DEV double fsqrt_pos(double x) { return x * frsqrt(x); }
+// max(x, 0) / min(x, 0) on the sign bit
+DEV double clamp_lo0(double x) {
+  const int hi = __double2hiint(x);
+  const int m = ~(hi >> 31);
+  return __hiloint2double(hi & m, __double2loint(x) & m);
+}
+DEV double clamp_hi0(double x) {
+  const int hi = __double2hiint(x);
+  const int m = hi >> 31;
+  return __hiloint2double(hi & m, __double2loint(x) & m);
+}
 
 // Fast-arithmetic variant of riemann_hlld (same algebra as RiemannSolvers_MHD.h:133-367, evaluated with
 // shared reciprocals: fp64 '/' and sqrt cost ~10 FP64-pipe instructions each and were 3/4 of the kernel).
@@ -112,11 +153,11 @@ DEV void riemann_hlld_fast(double gamma0, double rl, double pl, double ul, doubl
   const double irl = frcp(rl), irr = frcp(rr);
   const double c2l = gamma0 * pl * irl, d2l = 0.5 * (2.0 * emagl * irl + c2l);
   const double c2r = gamma0 * pr * irr, d2r = 0.5 * (2.0 * emagr * irr + c2r);
-  const double cf2l = d2l + fsqrt(fmax(d2l * d2l - c2l * a2 * irl, 0.0));
-  const double cf2r = d2r + fsqrt(fmax(d2r * d2r - c2r * a2 * irr, 0.0));
-  const double cfmax = fsqrt(fmax(cf2l, cf2r));
-  const double sl = fmin(ul, ur) - cfmax;
-  const double sr = fmax(ul, ur) + cfmax;
+  const double cf2l = d2l + fsqrt_clamped(d2l * d2l - c2l * a2 * irl);
+  const double cf2r = d2r + fsqrt_clamped(d2r * d2r - c2r * a2 * irr);
+  const double cfmax = fsqrt_pos(pmax(cf2l, cf2r));
+  const double sl = dmin(ul, ur) - cfmax;
+  const double sr = dmax(ul, ur) + cfmax;
 
   const double rcl = rl * (ul - sl);
   const double rcr = rr * (sr - ur);
@@ -337,13 +378,13 @@ DEV double mag_riemann2d_hlld_fast(double gamma0, double smallc, const Corner &L
     const double c2 = gamma0 * q.p * ir;
     const double d2 = 0.5 * (m2 * ir + c2);
     const double dd = d2 * d2, k = c2 * ir;
-    cx2 = d2 + fsqrt(fmax(dd - k * q.a * q.a, 0.0));
-    cy2 = d2 + fsqrt(fmax(dd - k * q.b * q.b, 0.0));
+    cx2 = d2 + fsqrt_clamped(dd - k * q.a * q.a);
+    cy2 = d2 + fsqrt_clamped(dd - k * q.b * q.b);
   };
   double xLL, yLL, xLR, yLR, xRL, yRL, xRR, yRR;
   cf2(LL, iLL, m2LL, xLL, yLL); cf2(LR, iLR, m2LR, xLR, yLR); cf2(RL, iRL, m2RL, xRL, yRL); cf2(RR, iRR, m2RR, xRR, yRR);
-  const double cxmax = fsqrt(max4(xLL, xLR, xRL, xRR));
-  const double cymax = fsqrt(max4(yLL, yLR, yRL, yRR));
+  const double cxmax = fsqrt_pos(pmax4(xLL, xLR, xRL, xRR));
+  const double cymax = fsqrt_pos(pmax4(yLL, yLR, yRL, yRR));
   const double SL = min4(LL.u, LR.u, RL.u, RR.u) - cxmax;
   const double SR = max4(LL.u, LR.u, RL.u, RR.u) + cxmax;
   const double SB = min4(LL.v, LR.v, RL.v, RR.v) - cymax;
@@ -370,15 +411,15 @@ DEV double mag_riemann2d_hlld_fast(double gamma0, double smallc, const Corner &L
   const double byLL = LL.b * LL.b * iLL * frcp(gyLL), byLR = LR.b * LR.b * iLR * frcp(gyLR);
   const double byRL = RL.b * RL.b * iRL * frcp(gyRL), byRR = RR.b * RR.b * iRR * frcp(gyRR);
   const double sc2 = smallc * smallc;
-  const double calfvenL = fsqrt(max5(axLR, axLR * gyLR, axLL, axLL * gyLL, sc2));
-  const double calfvenR = fsqrt(max5(axRR, axRR * gyRR, axRL, axRL * gyRL, sc2));
-  const double calfvenB = fsqrt(max5(byLL, byLL * gxLL, byRL, byRL * gxRL, sc2));
-  const double calfvenT = fsqrt(max5(byLR, byLR * gxLR, byRR, byRR * gxRR, sc2));
+  const double calfvenL = fsqrt_pos(pmax5(axLR, axLR * gyLR, axLL, axLL * gyLL, sc2));
+  const double calfvenR = fsqrt_pos(pmax5(axRR, axRR * gyRR, axRL, axRL * gyRL, sc2));
+  const double calfvenB = fsqrt_pos(pmax5(byLL, byLL * gxLL, byRL, byRL * gxRL, sc2));
+  const double calfvenT = fsqrt_pos(pmax5(byLR, byLR * gxLR, byRR, byRR * gxRR, sc2));
 
-  const double SAL = fmin(ustar - calfvenL, 0.0);
-  const double SAR = fmax(ustar + calfvenR, 0.0);
-  const double SAB = fmin(vstar - calfvenB, 0.0);
-  const double SAT = fmax(vstar + calfvenT, 0.0);
+  const double SAL = clamp_hi0(ustar - calfvenL);
+  const double SAR = clamp_lo0(ustar + calfvenR);
+  const double SAB = clamp_hi0(vstar - calfvenB);
+  const double SAT = clamp_lo0(vstar + calfvenT);
 
   const bool SB_pos = !signbit(SB), ST_pos = !signbit(ST), SL_pos = !signbit(SL), SR_pos = !signbit(SR);
   if (SB_pos) {
@@ -609,7 +650,7 @@ __global__ void __launch_bounds__(256) k_prim_dt(const GridParams g, const doubl
     const double fa1 = U[c + 1 + IA * N];
     const double fb1 = U[c + g.isize + IB * N];
     const double fc1 = U[c + (long long)g.isize * g.jsize + IC * N];
-    const double r = fmax(ur, g.smallr);
+    const double r = vmax(ur, g.smallr);
 #if PPK_EXACT
     const double u = mu / r, v = mv / r, w = mw / r;
 #else
@@ -624,7 +665,7 @@ __global__ void __launch_bounds__(256) k_prim_dt(const GridParams g, const doubl
 #else
     const double eint = (ue - emag) * ir - eken;
 #endif
-    const double p = fmax((g.gamma0 - 1.0) * r * eint, r * g.smallp);
+    const double p = vmax((g.gamma0 - 1.0) * r * eint, r * g.smallp);
     Q[c + ID * N] = r; Q[c + IP * N] = p; Q[c + IU * N] = u; Q[c + IV * N] = v; Q[c + IW * N] = w;
     Q[c + IA * N] = A; Q[c + IB * N] = B; Q[c + IC * N] = C;
     const int gw = g.gw;
@@ -638,9 +679,9 @@ __global__ void __launch_bounds__(256) k_prim_dt(const GridParams g, const doubl
       inv = vx / g.dx + vy / g.dy + vz / g.dz;
 #else
       const double c2 = g.gamma0 * p * ir, d2 = 0.5 * (2.0 * emag * ir + c2), dd = d2 * d2, kk = c2 * ir;
-      const double vx = fsqrt(d2 + fsqrt(fmax(dd - kk * A * A, 0.0))) + fabs(u);
-      const double vy = fsqrt(d2 + fsqrt(fmax(dd - kk * B * B, 0.0))) + fabs(v);
-      const double vz = fsqrt(d2 + fsqrt(fmax(dd - kk * C * C, 0.0))) + fabs(w);
+      const double vx = fsqrt_pos(d2 + fsqrt_clamped(dd - kk * A * A)) + fabs(u);
+      const double vy = fsqrt_pos(d2 + fsqrt_clamped(dd - kk * B * B)) + fabs(v);
+      const double vz = fsqrt_pos(d2 + fsqrt_clamped(dd - kk * C * C)) + fabs(w);
       inv = vx * g.idx + vy * g.idy + vz * g.idz;
 #endif
     }
@@ -827,8 +868,8 @@ DEV void flux_face(const GridParams &g, const double *__restrict__ BASIS, long l
   const double *BL_ = BASIS + cL, *BR_ = BASIS + cR;
 
   // left state: q + slope (qm), normal field = upper-face value of the left cell
-  const double rl = fmax(g.smallr, BL_[(BQ + ID) * N] + BL_[(SB + 0) * N]);
-  const double pl = fmax(g.smallp, BL_[(BQ + IP) * N] + BL_[(SB + 1) * N]);
+  const double rl = vmax(g.smallr, BL_[(BQ + ID) * N] + BL_[(SB + 0) * N]);
+  const double pl = vmax(g.smallp, BL_[(BQ + IP) * N] + BL_[(SB + 1) * N]);
   const double unl = BL_[(BQ + IU + D) * N] + BL_[(SB + 2 + D) * N];
   const double t1l = BL_[(BQ + IU + T1) * N] + BL_[(SB + 2 + T1) * N];
   const double t2l = BL_[(BQ + IU + T2) * N] + BL_[(SB + 2 + T2) * N];
@@ -836,8 +877,8 @@ DEV void flux_face(const GridParams &g, const double *__restrict__ BASIS, long l
   const double b1l = BL_[(BQ + IA + T1) * N] + BL_[(SB + slope_b(D, T1)) * N];
   const double b2l = BL_[(BQ + IA + T2) * N] + BL_[(SB + slope_b(D, T2)) * N];
   // right state: q - slope (qp), normal field = lower-face value of the right cell
-  const double rr = fmax(g.smallr, BR_[(BQ + ID) * N] - BR_[(SB + 0) * N]);
-  const double pr = fmax(g.smallp, BR_[(BQ + IP) * N] - BR_[(SB + 1) * N]);
+  const double rr = vmax(g.smallr, BR_[(BQ + ID) * N] - BR_[(SB + 0) * N]);
+  const double pr = vmax(g.smallp, BR_[(BQ + IP) * N] - BR_[(SB + 1) * N]);
   const double unr = BR_[(BQ + IU + D) * N] - BR_[(SB + 2 + D) * N];
   const double t1r = BR_[(BQ + IU + T1) * N] - BR_[(SB + 2 + T1) * N];
   const double t2r = BR_[(BQ + IU + T2) * N] - BR_[(SB + 2 + T2) * N];
@@ -893,8 +934,8 @@ DEV Corner edge_state(const GridParams &g, const double *__restrict__ BASIS, con
     return Bc[qi * N] + ((s1p ? a : -a) + (s2p ? b : -b));
   };
   Corner o;
-  o.r = fmax(g.smallr, comb(BQ + ID, 0, 0));
-  o.p = fmax(g.smallp, comb(BQ + IP, 1, 1));
+  o.r = vmax(g.smallr, comb(BQ + ID, 0, 0));
+  o.p = vmax(g.smallp, comb(BQ + IP, 1, 1));
   o.u = comb(BQ + IU + D1, 2 + D1, 2 + D1);
   o.v = comb(BQ + IU + D2, 2 + D2, 2 + D2);
   // field component normal to d1: face value on side s1, plus/minus half its limited slope along d2
@@ -1058,8 +1099,8 @@ DEV Corner edge_state_smem(const GridParams &g, const double *__restrict__ sm, i
     return sm[sq * S + o] + ((s1p ? a : -a) + (s2p ? b : -b));
   };
   Corner c;
-  c.r = fmax(g.smallr, comb(0));
-  c.p = fmax(g.smallp, comb(1));
+  c.r = vmax(g.smallr, comb(0));
+  c.p = vmax(g.smallp, comb(1));
   c.u = comb(2);
   c.v = comb(3);
   {
@@ -1147,16 +1188,16 @@ __global__ void __launch_bounds__(FluxCfg<D>::THREADS, FluxCfg<D>::MINB)
   constexpr int S = Cfg::SLOT;
   const int oR = (tx + Cfg::HX) + Cfg::XB * ((ty + Cfg::HY) + Cfg::YB * (tz + Cfg::HZ)), oL = oR - st[D];
   // left state: q + slope (qm) of the cell below the face; right state: q - slope (qp) of the cell above
-  const double rl = fmax(g.smallr, sm[0 * S + oL] + sm[7 * S + oL]);
-  const double pl = fmax(g.smallp, sm[1 * S + oL] + sm[8 * S + oL]);
+  const double rl = vmax(g.smallr, sm[0 * S + oL] + sm[7 * S + oL]);
+  const double pl = vmax(g.smallp, sm[1 * S + oL] + sm[8 * S + oL]);
   const double unl = sm[2 * S + oL] + sm[9 * S + oL];
   const double t1l = sm[3 * S + oL] + sm[10 * S + oL];
   const double t2l = sm[4 * S + oL] + sm[11 * S + oL];
   const double bnl = sm[14 * S + oR];
   const double b1l = sm[5 * S + oL] + sm[12 * S + oL];
   const double b2l = sm[6 * S + oL] + sm[13 * S + oL];
-  const double rr = fmax(g.smallr, sm[0 * S + oR] - sm[7 * S + oR]);
-  const double pr = fmax(g.smallp, sm[1 * S + oR] - sm[8 * S + oR]);
+  const double rr = vmax(g.smallr, sm[0 * S + oR] - sm[7 * S + oR]);
+  const double pr = vmax(g.smallp, sm[1 * S + oR] - sm[8 * S + oR]);
   const double unr = sm[2 * S + oR] - sm[9 * S + oR];
   const double t1r = sm[3 * S + oR] - sm[10 * S + oR];
   const double t2r = sm[4 * S + oR] - sm[11 * S + oR];
