@@ -87,30 +87,77 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe). NVML is polled from a thread
+    every few ms (the timed region of a default run is ~150 ms, shorter than nvidia-smi's start-up); `nvidia-smi
+    --query-gpu` with the same fields is the fallback when the NVML binding is missing."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index=0, period_s=0.004):
+        self.index, self.period = index, period_s
+        self.sm, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self.stop_flag, self.thread, self.nvml, self.proc, self.rows = threading.Event(), None, None, None, []
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.index])
+            except Exception:
+                pass
+        return self.index
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml as N
+
+            N.nvmlInit()
+            self.nvml = N
+            self.handle = N.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(self.handle, N.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self._physical_index()}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        N = self.nvml
+        names = ((N.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"), (N.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                 (N.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"), (N.nvmlClocksEventReasonSwPowerCap, "sw_power_cap"))
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(self.handle, N.NVML_CLOCK_SM)))
+                mask = N.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                for bit, nm in names:
+                    if mask & bit:
+                        self.reasons.add(nm)
+                self.power.append(N.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag.set()
+            self.thread.join()
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                    "samples": len(sm), "power_w_max": max(self.power) if self.power else None, "source": "nvml"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
@@ -126,7 +173,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -303,21 +350,62 @@ def run_ours(args):
                         "see DESIGN.md"}
 
     # ---- e2e leg: host buffers through the C ABI, H2D + step + D2H every step ------------------
+    # Every step is one batch: upload a full host state (pinned), advance it one step, download the full result.
+    # N=1: `depth` solver handles are in flight, each on its own stream, so that the download of batch i overlaps the
+    # upload of batch i+1 and the step of the batch between them (PCIe is full duplex; the copies bound the leg).
+    # N>1: one handle (one NCCL communicator per rank), the three phases run back to back.
     Ke = max(2, min(K, args.e2e_steps))
+    nbytes = int(np.prod(p.shape)) * 8
+    depth = args.e2e_depth if world == 1 else 1
+    e2e_solvers, e2e_streams = [solver], [stream]
+    for _ in range(depth - 1):
+        s2 = ppk.Mhd3d(p)
+        s2.set_pipeline(args.pipeline)
+        st2 = torch.cuda.Stream()
+        s2.set_stream(st2.cuda_stream)
+        s2.set_time(0.0, t_end, 0)
+        e2e_solvers.append(s2)
+        e2e_streams.append(st2)
+    host_in = [host] + [torch.empty(p.shape, dtype=torch.float64).pin_memory() for _ in range(depth - 1)]
+    host_out = [torch.empty(p.shape, dtype=torch.float64).pin_memory() for _ in range(depth)]
+    for hb in host_in[1:]:
+        hb.copy_(host)
+
+    def e2e_pass(nsteps):
+        for it in range(nsteps):
+            sv = e2e_solvers[it % depth]
+            sv.synchronize()  # batch it-depth is back on the host: its buffers are free again
+            sv.upload(host_in[it % depth].data_ptr())
+            sv.step()
+            sv.download_async(host_out[it % depth].data_ptr())
+        for sv in e2e_solvers:
+            sv.synchronize()
+
+    e2e_pass(depth)  # warm the extra handles (first-touch allocations, flux arrays)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record(stream)
-    for _ in range(Ke):
-        solver.upload(host.data_ptr())
-        solver.step()
-        solver.download(host.data_ptr())
-    f1.record(stream)
+    join = torch.cuda.Stream()
+    f0.record(join)
+    for st_ in e2e_streams:
+        st_.wait_stream(join)  # nothing of the timed region starts before f0
+    w0 = time.perf_counter()
+    e2e_pass(Ke)
+    for st_ in e2e_streams:
+        join.wait_stream(st_)
+    f1.record(join)
     barrier()
+    w1 = time.perf_counter()
     ems = max_over_ranks(f0.elapsed_time(f1))
-    nbytes = int(np.prod(p.shape)) * 8
+    assert np.all(np.isfinite(host_out[0].numpy()[:, 3:-3, 3:-3, 3:-3].sum()))
     e2e = {"value": cells * Ke / (ems * 1e-3) * 1e-6, "unit": UNIT, "h2d_bytes_per_step": nbytes * world,
-           "d2h_bytes_per_step": nbytes * world, "steps": Ke,
-           "what": "ppk_mhd3d_upload(pinned host U) + ppk_mhd3d_step + ppk_mhd3d_download(host U) per step"}
+           "d2h_bytes_per_step": nbytes * world, "steps": Ke, "ms_per_step": ems / Ke, "wall_ms_per_step": (w1 - w0) * 1e3 / Ke,
+           "handles_in_flight": depth,
+           "what": "per step: ppk_mhd3d_upload(pinned host U) + ppk_mhd3d_step + ppk_mhd3d_download_async(pinned host U); "
+                   f"{depth} independent batches in flight on {depth} streams, a batch's buffers are reused after "
+                   "ppk_mhd3d_synchronize"}
+    for s2 in e2e_solvers[1:]:
+        s2.close()
+    torch.cuda.set_stream(stream)
 
     # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) -----------------------------
     cpu = None
@@ -359,9 +447,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=256, help="cells per axis per GPU")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
-    ap.add_argument("--pipeline", default="unfused", choices=["fused", "fused_split", "unfused"])
+    ap.add_argument("--pipeline", default="unfused", choices=["fused", "fused_split", "unfused", "streamed"])
     ap.add_argument("--ref-n", type=int, default=128, help="grid of the bounded CPU sample")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=9)
+    ap.add_argument("--e2e-depth", type=int, default=3, help="solver handles (batches) in flight in the e2e leg at N=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -72,6 +72,11 @@ int ppk_mhd3d_destroy(ppk_mhd3d *handle);
  * Replaces Kokkos::deep_copy(Uhost, Udata) (src/utils/io/IO_VTK.cpp:253) and its inverse after init(). */
 int ppk_mhd3d_upload(ppk_mhd3d *handle, const double *u_host);
 int ppk_mhd3d_download(ppk_mhd3d *handle, double *u_host);
+/* The same copy enqueued on the handle's stream WITHOUT waiting for it (pinned `u_host`): with one handle per batch in
+ * flight, the download of one batch overlaps the upload and the step of the next ones (bench.py's e2e leg).
+ * ppk_mhd3d_synchronize(handle) makes `u_host` valid. Plays the role of the asynchronous deep_copy(exec_space, ...)
+ * overloads of Kokkos the reference never uses (its IO_VTK.cpp:253 copy is blocking). */
+int ppk_mhd3d_download_async(ppk_mhd3d *handle, double *u_host);
 
 /* Time bookkeeping of SolverBase (m_t, m_tEnd, m_iteration; SolverBase.cpp:119-124, 206-220). */
 int ppk_mhd3d_set_time(ppk_mhd3d *handle, double t, double t_end, long iteration);
@@ -137,8 +142,11 @@ int ppk_mhd3d_set_stream(ppk_mhd3d *handle, void *cuda_stream);
  *   PPK_PIPELINE_FUSED: after the trace, ONE z-marching consumer kernel = HLLD fluxes x,y,z + edge EMFs z,y,x +
  *       conservative and CT update; fluxes and EMFs never reach HBM (2.2x less DRAM traffic for that part, but
  *       slower today: see DESIGN.md);
- *   PPK_PIPELINE_FUSED_SPLIT: that consumer as two kernels (fluxes + hydro update, EMFs + CT update). */
-enum ppk_pipeline { PPK_PIPELINE_UNFUSED = 0, PPK_PIPELINE_FUSED = 1, PPK_PIPELINE_FUSED_SPLIT = 2 };
+ *   PPK_PIPELINE_FUSED_SPLIT: that consumer as two kernels (fluxes + hydro update, EMFs + CT update);
+ *   PPK_PIPELINE_STREAMED: after the trace, one z-marching kernel whose threads exchange one-sided states (warp
+ *       shuffles / shared memory) solves the three HLLD fluxes of every cell and applies the hydro update (no flux
+ *       array), then the TMA-staged EMF kernels and the CT update of the field. */
+enum ppk_pipeline { PPK_PIPELINE_UNFUSED = 0, PPK_PIPELINE_FUSED = 1, PPK_PIPELINE_FUSED_SPLIT = 2, PPK_PIPELINE_STREAMED = 3 };
 int ppk_mhd3d_set_pipeline(ppk_mhd3d *handle, int pipeline);
 /* Per-kernel CUDA-event timing (replaces the coarse timers of SolverBase.h:35-42 for profiling).
  * While enabled every kernel launch is bracketed by events on the launch stream. */

@@ -59,7 +59,7 @@ _lib = None
 
 # every symbol include/*.h declares (tests/test_abi.py checks the library exports them all)
 EXPORTS = [
-    "ppk_mhd3d_create", "ppk_mhd3d_destroy", "ppk_mhd3d_upload", "ppk_mhd3d_download", "ppk_mhd3d_set_time",
+    "ppk_mhd3d_create", "ppk_mhd3d_destroy", "ppk_mhd3d_upload", "ppk_mhd3d_download", "ppk_mhd3d_download_async", "ppk_mhd3d_set_time",
     "ppk_mhd3d_get_time", "ppk_mhd3d_make_boundaries", "ppk_mhd3d_compute_dt", "ppk_mhd3d_step", "ppk_mhd3d_run",
     "ppk_mhd3d_synchronize", "ppk_mhd3d_diagnostics", "ppk_nccl_get_unique_id", "ppk_mhd3d_comm_init",
     "ppk_mhd3d_set_stream", "ppk_mhd3d_profile", "ppk_mhd3d_kernel_times", "ppk_mhd3d_launch_count",
@@ -83,6 +83,7 @@ def load_library():
     L.ppk_mhd3d_destroy.argtypes = [vp]
     L.ppk_mhd3d_upload.argtypes = [vp, vp]
     L.ppk_mhd3d_download.argtypes = [vp, vp]
+    L.ppk_mhd3d_download_async.argtypes = [vp, vp]
     L.ppk_mhd3d_set_time.argtypes = [vp, C.c_double, C.c_double, C.c_long]
     L.ppk_mhd3d_get_time.argtypes = [vp, dp, dp, C.POINTER(C.c_long)]
     L.ppk_mhd3d_make_boundaries.argtypes = [vp]
@@ -180,6 +181,10 @@ class Mhd3d:
             _check(self.L.ppk_mhd3d_download(self.h, int(out)))
         return out
 
+    def download_async(self, out_ptr):
+        """Enqueue the device-to-host copy into the PINNED buffer at address `out_ptr`; valid after synchronize()."""
+        _check(self.L.ppk_mhd3d_download_async(self.h, int(out_ptr)))
+
     def interior(self):
         return self.download()[:, 3:-3, 3:-3, 3:-3]
 
@@ -221,7 +226,7 @@ class Mhd3d:
     def set_stream(self, stream_ptr):
         _check(self.L.ppk_mhd3d_set_stream(self.h, stream_ptr))
 
-    PIPELINES = {"unfused": 0, "fused": 1, "fused_split": 2}
+    PIPELINES = {"unfused": 0, "fused": 1, "fused_split": 2, "streamed": 3}
 
     def set_pipeline(self, name: str):
         _check(self.L.ppk_mhd3d_set_pipeline(self.h, self.PIPELINES[name]))

@@ -86,7 +86,7 @@ int load_nccl() {
 
 const char *const kKernelNames[KK_COUNT] = {"boundary", "prim_dt", "finalize_dt", "elec_dbf", "trace",
                                             "flux_x", "flux_y", "flux_z", "emf_z", "emf_y", "emf_x",
-                                            "update", "diagnostics", "halo_exchange", "consume"};
+                                            "update", "diagnostics", "halo_exchange", "consume", "hydro", "update_ct"};
 
 }  // namespace
 
@@ -264,6 +264,15 @@ int enqueue_step(ppk_mhd3d *h) {
     { Scope sc(h, KK_EMF_Y, s); h->kt->emf(g, 1, h->BASIS, h->DBF, h->EMF, h->tma, s); }
     { Scope sc(h, KK_EMF_X, s); h->kt->emf(g, 0, h->BASIS, h->DBF, h->EMF, h->tma, s); }
     { Scope sc(h, KK_UPDATE, s); h->kt->update(g, h->st, Uin, Uout, h->F[0], h->F[1], h->F[2], h->EMF, s); }
+  } else if (h->pipeline == PPK_PIPELINE_STREAMED) {
+    if (!h->EMF) {
+      if (int rc = ppk_mhd3d_set_pipeline(h, PPK_PIPELINE_STREAMED)) return rc;
+    }
+    { Scope sc(h, KK_HYDRO, s); h->kt->hydro(g, h->st, h->BASIS, Uin, Uout, s); }
+    { Scope sc(h, KK_EMF_Z, s); h->kt->emf(g, 2, h->BASIS, h->DBF, h->EMF, h->tma, s); }
+    { Scope sc(h, KK_EMF_Y, s); h->kt->emf(g, 1, h->BASIS, h->DBF, h->EMF, h->tma, s); }
+    { Scope sc(h, KK_EMF_X, s); h->kt->emf(g, 0, h->BASIS, h->DBF, h->EMF, h->tma, s); }
+    { Scope sc(h, KK_UPDATE_CT, s); h->kt->update_ct(g, h->st, Uin, Uout, h->EMF, s); }
   } else {
     Scope sc(h, KK_CONSUME, s);
     h->kt->consume(g, h->st, h->BASIS, h->DBF, Uin, Uout, h->pipeline == PPK_PIPELINE_FUSED_SPLIT, s);
@@ -380,6 +389,13 @@ int ppk_mhd3d_download(ppk_mhd3d *h, double *u_host) {
   DeviceGuard guard(h->device);
   CUDA_TRY(cudaMemcpyAsync(u_host, h->cur(), (size_t)NBVAR * h->g.ncell * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int ppk_mhd3d_download_async(ppk_mhd3d *h, double *u_host) {
+  if (!h || !u_host) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaMemcpyAsync(u_host, h->cur(), (size_t)NBVAR * h->g.ncell * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   return 0;
 }
 
@@ -534,14 +550,17 @@ int ppk_mhd3d_set_stream(ppk_mhd3d *h, void *cuda_stream) {
 
 int ppk_mhd3d_set_pipeline(ppk_mhd3d *h, int pipeline) {
   if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
-  if (pipeline < PPK_PIPELINE_UNFUSED || pipeline > PPK_PIPELINE_FUSED_SPLIT) return fail(PPK_ERR_INVALID_ARGUMENT, "unknown pipeline");
+  if (pipeline < PPK_PIPELINE_UNFUSED || pipeline > PPK_PIPELINE_STREAMED) return fail(PPK_ERR_INVALID_ARGUMENT, "unknown pipeline");
   DeviceGuard guard(h->device);
   if (pipeline == PPK_PIPELINE_UNFUSED && !h->F[0]) {  // flux / EMF arrays exist only for the unfused pipeline
     int rc = 0;
     const long long n = h->g.ncell;
     if ((rc = alloc_doubles(h, &h->F[0], NFLUX * n)) || (rc = alloc_doubles(h, &h->F[1], NFLUX * n)) ||
-        (rc = alloc_doubles(h, &h->F[2], NFLUX * n)) || (rc = alloc_doubles(h, &h->EMF, NEMF * n)))
+        (rc = alloc_doubles(h, &h->F[2], NFLUX * n)) || (!h->EMF && (rc = alloc_doubles(h, &h->EMF, NEMF * n))))
       return rc;
+  }
+  if (pipeline == PPK_PIPELINE_STREAMED && !h->EMF) {  // the streamed pipeline stores the EMFs but no flux
+    if (int rc = alloc_doubles(h, &h->EMF, NEMF * h->g.ncell)) return rc;
   }
   h->pipeline = pipeline;
   return 0;

@@ -48,7 +48,7 @@ struct StepState {
 // kernel kinds, for the per-kernel timers
 enum KernelKind {
   KK_BOUNDARY = 0, KK_PRIM_DT, KK_FINALIZE_DT, KK_ELEC_DBF, KK_TRACE,
-  KK_FLUX_X, KK_FLUX_Y, KK_FLUX_Z, KK_EMF_Z, KK_EMF_Y, KK_EMF_X, KK_UPDATE, KK_DIAG, KK_HALO, KK_CONSUME, KK_COUNT
+  KK_FLUX_X, KK_FLUX_Y, KK_FLUX_Z, KK_EMF_Z, KK_EMF_Y, KK_EMF_X, KK_UPDATE, KK_DIAG, KK_HALO, KK_CONSUME, KK_HYDRO, KK_UPDATE_CT, KK_COUNT
 };
 
 // Launchers exported by each arithmetic build (mhd_kernels.cu compiled twice).
@@ -74,6 +74,9 @@ struct KernelTable {
   // tensor maps of the basis / face-slope arrays for the TMA-staged kernels (nullptr: not applicable)
   void *(*tma_create)(const GridParams &g, const double *BASIS, const double *DBF);
   void (*tma_destroy)(void *ctx);
+  // streamed pipeline: z-marching HLLD fluxes + hydro update (no flux array), then the CT update alone
+  void (*hydro)(const GridParams &g, const StepState *st, const double *BASIS, const double *Uin, double *Uout, cudaStream_t s);
+  void (*update_ct)(const GridParams &g, const StepState *st, const double *Uin, double *Uout, const double *EMF, cudaStream_t s);
 };
 
 const KernelTable *kernel_table_exact();

@@ -1372,6 +1372,300 @@ __global__ void __launch_bounds__(CBX *CBY, 2)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streamed hydro consumer (PPK_PIPELINE_STREAMED): ComputeFluxesAndStore x,y,z (MHDRunFunctors3D.h:1783-1909) +
+// UpdateFunctor3D_MHD (:2430-2544) in one z-marching kernel whose threads exchange one-sided STATES, not basis
+// cells.
+//
+// A CTA owns 32 x SHY columns of cells and marches upwards in k. Thread (lane, w) reads the basis of ITS cell only
+// (coalesced, every basis number is read once), forms the six one-sided states q -/+ slope of that cell, and hands
+//   qm_x to lane+1 (warp shuffle), qm_y to row w+1 (shared memory), qm_z to itself one plane later (shared memory
+// slot of its own), then solves the Riemann problems of its three LOWER faces. The upper-face fluxes come back the
+// same way (shuffle / shared memory / next plane). One extra warp solves the faces on the far side of the tile
+// (row j0+SHY: 32 y-faces; column i0+32: SHY x-faces in 8 lanes) through the SAME call sites as the tile's warps,
+// so a face solved by two neighbouring CTAs gets the same bits from both. The left neighbours' states (column i0-1,
+// row j0-1) are formed by lane 0 / warp 0 from 14 extra loads. No flux reaches HBM, and the update keeps the
+// reference's order x-lo, x-hi, y-lo, y-hi, z-lo | z-hi (the last term one plane later): bit-identical.
+// Only the 5 hydro variables of interior cells are written (the field is advanced by k_update_ct; ghost cells of
+// Uout are refilled by the next step's boundary kernels before anything reads them).
+// ---------------------------------------------------------------------------------------------
+constexpr int SHY = 8;
+constexpr int SH_THREADS = (SHY + 1) * 32;
+
+// one-sided states of a cell along D in the face frame (r, p, un, t1, t2, b1, b2): qm = q + slope is the LEFT state
+// of the cell's upper D-face, qp = q - slope the RIGHT state of its lower D-face (MHDBaseFunctor3D.h:898-968; the
+// frame is the one the reference's swapValues calls produce, see flux_face)
+template <int D>
+DEV void one_sided_states(const GridParams &g, const double *__restrict__ Bc, const long long N, double qm[7], double qp[7]) {
+  constexpr int T1 = D == 0 ? 1 : (D == 1 ? 0 : 1), T2 = D == 0 ? 2 : (D == 1 ? 2 : 0);
+  constexpr int SB = slope_base(D);
+  constexpr int qi[7] = {BQ + ID, BQ + IP, BQ + IU + D, BQ + IU + T1, BQ + IU + T2, BQ + IA + T1, BQ + IA + T2};
+  constexpr int si[7] = {0, 1, 2 + D, 2 + T1, 2 + T2, slope_b(D, T1), slope_b(D, T2)};
+#pragma unroll
+  for (int v = 0; v < 7; ++v) {
+    const double q = Bc[qi[v] * N], s = Bc[(SB + si[v]) * N];
+    qm[v] = q + s;
+    qp[v] = q - s;
+  }
+  qm[0] = vmax(g.smallr, qm[0]); qm[1] = vmax(g.smallp, qm[1]);
+  qp[0] = vmax(g.smallr, qp[0]); qp[1] = vmax(g.smallp, qp[1]);
+}
+// the same states from a register copy b[NBASIS] of the cell's basis (k_hydro loads a whole cell in one burst so that a
+// plane costs one exposed memory round trip instead of one per phase)
+template <int D>
+DEV void one_sided_states_reg(const GridParams &g, const double b[NBASIS], double qm[7], double qp[7]) {
+  constexpr int T1 = D == 0 ? 1 : (D == 1 ? 0 : 1), T2 = D == 0 ? 2 : (D == 1 ? 2 : 0);
+  constexpr int SB = slope_base(D);
+  constexpr int qi[7] = {BQ + ID, BQ + IP, BQ + IU + D, BQ + IU + T1, BQ + IU + T2, BQ + IA + T1, BQ + IA + T2};
+  constexpr int si[7] = {0, 1, 2 + D, 2 + T1, 2 + T2, slope_b(D, T1), slope_b(D, T2)};
+#pragma unroll
+  for (int v = 0; v < 7; ++v) {
+    qm[v] = b[qi[v]] + b[SB + si[v]];
+    qp[v] = b[qi[v]] - b[SB + si[v]];
+  }
+  qm[0] = vmax(g.smallr, qm[0]); qm[1] = vmax(g.smallp, qm[1]);
+  qp[0] = vmax(g.smallr, qp[0]); qp[1] = vmax(g.smallp, qp[1]);
+}
+// loads of the basis numbers direction D needs (q, slopes along D, lower D-face field)
+template <int D>
+DEV void load_basis_dir(const double *__restrict__ Bc, const long long N, double b[NBASIS]) {
+  constexpr int T1 = D == 0 ? 1 : (D == 1 ? 0 : 1), T2 = D == 0 ? 2 : (D == 1 ? 2 : 0);
+  constexpr int SB = slope_base(D);
+  constexpr int qi[7] = {BQ + ID, BQ + IP, BQ + IU + D, BQ + IU + T1, BQ + IU + T2, BQ + IA + T1, BQ + IA + T2};
+#pragma unroll
+  for (int v = 0; v < 7; ++v) { b[qi[v]] = Bc[qi[v] * N]; b[SB + v] = Bc[(SB + v) * N]; }
+  b[BFACE + D] = Bc[(BFACE + D) * N];
+}
+DEV void benign_basis(double b[NBASIS]) {
+#pragma unroll
+  for (int v = 0; v < NBASIS; ++v) b[v] = 0.0;
+  b[BQ + ID] = 1.0; b[BQ + IP] = 1.0;
+}
+DEV void benign_state(double q[7]) {  // operands of a solve whose result nobody reads
+  q[0] = 1.0; q[1] = 1.0; q[2] = 0.0; q[3] = 0.0; q[4] = 0.0; q[5] = 0.0; q[6] = 0.0;
+}
+DEV void hlld7(const GridParams &g, const double L[7], const double R[7], const double bn, double f[5]) {
+#if PPK_EXACT
+  riemann_hlld(g.gamma0, L[0], L[1], L[2], L[3], L[4], bn, L[5], L[6], R[0], R[1], R[2], R[3], R[4], bn, R[5], R[6], f[0], f[1],
+               f[2], f[3], f[4]);
+#else
+  riemann_hlld_fast(g.gamma0, L[0], L[1], L[2], L[3], L[4], bn, L[5], L[6], R[0], R[1], R[2], R[3], R[4], bn, R[5], R[6], f[0],
+                    f[1], f[2], f[3], f[4]);
+#endif
+}
+
+// shared-memory layout of k_hydro (doubles): per-thread slots are [component][thread] so that a warp's access is
+// conflict-free
+struct HydroSmem {
+  double xL[7][SHY * 32], xR[7][SHY * 32], xbn[SHY * 32];  // operands of the thread's x-face (formed one phase earlier)
+  double yR[7][SHY * 32], ybn[SHY * 32];                   // right state of its y-face
+  double lz[7][SHY * 32];                                  // qm_z of its cell, one plane below
+  double yrow[SHY + 1][7][32];                             // qm_y of rows j0-1 .. j0+SHY-1 (index = tile row + 1)
+  double fy[SHY + 1][5][32];                               // y-face fluxes of rows j0 .. j0+SHY
+  double xcol[SHY][7];                                     // qm_x of the last cell of each row (left state, far x-face)
+  double fxx[SHY][5];                                      // far x-face fluxes
+  int fxx_plane;                                           // last plane whose far x-face fluxes are in fxx
+};
+
+template <int MAXREG>
+__global__ void __launch_bounds__(SH_THREADS) __maxnreg__(MAXREG)
+  k_hydro(const GridParams g, const StepState *__restrict__ stp, const double *__restrict__ BASIS,
+          const double *__restrict__ Uin, double *__restrict__ Uout, const int zchunk) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  HydroSmem &S = *reinterpret_cast<HydroSmem *>(smem_raw);
+  volatile int *fxx_plane = &S.fxx_plane;
+
+  const int gw = g.gw;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const bool main_warp = w < SHY;
+  const int i0 = gw + blockIdx.x * 32, j0 = gw + blockIdx.y * SHY;
+  const int ie = gw + g.nx, je = gw + g.ny;  // one past the last interior cell
+  const long long N = g.ncell, sj = g.isize, sk = (long long)g.isize * g.jsize;
+  const double dtdx = stp->dtdx, dtdy = stp->dtdy, dtdz = stp->dtdz;
+  const int k0 = gw + blockIdx.z * zchunk;
+  const int k1 = min(k0 + zchunk, gw + g.nz);
+
+  // tile warps: cell (i, j); the extra warp: cell (i0+lane, j0+SHY) for the far y-faces, cell (i0+32, j0+lane) for
+  // the far x-faces
+  const int i = i0 + lane, j = main_warp ? j0 + w : j0 + SHY;
+  const bool cell_ok = main_warp && i < ie && j < je;
+  const bool ld_ok = main_warp && i <= ie && j <= je;  // cells whose lower x- or y-face a cell of the tile consumes
+  const bool ey_ok = !main_warp && i < ie && j <= je;
+  const bool ex_ok = !main_warp && lane < SHY && i0 + 32 <= ie && j0 + lane < je;
+  long long c = cidx(g, i, j, k0);                               // tile warps: own cell; extra warp: far-row cell
+  long long cx = cidx(g, i0 + 32, j0 + (lane & (SHY - 1)), k0);  // extra warp: far-column cell
+  if (tid == 0) *fxx_plane = k0 - 1;
+
+  if (main_warp) {  // prologue: left state of the lowest z-face
+    double qm[7], qp[7];
+    if (cell_ok) one_sided_states<2>(g, BASIS + c - sk, N, qm, qp);
+    else benign_state(qm);
+#pragma unroll
+    for (int v = 0; v < 7; ++v) S.lz[v][tid] = qm[v];
+  }
+  double u[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+
+  for (int k = k0; k <= k1; ++k, c += sk, cx += sk) {
+    const bool last = k == k1;  // the top plane only closes the cells below it
+    double fz[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    double Rx[7], Ry[7], bnx = 0.0, bny = 0.0;  // extra warp: right states of its far faces (registers)
+    // ---- phase A: every load of this plane in one burst, all one-sided states, operands parked in shared memory ----
+    if (main_warp) {
+      double Lz[7], Rz[7], bnz;
+      {
+        double b[NBASIS];
+        if (last) {
+          if (cell_ok) load_basis_dir<2>(BASIS + c, N, b); else benign_basis(b);
+        } else if (ld_ok) {
+#pragma unroll
+          for (int v = 0; v < NBASIS; ++v) b[v] = BASIS[c + v * N];
+        } else benign_basis(b);
+        double qm[7], qp[7];
+        if (!last) {
+          // y: left state of the row above goes through shared memory, the own right state is parked
+          one_sided_states_reg<1>(g, b, qm, qp);
+#pragma unroll
+          for (int v = 0; v < 7; ++v) { S.yrow[w + 1][v][lane] = qm[v]; S.yR[v][tid] = qp[v]; }
+          S.ybn[tid] = b[BFACE + 1];
+          // x: left state from lane-1 (lane 0: column i0-1, formed by the extra warp), own right state
+          one_sided_states_reg<0>(g, b, qm, qp);
+#pragma unroll
+          for (int v = 0; v < 7; ++v) {
+            const double up = __shfl_up_sync(0xffffffffu, qm[v], 1);
+            if (lane != 0) S.xL[v][tid] = up;
+            S.xR[v][tid] = qp[v];
+            if (lane == 31) S.xcol[w][v] = qm[v];
+          }
+          S.xbn[tid] = b[BFACE + 0];
+        }
+        one_sided_states_reg<2>(g, b, qm, Rz);
+        bnz = b[BFACE + 2];
+#pragma unroll
+        for (int v = 0; v < 7; ++v) { Lz[v] = S.lz[v][tid]; S.lz[v][tid] = qm[v]; }
+      }
+      // ---- z face (needs no neighbour: runs before the barrier) ----
+      hlld7(g, Lz, Rz, bnz, fz);
+      if (cell_ok && k > k0) {  // cell k-1 receives its z-hi term and is complete
+        const long long cp = c - sk;
+        u[0] -= fz[0] * dtdz; u[1] -= fz[1] * dtdz; u[2] -= fz[4] * dtdz; u[3] -= fz[3] * dtdz; u[4] -= fz[2] * dtdz;
+        Uout[cp + ID * N] = u[0]; Uout[cp + IP * N] = u[1]; Uout[cp + IU * N] = u[2];
+        Uout[cp + IV * N] = u[3]; Uout[cp + IW * N] = u[4];
+      }
+      if (cell_ok && !last) {
+        u[0] = Uin[c + ID * N]; u[1] = Uin[c + IP * N]; u[2] = Uin[c + IU * N]; u[3] = Uin[c + IV * N]; u[4] = Uin[c + IW * N];
+      }
+    } else if (!last) {
+      // the extra warp forms every state that comes from outside the tile: right states of the far row / far column
+      // (kept in registers for its own solves), left states of row j0-1 and of column i0-1 (published)
+      double b[NBASIS], qm[7], qp[7];
+      if (ey_ok) load_basis_dir<1>(BASIS + c, N, b); else benign_basis(b);
+      one_sided_states_reg<1>(g, b, qm, Ry);
+      bny = b[BFACE + 1];
+      if (i < ie) load_basis_dir<1>(BASIS + c - (SHY + 1) * sj, N, b); else benign_basis(b);  // row j0-1
+      one_sided_states_reg<1>(g, b, qm, qp);
+#pragma unroll
+      for (int v = 0; v < 7; ++v) S.yrow[0][v][lane] = qm[v];
+      // lanes 0..SHY-1: far column i0+32 (right states); lanes SHY..2SHY-1: column i0-1 (left states)
+      const bool hx = lane >= SHY && lane < 2 * SHY && j0 + (lane - SHY) < je;
+      if (ex_ok) load_basis_dir<0>(BASIS + cx, N, b);
+      else if (hx) load_basis_dir<0>(BASIS + cx - 33, N, b);
+      else benign_basis(b);
+      one_sided_states_reg<0>(g, b, qm, Rx);
+      bnx = b[BFACE + 0];
+      if (lane >= SHY && lane < 2 * SHY) {
+#pragma unroll
+        for (int v = 0; v < 7; ++v) S.xL[v][(lane - SHY) * 32] = qm[v];
+      }
+    }
+    if (last) break;  // uniform
+    __syncthreads();  // (1) published states are visible
+
+    double L[7], R[7], f[5], bn;
+    // ---- x faces ----
+    if (main_warp) {
+#pragma unroll
+      for (int v = 0; v < 7; ++v) { L[v] = S.xL[v][tid]; R[v] = S.xR[v][tid]; }
+      bn = S.xbn[tid];
+    } else {
+#pragma unroll
+      for (int v = 0; v < 7; ++v) { L[v] = S.xcol[lane & (SHY - 1)][v]; R[v] = Rx[v]; }
+      bn = bnx;
+    }
+    hlld7(g, L, R, bn, f);
+    if (main_warp) {
+      double fh[5];
+#pragma unroll
+      for (int v = 0; v < 5; ++v) fh[v] = __shfl_down_sync(0xffffffffu, f[v], 1);
+      if (lane == 31) {  // the far x-face comes from the extra warp, which solved it while this warp did its own
+        while (*fxx_plane < k) {}
+        __threadfence_block();
+#pragma unroll
+        for (int v = 0; v < 5; ++v) fh[v] = ((volatile double *)&S.fxx[w][0])[v];
+      }
+      // x faces: (rho,E,mx,my,mz) <- (0,1,2,3,4)
+      u[0] += f[0] * dtdx; u[1] += f[1] * dtdx; u[2] += f[2] * dtdx; u[3] += f[3] * dtdx; u[4] += f[4] * dtdx;
+      u[0] -= fh[0] * dtdx; u[1] -= fh[1] * dtdx; u[2] -= fh[2] * dtdx; u[3] -= fh[3] * dtdx; u[4] -= fh[4] * dtdx;
+    } else {
+      if (lane < SHY) {
+#pragma unroll
+        for (int v = 0; v < 5; ++v) S.fxx[lane][v] = f[v];
+      }
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) *fxx_plane = k;
+    }
+    // ---- y faces ----
+    if (main_warp) {
+#pragma unroll
+      for (int v = 0; v < 7; ++v) { L[v] = S.yrow[w][v][lane]; R[v] = S.yR[v][tid]; }
+      bn = S.ybn[tid];
+    } else {
+#pragma unroll
+      for (int v = 0; v < 7; ++v) { L[v] = S.yrow[SHY][v][lane]; R[v] = Ry[v]; }
+      bn = bny;
+    }
+    hlld7(g, L, R, bn, f);
+#pragma unroll
+    for (int v = 0; v < 5; ++v) S.fy[w][v][lane] = f[v];
+    __syncthreads();  // (2) y-face fluxes are visible; the operand slots may be rewritten
+    if (main_warp) {
+      // y faces, rotated frame: normal=my (2), t1=mx (3), t2=mz (4)
+      u[0] += f[0] * dtdy; u[1] += f[1] * dtdy; u[2] += f[3] * dtdy; u[3] += f[2] * dtdy; u[4] += f[4] * dtdy;
+      u[0] -= S.fy[w + 1][0][lane] * dtdy; u[1] -= S.fy[w + 1][1][lane] * dtdy; u[2] -= S.fy[w + 1][3][lane] * dtdy;
+      u[3] -= S.fy[w + 1][2][lane] * dtdy; u[4] -= S.fy[w + 1][4][lane] * dtdy;
+      // z-lo face: normal=mz (2), t1=my (3), t2=mx (4)
+      u[0] += fz[0] * dtdz; u[1] += fz[1] * dtdz; u[2] += fz[4] * dtdz; u[3] += fz[3] * dtdz; u[4] += fz[2] * dtdz;
+    }
+  }
+}
+
+// UpdateEmfFunctor3D (MHDRunFunctors3D.h:2549-2628) alone: the field components of interior cells, expression order
+// of :2602-2616 (the streamed pipeline's hydro variables are written by k_hydro)
+__global__ void __launch_bounds__(256) k_update_ct(const GridParams g, const StepState *__restrict__ stp,
+                                                   const double *__restrict__ Uin, double *__restrict__ Uout,
+                                                   const double *__restrict__ EMF) {
+  const int gw = g.gw;
+  const int k = gw + blockIdx.y;
+  const unsigned ni = g.nx;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned jj = t / ni;
+  if (jj >= (unsigned)g.ny) return;
+  const int i = gw + (int)(t - jj * ni), j = gw + (int)jj;
+  const long long N = g.ncell, sj = g.isize, sk = (long long)g.isize * g.jsize;
+  const long long c = cidx(g, i, j, k);
+  const double dtdx = stp->dtdx, dtdy = stp->dtdy, dtdz = stp->dtdz;
+  double a = Uin[c + IA * N], b = Uin[c + IB * N], cc = Uin[c + IC * N];
+  const double *Ez = EMF, *Ey = EMF + N, *Ex = EMF + 2 * N;
+  const double ez = Ez[c], ey = Ey[c], ex = Ex[c];
+  a += (Ez[c + sj] - ez) * dtdy;
+  b -= (Ez[c + 1] - ez) * dtdx;
+  a -= (Ey[c + sk] - ey) * dtdz;
+  b += (Ex[c + sk] - ex) * dtdz;
+  cc += (Ey[c + 1] - ey) * dtdx;
+  cc -= (Ex[c + sj] - ex) * dtdy;
+  Uout[c + IA * N] = a; Uout[c + IB * N] = b; Uout[c + IC * N] = cc;
+}
+
 // Diagnostics: per-variable sums over the interior and max |div B| (needs filled upper ghosts).
 // Two-stage: per-block partials with warp shuffles, then double atomicAdd / ordered-bits atomicMax.
 __global__ void __launch_bounds__(256) k_diagnostics(const GridParams g, const double *__restrict__ U, double *out9) {
@@ -1582,6 +1876,34 @@ static void l_consume(const GridParams &g, const StepState *st, const double *BA
     k_consume<false, true><<<grid, block, 0, s>>>(g, st, BASIS, DBF, Uin, Uout, zchunk);
   }
 }
+static void l_hydro(const GridParams &g, const StepState *st, const double *BASIS, const double *Uin, double *Uout, cudaStream_t s) {
+  static const int zc_env = getenv("PPK_HYDRO_ZCHUNK") ? atoi(getenv("PPK_HYDRO_ZCHUNK")) : 0;
+  static const int minb = getenv("PPK_HYDRO_MINB") ? atoi(getenv("PPK_HYDRO_MINB")) : 1;  // 1: 168 registers, no spills (fastest measured)
+  const long long tiles = (long long)cdiv(g.nx, 32) * cdiv(g.ny, SHY);
+  // z-chunks only exist to give the grid enough CTAs (each one re-solves one plane of z-faces): ~10 waves of 148 x 2
+  int nchunk = (int)((10LL * 296 + tiles - 1) / tiles);
+  const int max_chunks = g.nz / 8 > 0 ? g.nz / 8 : 1;
+  if (nchunk > max_chunks) nchunk = max_chunks;
+  if (nchunk < 1) nchunk = 1;
+  int zchunk = (g.nz + nchunk - 1) / nchunk;
+  if (zc_env > 0) zchunk = zc_env;
+  dim3 grid(cdiv(g.nx, 32), cdiv(g.ny, SHY), cdiv(g.nz, zchunk));
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_hydro<168>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HydroSmem));
+    cudaFuncSetAttribute(k_hydro<112>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HydroSmem));
+    cudaFuncSetAttribute(k_hydro<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HydroSmem));
+    attr_done = true;
+  }
+  if (minb == 1) k_hydro<168><<<grid, SH_THREADS, sizeof(HydroSmem), s>>>(g, st, BASIS, Uin, Uout, zchunk);
+  else if (minb == 3) k_hydro<96><<<grid, SH_THREADS, sizeof(HydroSmem), s>>>(g, st, BASIS, Uin, Uout, zchunk);
+  else k_hydro<112><<<grid, SH_THREADS, sizeof(HydroSmem), s>>>(g, st, BASIS, Uin, Uout, zchunk);
+}
+static void l_update_ct(const GridParams &g, const StepState *st, const double *Uin, double *Uout, const double *EMF, cudaStream_t s) {
+  const int bs = 256;
+  dim3 grid(cdiv((long long)g.nx * g.ny, bs), g.nz);
+  k_update_ct<<<grid, bs, 0, s>>>(g, st, Uin, Uout, EMF);
+}
 static void l_diagnostics(const GridParams &g, const double *U, double *out9, cudaStream_t s) {
   const int bs = 256;
   dim3 grid(cdiv((long long)g.nx * g.ny, bs), g.nz);
@@ -1598,7 +1920,7 @@ static const KernelTable table = {
 #else
   "fast",
 #endif
-  l_boundary, l_prim_dt, l_finalize_dt, l_advance_time, l_elec_dbf, l_trace, l_flux, l_emf, l_update, l_diagnostics, l_fastmath_selftest, l_consume, l_tma_create, l_tma_destroy,
+  l_boundary, l_prim_dt, l_finalize_dt, l_advance_time, l_elec_dbf, l_trace, l_flux, l_emf, l_update, l_diagnostics, l_fastmath_selftest, l_consume, l_tma_create, l_tma_destroy, l_hydro, l_update_ct,
 };
 
 }  // namespace PPK_NS

@@ -42,7 +42,7 @@ def close_per_cell(a, b, rtol=1e-12):
         assert not bad.any(), f"var {v}: max abs diff {np.abs(a[v] - b[v]).max():.3e} (field max {np.abs(b[v]).max():.3e})"
 
 
-@pytest.mark.parametrize("pipeline", ["fused", "fused_split", "unfused"])
+@pytest.mark.parametrize("pipeline", ["fused", "fused_split", "unfused", "streamed"])
 @pytest.mark.parametrize("case", golden_cases())
 def test_exact_mode_bit_identical_to_reference(case, pipeline):
     g = np.load(f"{GOLDEN}/{case}.npz")
@@ -59,7 +59,7 @@ def test_exact_mode_bit_identical_to_reference(case, pipeline):
     s.close()
 
 
-@pytest.mark.parametrize("pipeline", ["fused", "unfused"])
+@pytest.mark.parametrize("pipeline", ["fused", "unfused", "streamed"])
 @pytest.mark.parametrize("case", golden_cases())
 def test_fast_mode_within_1e12_of_reference(case, pipeline):
     g = np.load(f"{GOLDEN}/{case}.npz")
@@ -83,11 +83,14 @@ def test_exact_mode_vs_oracle_with_intermediates(problem, n, extra, bounds, cfl,
     orc = O.Oracle(ini)
     s, _ = make_solver(ini, exact=True, pipeline="unfused")   # the pipeline that stores Fluxes_* and Emf
     f, _ = make_solver(ini, exact=True, pipeline="fused")
+    m, _ = make_solver(ini, exact=True, pipeline="streamed")
     for step in range(4):
         orc.step()
         s.step()
         f.step()
+        m.step()
         assert np.array_equal(f.interior(), orc.interior()), f"fused pipeline differs at step {step + 1}"
+        assert np.array_equal(m.interior(), orc.interior()), f"streamed pipeline differs at step {step + 1}"
         t, dt, it = s.get_time()
         assert dt == orc.dt and t == orc.t, f"dt/t differ at step {step}: {dt} vs {orc.dt}"
         if step == 0:
@@ -115,6 +118,7 @@ def test_exact_mode_vs_oracle_with_intermediates(problem, n, extra, bounds, cfl,
     assert abs(divb - do) <= 1e-18 + 1e-12 * do, (divb, do)
     s.close()
     f.close()
+    m.close()
 
 
 def test_hundred_steps_conserved_sums_and_divb(oracle_mod):
