@@ -27,9 +27,16 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-    os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p")
+# rank 0 prints ONE JSON line on stdout. Libraries write there too (NCCL's version banner when NCCL_DEBUG is set in
+# the environment or in nccl.conf): file descriptor 1 is pointed at stderr for the whole run and the JSON line goes
+# to the saved original descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 METRIC = "Orszag-Tang 3D MHD fp64 Mcell-updates/s"
 UNIT = "Mcell-updates/s"
@@ -224,7 +231,7 @@ def run_reference_arm(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -433,7 +440,7 @@ def run_ours(args):
             "profiled_step_ms": step_ms_prof,
             "sim": {"t": t_sim, "dt": dt_sim, "iteration": it, "max_divB": divb, "device_GB": solver.device_bytes() / 1e9},
         }
-        print(json.dumps(line))
+        emit(line)
     solver.close()
     if world > 1:
         dist.destroy_process_group()

@@ -15,6 +15,7 @@
 #include <nccl.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -96,7 +97,7 @@ struct ppk_mhd3d {
   const KernelTable *kt = nullptr;
   int device = 0;
   cudaStream_t stream = nullptr, own_stream = nullptr, comm_stream = nullptr;
-  cudaEvent_t ev_xy = nullptr, ev_halo = nullptr;
+  cudaEvent_t ev_xy = nullptr, ev_halo = nullptr, ev_dt = nullptr;
   double *U[2] = {nullptr, nullptr};
   double *Q = nullptr, *E = nullptr, *DBF = nullptr, *BASIS = nullptr, *F[3] = {nullptr, nullptr, nullptr}, *EMF = nullptr;
   StepState *st = nullptr;
@@ -117,6 +118,8 @@ struct ppk_mhd3d {
   int nranks = 1, rank = 0, zlo = 0, zhi = 0;
   bool exch_lo = false, exch_hi = false;  // z faces filled by the halo exchange
   int pipeline = PPK_PIPELINE_UNFUSED;
+  double *halo_posted = nullptr;  // array whose z exchange was started at the end of the previous step
+  bool early_halo = true, defer_dt = true;
 
   double *cur() { return U[host_iteration & 1]; }
   double *nxt() { return U[(host_iteration + 1) & 1]; }
@@ -208,26 +211,37 @@ int halo_exchange_z(ppk_mhd3d *h, double *U, cudaStream_t s) {
   return 0;
 }
 
-// make_boundaries on array U, optionally overlapped with the part of prim+CFL that needs no z ghost
-int boundaries_and_primitives(ppk_mhd3d *h, double *U, bool with_prim) {
+// make_boundaries on array U, optionally overlapped with the part of prim+CFL that needs no z ghost.
+// `defer_dt`: the caller finishes the time step size itself (enqueue_step overlaps the all-reduce with E + dB).
+int boundaries_and_primitives(ppk_mhd3d *h, double *U, bool with_prim, bool defer_dt = false) {
   const GridParams &g = h->g;
   cudaStream_t s = h->stream;
-  { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, U, 0, s); }
-  { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, U, 1, s); }
   const bool exch = h->exch_lo || h->exch_hi;
+  const bool posted = exch && h->halo_posted == U;  // the z exchange of this array started at the end of the last step
+  if (exch && !h->comm) return fail(PPK_ERR_STATE, "mz > 1 but ppk_mhd3d_comm_init was not called");
+  if (posted) {
+    // the edge planes already carry their x / y ghosts (they are being sent), the z ghost planes are being received
+    { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, U, 0, 2 * g.gw, g.nz, s); }
+    { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, U, 1, 2 * g.gw, g.nz, s); }
+  } else {
+    { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, U, 0, 0, g.ksize, s); }
+    { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, U, 1, 0, g.ksize, s); }
+  }
   if (exch) {
-    if (!h->comm) return fail(PPK_ERR_STATE, "mz > 1 but ppk_mhd3d_comm_init was not called");
-    CUDA_TRY(cudaEventRecord(h->ev_xy, s));
-    CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_xy, 0));
-    if (int rc = halo_exchange_z(h, U, h->comm_stream)) return rc;
-    CUDA_TRY(cudaEventRecord(h->ev_halo, h->comm_stream));
+    if (!posted) {
+      CUDA_TRY(cudaEventRecord(h->ev_xy, s));
+      CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_xy, 0));
+      if (int rc = halo_exchange_z(h, U, h->comm_stream)) return rc;
+      CUDA_TRY(cudaEventRecord(h->ev_halo, h->comm_stream));
+    }
+    h->halo_posted = nullptr;
     if (with_prim) {  // interior planes: Q(k) reads U(k) and U(k+1), both inside [gw, nz+gw)
       Scope sc(h, KK_PRIM_DT, s);
       h->kt->prim_dt(g, U, h->Q, h->st, g.gw, g.nz + g.gw - 1, s);
     }
     CUDA_TRY(cudaStreamWaitEvent(s, h->ev_halo, 0));
   }
-  { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, U, 2, s); }  // physical / locally periodic z faces
+  { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, U, 2, 0, g.ksize, s); }  // physical / locally periodic z faces
   if (with_prim) {
     if (exch) {
       { Scope sc(h, KK_PRIM_DT, s); h->kt->prim_dt(g, U, h->Q, h->st, 0, g.gw, s); }
@@ -236,6 +250,7 @@ int boundaries_and_primitives(ppk_mhd3d *h, double *U, bool with_prim) {
       Scope sc(h, KK_PRIM_DT, s);
       h->kt->prim_dt(g, U, h->Q, h->st, 0, g.ksize - 1, s);
     }
+    if (defer_dt) return 0;
     if (h->comm && h->nranks > 1) {
       // MPI_Allreduce(MIN) of dt (SolverBase.cpp:152-165) == max-allreduce of 1/dt: the division
       // cfl/invDt is monotonic, so min_r(cfl/invDt_r) and cfl/max_r(invDt_r) are the same double.
@@ -250,8 +265,18 @@ int enqueue_step(ppk_mhd3d *h) {
   const GridParams &g = h->g;
   cudaStream_t s = h->stream;
   double *Uin = h->cur(), *Uout = h->nxt();
-  if (int rc = boundaries_and_primitives(h, Uin, true)) return rc;
+  const bool multi = h->comm && h->nranks > 1 && h->defer_dt;
+  if (int rc = boundaries_and_primitives(h, Uin, true, multi)) return rc;
+  if (multi) {
+    // the dt all-reduce (latency + rank skew) runs on the comm stream under E + dB, which do not need dt
+    CUDA_TRY(cudaEventRecord(h->ev_xy, s));
+    CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_xy, 0));
+    NCCL_TRY(g_nccl.AllReduce(&h->st->inv_dt_bits, &h->st->inv_dt_bits, 1, ncclDouble, ncclMax, h->comm, h->comm_stream));
+    { Scope sc(h, KK_FINALIZE_DT, h->comm_stream); h->kt->finalize_dt(g, h->st, h->comm_stream); }
+    CUDA_TRY(cudaEventRecord(h->ev_dt, h->comm_stream));
+  }
   { Scope sc(h, KK_ELEC_DBF, s); h->kt->elec_dbf(g, Uin, h->Q, h->E, h->DBF, s); }
+  if (multi) CUDA_TRY(cudaStreamWaitEvent(s, h->ev_dt, 0));
   { Scope sc(h, KK_TRACE, s); h->kt->trace(g, h->st, Uin, h->Q, h->E, h->BASIS, s); }
   if (h->pipeline == PPK_PIPELINE_UNFUSED) {
     if (!h->F[0]) {  // flux / EMF arrays are allocated on first use of this pipeline
@@ -263,7 +288,28 @@ int enqueue_step(ppk_mhd3d *h) {
     { Scope sc(h, KK_EMF_Z, s); h->kt->emf(g, 2, h->BASIS, h->DBF, h->EMF, h->tma, s); }
     { Scope sc(h, KK_EMF_Y, s); h->kt->emf(g, 1, h->BASIS, h->DBF, h->EMF, h->tma, s); }
     { Scope sc(h, KK_EMF_X, s); h->kt->emf(g, 0, h->BASIS, h->DBF, h->EMF, h->tma, s); }
-    { Scope sc(h, KK_UPDATE, s); h->kt->update(g, h->st, Uin, Uout, h->F[0], h->F[1], h->F[2], h->EMF, s); }
+    const bool exch = h->exch_lo || h->exch_hi;
+    if (exch && h->comm && h->early_halo && g.nz >= 2 * g.gw) {
+      // Update the planes the neighbours need first, fill their x / y ghosts and start the z exchange of the NEXT
+      // step; it then runs under the update of the remaining planes and the next step's primitives. The z ghost
+      // planes of Uout are not written here: they are being received.
+      const int gw = g.gw, nz = g.nz;
+      { Scope sc(h, KK_UPDATE, s); h->kt->update(g, h->st, Uin, Uout, h->F[0], h->F[1], h->F[2], h->EMF, gw, 2 * gw, s); }
+      { Scope sc(h, KK_UPDATE, s); h->kt->update(g, h->st, Uin, Uout, h->F[0], h->F[1], h->F[2], h->EMF, nz, nz + gw, s); }
+      for (int dir = 0; dir < 2; ++dir) {
+        { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, Uout, dir, gw, 2 * gw, s); }
+        { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, Uout, dir, nz, nz + gw, s); }
+      }
+      CUDA_TRY(cudaEventRecord(h->ev_xy, s));
+      CUDA_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_xy, 0));
+      if (int rc = halo_exchange_z(h, Uout, h->comm_stream)) return rc;
+      CUDA_TRY(cudaEventRecord(h->ev_halo, h->comm_stream));
+      h->halo_posted = Uout;
+      { Scope sc(h, KK_UPDATE, s); h->kt->update(g, h->st, Uin, Uout, h->F[0], h->F[1], h->F[2], h->EMF, 2 * gw, nz, s); }
+    } else {
+      Scope sc(h, KK_UPDATE, s);
+      h->kt->update(g, h->st, Uin, Uout, h->F[0], h->F[1], h->F[2], h->EMF, 0, g.ksize, s);
+    }
   } else if (h->pipeline == PPK_PIPELINE_STREAMED) {
     if (!h->EMF) {
       if (int rc = ppk_mhd3d_set_pipeline(h, PPK_PIPELINE_STREAMED)) return rc;
@@ -282,6 +328,12 @@ int enqueue_step(ppk_mhd3d *h) {
   h->launches += 1;
   h->host_iteration += 1;
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// a posted z exchange writes ghost planes of the current array: finish it before the host reads or replaces that array
+int settle_halo(ppk_mhd3d *h) {
+  if (h->halo_posted) CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
   return 0;
 }
 
@@ -335,10 +387,21 @@ int ppk_mhd3d_create(const ppk_mhd3d_params *p, ppk_mhd3d **out) {
   }
   DeviceGuard guard(h->device);
   CUDA_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-  CUDA_TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  {
+    // the comm stream carries short kernels (NCCL send/recv, the dt all-reduce) that must not queue behind the
+    // thousands of CTAs of a compute kernel launched a moment earlier on the main stream: highest priority
+    int lo = 0, hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const char *e = getenv("PPK_COMM_PRIORITY");
+    const bool high = !e || atoi(e) != 0;
+    CUDA_TRY(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, high ? hi : lo));
+  }
   h->stream = h->own_stream;
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_xy, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_dt, cudaEventDisableTiming));
+  if (const char *e = getenv("PPK_EARLY_HALO")) h->early_halo = atoi(e) != 0;
+  if (const char *e = getenv("PPK_DEFER_DT")) h->defer_dt = atoi(e) != 0;
   int rc = 0;
   const long long n = g.ncell;
   if ((rc = alloc_doubles(h, &h->U[0], NBVAR * n)) || (rc = alloc_doubles(h, &h->U[1], NBVAR * n)) ||
@@ -371,6 +434,7 @@ int ppk_mhd3d_destroy(ppk_mhd3d *h) {
   for (auto e : h->pool) cudaEventDestroy(e);
   if (h->ev_xy) cudaEventDestroy(h->ev_xy);
   if (h->ev_halo) cudaEventDestroy(h->ev_halo);
+  if (h->ev_dt) cudaEventDestroy(h->ev_dt);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   delete h;
@@ -380,6 +444,8 @@ int ppk_mhd3d_destroy(ppk_mhd3d *h) {
 int ppk_mhd3d_upload(ppk_mhd3d *h, const double *u_host) {
   if (!h || !u_host) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
   DeviceGuard guard(h->device);
+  if (int rc = settle_halo(h)) return rc;
+  h->halo_posted = nullptr;  // the array is replaced: its ghosts are exchanged again at the next step
   CUDA_TRY(cudaMemcpyAsync(h->cur(), u_host, (size_t)NBVAR * h->g.ncell * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   return 0;
 }
@@ -387,6 +453,7 @@ int ppk_mhd3d_upload(ppk_mhd3d *h, const double *u_host) {
 int ppk_mhd3d_download(ppk_mhd3d *h, double *u_host) {
   if (!h || !u_host) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
   DeviceGuard guard(h->device);
+  if (int rc = settle_halo(h)) return rc;
   CUDA_TRY(cudaMemcpyAsync(u_host, h->cur(), (size_t)NBVAR * h->g.ncell * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;
@@ -395,6 +462,7 @@ int ppk_mhd3d_download(ppk_mhd3d *h, double *u_host) {
 int ppk_mhd3d_download_async(ppk_mhd3d *h, double *u_host) {
   if (!h || !u_host) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
   DeviceGuard guard(h->device);
+  if (int rc = settle_halo(h)) return rc;
   CUDA_TRY(cudaMemcpyAsync(u_host, h->cur(), (size_t)NBVAR * h->g.ncell * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   return 0;
 }
@@ -402,6 +470,7 @@ int ppk_mhd3d_download_async(ppk_mhd3d *h, double *u_host) {
 int ppk_mhd3d_set_time(ppk_mhd3d *h, double t, double t_end, long iteration) {
   if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
   DeviceGuard guard(h->device);
+  if (int rc = settle_halo(h)) return rc;
   // keep the array that is current now current after the parity change
   if (((iteration ^ h->host_iteration) & 1) != 0) std::swap(h->U[0], h->U[1]);
   StepState st{};

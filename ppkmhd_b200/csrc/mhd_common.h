@@ -54,7 +54,8 @@ enum KernelKind {
 // Launchers exported by each arithmetic build (mhd_kernels.cu compiled twice).
 struct KernelTable {
   const char *mode;
-  void (*boundary)(const GridParams &g, double *U, int dir, cudaStream_t s);
+  // x / y ghost fill of the planes k in [k0, k1); dir 2 (z) always fills whole planes
+  void (*boundary)(const GridParams &g, double *U, int dir, int k0, int k1, cudaStream_t s);
   void (*prim_dt)(const GridParams &g, const double *U, double *Q, StepState *st, int k0, int k1, cudaStream_t s);
   void (*finalize_dt)(const GridParams &g, StepState *st, cudaStream_t s);
   void (*advance_time)(StepState *st, cudaStream_t s);
@@ -65,7 +66,7 @@ struct KernelTable {
   void (*flux)(const GridParams &g, int dir, const double *BASIS, double *F, const void *tma, cudaStream_t s);
   void (*emf)(const GridParams &g, int edir, const double *BASIS, const double *DBF, double *EMF, const void *tma, cudaStream_t s);
   void (*update)(const GridParams &g, const StepState *st, const double *Uin, double *Uout, const double *Fx,
-                 const double *Fy, const double *Fz, const double *EMF, cudaStream_t s);
+                 const double *Fy, const double *Fz, const double *EMF, int k0, int k1, cudaStream_t s);
   void (*diagnostics)(const GridParams &g, const double *U, double *out9, cudaStream_t s);
   void (*fastmath_selftest)(int n, const double *x, double *rcp, double *sq, double *rsq, cudaStream_t s);
   // fused fluxes + EMFs + update; split != 0: two launches (hydro part, CT part)

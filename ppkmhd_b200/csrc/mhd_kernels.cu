@@ -590,11 +590,13 @@ DEV double mag_riemann2d_hlld(double gamma0, double smallc, const Corner &LL, co
 
 // Ghost fill of one direction (both faces), MakeBoundariesFunctor3D_MHD<face>
 // (BoundariesFunctors.h:749-1053). Faces whose BC is BC_COPY belong to the halo exchange.
+// For x and y only the planes k in [kb0, kb0+nkb) are filled (the whole array, or the planes around an
+// in-flight z exchange).
 template <int DIR>
-__global__ void k_boundary(const GridParams g, double *__restrict__ U) {
+__global__ void k_boundary(const GridParams g, double *__restrict__ U, const int kb0, const int nkb) {
   const int gw = g.gw;
   const int e0 = DIR == 0 ? g.jsize : g.isize;
-  const int e1 = DIR == 2 ? g.jsize : g.ksize;
+  const int e1 = DIR == 2 ? g.jsize : nkb;
   const int n = DIR == 0 ? g.nx : (DIR == 1 ? g.ny : g.nz);
   const long long total = 2LL * gw * e0 * e1;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -612,8 +614,8 @@ __global__ void k_boundary(const GridParams g, double *__restrict__ U) {
   else if (bc == BC_NEUMANN) c0 = hi ? n + gw - 1 : gw;
   else c0 = hi ? c - n : n + c;
   long long dst, src;
-  if (DIR == 0) { dst = cidx(g, c, a, b); src = cidx(g, c0, a, b); }
-  else if (DIR == 1) { dst = cidx(g, a, c, b); src = cidx(g, a, c0, b); }
+  if (DIR == 0) { dst = cidx(g, c, a, b + kb0); src = cidx(g, c0, a, b + kb0); }
+  else if (DIR == 1) { dst = cidx(g, a, c, b + kb0); src = cidx(g, a, c0, b + kb0); }
   else { dst = cidx(g, a, b, c); src = cidx(g, a, b, c0); }
   const int vflip = IU + DIR, bflip = IA + DIR;
 #pragma unroll
@@ -1221,8 +1223,8 @@ __global__ void __launch_bounds__(FluxCfg<D>::THREADS, FluxCfg<D>::MINB)
 __global__ void __launch_bounds__(256) k_update(const GridParams g, const StepState *__restrict__ stp,
                                                 const double *__restrict__ Uin, double *__restrict__ Uout,
                                                 const double *__restrict__ Fx, const double *__restrict__ Fy,
-                                                const double *__restrict__ Fz, const double *__restrict__ EMF) {
-  const int k = blockIdx.y;
+                                                const double *__restrict__ Fz, const double *__restrict__ EMF, const int kb0) {
+  const int k = kb0 + blockIdx.y;
   const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned jj = t / (unsigned)g.isize;
   const int i = (int)(t - jj * (unsigned)g.isize), j = (int)jj;
@@ -1723,13 +1725,15 @@ __global__ void k_fastmath_selftest(int n, const double *x, double *rcp, double 
 // ---------------------------------------------------------------------------------------------
 static inline unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
-static void l_boundary(const GridParams &g, double *U, int dir, cudaStream_t s) {
-  const long long e0 = dir == 0 ? g.jsize : g.isize, e1 = dir == 2 ? g.jsize : g.ksize;
+static void l_boundary(const GridParams &g, double *U, int dir, int k0, int k1, cudaStream_t s) {
+  if (dir == 2) { k0 = 0; k1 = g.ksize; }
+  if (k1 <= k0) return;
+  const long long e0 = dir == 0 ? g.jsize : g.isize, e1 = dir == 2 ? g.jsize : k1 - k0;
   const long long total = 2LL * g.gw * e0 * e1;
   const int bs = 256;
-  if (dir == 0) k_boundary<0><<<cdiv(total, bs), bs, 0, s>>>(g, U);
-  else if (dir == 1) k_boundary<1><<<cdiv(total, bs), bs, 0, s>>>(g, U);
-  else k_boundary<2><<<cdiv(total, bs), bs, 0, s>>>(g, U);
+  if (dir == 0) k_boundary<0><<<cdiv(total, bs), bs, 0, s>>>(g, U, k0, k1 - k0);
+  else if (dir == 1) k_boundary<1><<<cdiv(total, bs), bs, 0, s>>>(g, U, k0, k1 - k0);
+  else k_boundary<2><<<cdiv(total, bs), bs, 0, s>>>(g, U, 0, g.ksize);
 }
 static void l_prim_dt(const GridParams &g, const double *U, double *Q, StepState *st, int k0, int k1, cudaStream_t s) {
   if (k1 <= k0) return;
@@ -1854,10 +1858,11 @@ static void l_emf(const GridParams &g, int e, const double *BASIS, const double 
   else launch_emf<2>(g, BASIS, DBF, EMF, (const TmaCtx *)tma, s);
 }
 static void l_update(const GridParams &g, const StepState *st, const double *Uin, double *Uout, const double *Fx,
-                     const double *Fy, const double *Fz, const double *EMF, cudaStream_t s) {
+                     const double *Fy, const double *Fz, const double *EMF, int k0, int k1, cudaStream_t s) {
+  if (k1 <= k0) return;
   const int bs = 256;
-  dim3 grid(cdiv((long long)g.isize * g.jsize, bs), g.ksize);
-  k_update<<<grid, bs, 0, s>>>(g, st, Uin, Uout, Fx, Fy, Fz, EMF);
+  dim3 grid(cdiv((long long)g.isize * g.jsize, bs), k1 - k0);
+  k_update<<<grid, bs, 0, s>>>(g, st, Uin, Uout, Fx, Fy, Fz, EMF, k0);
 }
 static void l_consume(const GridParams &g, const StepState *st, const double *BASIS, const double *DBF, const double *Uin,
                       double *Uout, int split, cudaStream_t s) {
