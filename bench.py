@@ -212,6 +212,33 @@ def cpu_reference_throughput(n, steps, warmup, threads):
     return n ** 3 * steps / dt * 1e-6, kind, dt / steps
 
 
+REF_CUDA = os.path.join(ROOT, "oracle", "_ref", "cuda", "ppkMHD_cuda")
+REF_CUDA_SHIM = os.path.join(ROOT, "oracle", "_ref", "cuda", "libcc_shim.so")
+
+
+def ref_cuda_throughput(n, device):
+    """The reference's OWN Kokkos-CUDA kernels on this GPU (oracle/ref_build/Makefile.cuda: unmodified sources, sm_90 SASS +
+    compute_90 PTX JIT-compiled for sm_100; cc_shim.c makes its Kokkos 4.3 accept a 10.x device). Same ini as our arm,
+    implementationVersion 0; (T(25 steps) - T(5 steps)) / 20 after a 1-step run that fills the JIT cache. Not the
+    contract's reference arm (that is the CPU build): an extra, like-for-like GPU baseline."""
+    if not (os.path.exists(REF_CUDA) and os.path.exists(REF_CUDA_SHIM)):
+        return None
+    env = dict(os.environ, LD_PRELOAD=REF_CUDA_SHIM, CUDA_VISIBLE_DEVICES=str(device),
+               LD_LIBRARY_PATH="/usr/local/cuda/lib64:" + os.environ.get("LD_LIBRARY_PATH", ""))
+    times = {}
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            for ns in (1, 5, 25):
+                open(os.path.join(tmp, "run.ini"), "w").write(make_ini(n, 1, ns))
+                out = subprocess.run([REF_CUDA, "run.ini"], cwd=tmp, env=env, capture_output=True, text=True, timeout=600).stdout
+                times[ns] = float(re.search(r"total\s+time\s*:\s*([0-9.]+)", out).group(1))
+    except Exception as exc:  # the baseline is optional: report why it is missing
+        return {"unavailable": repr(exc)[:200]}
+    spp = max(times[25] - times[5], 1e-9) / 20
+    return {"value": n ** 3 / spp * 1e-6, "unit": UNIT, "ms_per_step": spp * 1e3, "kind": "reference Kokkos-CUDA build (v0), same GPU",
+            "sample": f"Orszag-Tang 3D kt=1 {n}^3, 20 steps (difference of a 25- and a 5-step run), interior cells counted"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -423,6 +450,11 @@ def run_ours(args):
                "sample": f"Orszag-Tang 3D kt=1 {args.ref_n}^3, 6 timed steps after 2 warm-up (difference of two runs of oracle/_ref/ppkMHD, "
                          f"Kokkos-OpenMP, implementationVersion=0); {spp * 1e3:.0f} ms/step"}
 
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_ref_cuda:
+        solver.synchronize()
+        ref_cuda = ref_cuda_throughput(n, local)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -436,6 +468,7 @@ def run_ours(args):
                        "cells_with_ghosts_per_gpu": int(np.prod(p.shape[1:])),
                        "reference_style_value_with_ghosts": value * float(np.prod(p.shape[1:])) / float(n) ** 3},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "reference_cuda_baseline": ref_cuda,
             "per_kernel_ms": {k: round(v["ms_per_step"], 4) for k, v in per_kernel.items()},
             "profiled_step_ms": step_ms_prof,
             "sim": {"t": t_sim, "dt": dt_sim, "iteration": it, "max_divB": divb, "device_GB": solver.device_bytes() / 1e9},
@@ -459,6 +492,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=9)
     ap.add_argument("--e2e-depth", type=int, default=3, help="solver handles (batches) in flight in the e2e leg at N=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference's Kokkos-CUDA build on the same GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

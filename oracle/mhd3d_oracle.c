@@ -698,6 +698,67 @@ static void riemann_hlld(const orc_params *p, state_t ql, state_t qr, state_t fl
   flux[IC] = co * uo - a * wo;
 }
 
+static void find_mhd_flux(const orc_params *p, const state_t q, state_t cvar, state_t ff)
+{
+  /* src/shared/mhd_utils.h:175-231 (cIso == 0) */
+  const double entho = 1.0 / (p->gamma0 - 1.0);
+  double d = q[ID], pr = q[IP], u = q[IU], v = q[IV], w = q[IW], a = q[IA], b = q[IB], c = q[IC];
+  double ecin = 0.5 * (u * u + v * v + w * w) * d;
+  double emag = 0.5 * (a * a + b * b + c * c);
+  double etot = pr * entho + ecin + emag;
+  double ptot = pr + emag;
+  cvar[ID] = d; cvar[IP] = etot; cvar[IU] = d * u; cvar[IV] = d * v; cvar[IW] = d * w;
+  cvar[IA] = a; cvar[IB] = b; cvar[IC] = c;
+  ff[ID] = d * u;
+  ff[IP] = (etot + ptot) * u - a * (a * u + b * v + c * w);
+  ff[IU] = d * u * u - a * a + ptot;
+  ff[IV] = d * u * v - a * b;
+  ff[IW] = d * u * w - a * c;
+  ff[IA] = 0.0;
+  ff[IB] = b * u - a * v;
+  ff[IC] = c * u - a * w;
+}
+
+static void riemann_hll(const orc_params *p, state_t ql, state_t qr, state_t flux)
+{
+  /* src/shared/RiemannSolvers_MHD.h:27-69 */
+  double bx_mean = 0.5 * (ql[IA] + qr[IA]);
+  ql[IA] = bx_mean;
+  qr[IA] = bx_mean;
+  state_t ul, fl, ur, fr;
+  find_mhd_flux(p, ql, ul, fl);
+  find_mhd_flux(p, qr, ur, fr);
+  double cfl_ = fast_speed(p, ql, 0), cfr = fast_speed(p, qr, 0);
+  double vl = ql[IU], vr = qr[IU];
+  double sl = fmin(fmin(vl, vr) - fmax(cfl_, cfr), 0.0);
+  double sr = fmax(fmax(vl, vr) + fmax(cfl_, cfr), 0.0);
+  for (int v = 0; v < NVAR; ++v) flux[v] = (sr * fl[v] - sl * fr[v] + sr * sl * (ur[v] - ul[v])) / (sr - sl);
+}
+
+static void riemann_llf(const orc_params *p, state_t ql, state_t qr, state_t flux)
+{
+  /* src/shared/RiemannSolvers_MHD.h:83-111 ; find_speed_info (scalar overload) mhd_utils.h:377-402 */
+  double bx_mean = 0.5 * (ql[IA] + qr[IA]);
+  ql[IA] = bx_mean;
+  qr[IA] = bx_mean;
+  state_t ul, fl, ur, fr;
+  find_mhd_flux(p, ql, ul, fl);
+  find_mhd_flux(p, qr, ur, fr);
+  for (int v = 0; v < NVAR; ++v) flux[v] = (fl[v] + fr[v]) / 2;
+  double cleft = fast_speed(p, ql, 0) + fabs(ql[IU]);
+  double cright = fast_speed(p, qr, 0) + fabs(qr[IU]);
+  double vel_info = fmax(cleft, cright);
+  for (int v = 0; v < NVAR; ++v) flux[v] -= vel_info * (ur[v] - ul[v]) / 2;
+}
+
+static void riemann_mhd(const orc_params *p, state_t ql, state_t qr, state_t flux)
+{
+  /* src/shared/RiemannSolvers_MHD.h:372-392 */
+  if (p->riemann == 2) riemann_hll(p, ql, qr, flux);
+  else if (p->riemann == 1) riemann_llf(p, ql, qr, flux);
+  else riemann_hlld(p, ql, qr, flux);
+}
+
 static void swap2(double *a, double *b) { double t = *a; *a = *b; *b = t; }
 
 static void compute_fluxes(const orc_params *p, orc_scratch *s)
@@ -711,21 +772,21 @@ static void compute_fluxes(const orc_params *p, orc_scratch *s)
         state_t ql, qr, f;
         load_state(p, s->a8[S_QM_X], i - 1, j, k, ql);
         load_state(p, s->a8[S_QP_X], i, j, k, qr);
-        riemann_hlld(p, ql, qr, f);
+        riemann_mhd(p, ql, qr, f);
         store_state(p, s->a8[S_FX], i, j, k, f);
 
         load_state(p, s->a8[S_QM_Y], i, j - 1, k, ql);
         swap2(&ql[IU], &ql[IV]); swap2(&ql[IA], &ql[IB]);
         load_state(p, s->a8[S_QP_Y], i, j, k, qr);
         swap2(&qr[IU], &qr[IV]); swap2(&qr[IA], &qr[IB]);
-        riemann_hlld(p, ql, qr, f);
+        riemann_mhd(p, ql, qr, f);
         store_state(p, s->a8[S_FY], i, j, k, f);
 
         load_state(p, s->a8[S_QM_Z], i, j, k - 1, ql);
         swap2(&ql[IU], &ql[IW]); swap2(&ql[IA], &ql[IC]);
         load_state(p, s->a8[S_QP_Z], i, j, k, qr);
         swap2(&qr[IU], &qr[IW]); swap2(&qr[IA], &qr[IC]);
-        riemann_hlld(p, ql, qr, f);
+        riemann_mhd(p, ql, qr, f);
         store_state(p, s->a8[S_FZ], i, j, k, f);
       }
 }

@@ -46,6 +46,9 @@ typedef struct orc_params {
   /* Cartesian decomposition (HydroParams.cpp:231-233) and this rank's position in it */
   int mx, my, mz;
   int px, py, pz;
+  /* face Riemann solver, enum RiemannSolverType of src/shared/enums.h: 1 llf, 2 hll, 4 hlld (HydroParams.cpp:175-198);
+   * the edge EMFs always use the 2-D HLLD solver (MHDRunFunctors3D.h:2100-2238) */
+  int riemann;
 } orc_params;
 
 /* float-precision parse of an ini value: ConfigMap.cpp:37-46 (strtof) */

@@ -39,6 +39,7 @@ class OrcParams(C.Structure):
         + [("bc", C.c_int * 6)]
         + [(n, C.c_double) for n in ("gamma0", "cfl", "slope_type", "smallr", "smallc", "smallp")]
         + [(n, C.c_int) for n in ("mx", "my", "mz", "px", "py", "pz")]
+        + [("riemann", C.c_int)]
     )
 
     @property
@@ -308,7 +309,7 @@ def run_reference(ini_text: str, threads: int | None = None, workdir: str | None
 
 
 def make_ini(problem="orszag_tang", n=(32, 32, 32), nstepmax=5, tend=1.0, noutput=1, bounds=None, bc=3,
-             cfl=0.8, extra="", mz=1, prefix="run", nlog=10) -> str:
+             cfl=0.8, extra="", mz=1, prefix="run", nlog=10, riemann="hlld") -> str:
     """The ini family of SURVEY 8(d): gamma0=1.666 cfl=0.8 slope_type=2 hlld smallr=smallc=1e-8, v0."""
     b = bounds or (0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
     bcs = bc if isinstance(bc, (list, tuple)) else [bc] * 6
@@ -338,7 +339,7 @@ niter_riemann=10
 iorder=2
 slope_type=2
 problem={problem}
-riemann=hlld
+riemann={riemann}
 smallr=1e-8
 smallc=1e-8
 [mpi]
