@@ -29,7 +29,7 @@ extern "C" {
 enum ppk_status {
   PPK_OK = 0,
   PPK_ERR_INVALID_ARGUMENT = 10001,
-  PPK_ERR_UNSUPPORTED = 10002, /* e.g. riemann != hlld, mx*my != 1, ghost width != 3 */
+  PPK_ERR_UNSUPPORTED = 10002, /* e.g. riemann = approx|hllc, mx*my != 1, ghost width != 3 */
   PPK_ERR_NO_DEVICE = 10003,
   PPK_ERR_NCCL = 10004,
   PPK_ERR_STATE = 10005
@@ -51,7 +51,7 @@ typedef struct ppk_mhd3d_params {
   double dx, dy, dz;   /* (xmax-xmin)/(nx*mx) ... (HydroParams.cpp:400-402) */
   int boundary_type[6];/* xmin,xmax,ymin,ymax,zmin,zmax of the GLOBAL domain (enum ppk_bc) */
   double gamma0, cfl, slope_type, smallr, smallc, smallp; /* smallp = smallc*smallc/gamma0 (HydroParams.cpp:441) */
-  int riemann_solver;  /* enum ppk_riemann; only PPK_RIEMANN_HLLD is implemented */
+  int riemann_solver;  /* enum ppk_riemann: hlld, hll or llf for the face fluxes (the edge EMFs always use 2-D HLLD) */
   int implementation_version; /* only 0 (the deterministic variant, SolverMHDMuscl.cpp:494-517) */
   int mx, my, mz;      /* Cartesian decomposition ([mpi] mx,my,mz); this build supports z-slabs: mx = my = 1 */
   int rank_x, rank_y, rank_z; /* position of this slab (replaces myMpiPos, HydroParams.cpp:269-277) */

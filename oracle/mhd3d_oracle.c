@@ -732,7 +732,7 @@ static void riemann_hll(const orc_params *p, state_t ql, state_t qr, state_t flu
   double vl = ql[IU], vr = qr[IU];
   double sl = fmin(fmin(vl, vr) - fmax(cfl_, cfr), 0.0);
   double sr = fmax(fmax(vl, vr) + fmax(cfl_, cfr), 0.0);
-  for (int v = 0; v < NVAR; ++v) flux[v] = (sr * fl[v] - sl * fr[v] + sr * sl * (ur[v] - ul[v])) / (sr - sl);
+  for (int v = 0; v < NV; ++v) flux[v] = (sr * fl[v] - sl * fr[v] + sr * sl * (ur[v] - ul[v])) / (sr - sl);
 }
 
 static void riemann_llf(const orc_params *p, state_t ql, state_t qr, state_t flux)
@@ -744,11 +744,11 @@ static void riemann_llf(const orc_params *p, state_t ql, state_t qr, state_t flu
   state_t ul, fl, ur, fr;
   find_mhd_flux(p, ql, ul, fl);
   find_mhd_flux(p, qr, ur, fr);
-  for (int v = 0; v < NVAR; ++v) flux[v] = (fl[v] + fr[v]) / 2;
+  for (int v = 0; v < NV; ++v) flux[v] = (fl[v] + fr[v]) / 2;
   double cleft = fast_speed(p, ql, 0) + fabs(ql[IU]);
   double cright = fast_speed(p, qr, 0) + fabs(qr[IU]);
   double vel_info = fmax(cleft, cright);
-  for (int v = 0; v < NVAR; ++v) flux[v] -= vel_info * (ur[v] - ul[v]) / 2;
+  for (int v = 0; v < NV; ++v) flux[v] -= vel_info * (ur[v] - ul[v]) / 2;
 }
 
 static void riemann_mhd(const orc_params *p, state_t ql, state_t qr, state_t flux)

@@ -153,6 +153,8 @@ def params_from_config(cfg: Config, rank_pos=(0, 0, 0)) -> OrcParams:
     p.slope_type = cfg.f("hydro", "slope_type", 1.0)
     p.smallc = cfg.f("hydro", "smallc", 1e-10)
     p.smallr = cfg.f("hydro", "smallr", 1e-10)
+    # HydroParams.cpp:175-198 (enum RiemannSolverType: approx 0, llf 1, hll 2, hllc 3, hlld 4)
+    p.riemann = {"approx": 0, "llf": 1, "hll": 2, "hllc": 3, "hlld": 4}.get(cfg.s("hydro", "riemann", "approx"), 0)
     lib().orc_params_finalize(C.byref(p))
     return p
 

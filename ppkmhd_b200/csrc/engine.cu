@@ -349,8 +349,8 @@ int ppk_mhd3d_create(const ppk_mhd3d_params *p, ppk_mhd3d **out) {
   if (!p || !out) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
   *out = nullptr;
   if (p->ghost_width != PPK_GHOST_WIDTH) return fail(PPK_ERR_UNSUPPORTED, "ghost_width must be 3 (MHD_Muscl_3D)");
-  if (p->riemann_solver != PPK_RIEMANN_HLLD)
-    return fail(PPK_ERR_UNSUPPORTED, "only riemann=hlld is implemented (the reference's 'approx' is a silent no-op flux for MHD)");
+  if (p->riemann_solver != PPK_RIEMANN_HLLD && p->riemann_solver != PPK_RIEMANN_HLL && p->riemann_solver != PPK_RIEMANN_LLF)
+    return fail(PPK_ERR_UNSUPPORTED, "riemann must be hlld, hll or llf (the reference's 'approx' and 'hllc' are silent no-op fluxes for MHD, RiemannSolvers_MHD.h:372-392)");
   if (p->implementation_version != 0)
     return fail(PPK_ERR_UNSUPPORTED, "only implementationVersion=0 (the deterministic reference variant) is implemented");
   if (p->mx != 1 || p->my != 1 || p->mz < 1) return fail(PPK_ERR_UNSUPPORTED, "only z-slab decompositions (mx=my=1) are supported");
@@ -373,6 +373,7 @@ int ppk_mhd3d_create(const ppk_mhd3d_params *p, ppk_mhd3d **out) {
   g.idx = 1.0 / p->dx; g.idy = 1.0 / p->dy; g.idz = 1.0 / p->dz;
   g.gamma0 = p->gamma0; g.cfl = p->cfl; g.slope_type = p->slope_type;
   g.smallr = p->smallr; g.smallc = p->smallc; g.smallp = p->smallp;
+  g.riemann = p->riemann_solver;
   for (int f = 0; f < 6; ++f) g.bc[f] = p->boundary_type[f];
   // z faces of a decomposed run: inner faces, and outer faces of a periodic domain, belong to the halo
   // exchange (HydroParams.cpp:300-351: neighborsBC = BC_COPY unless on the outer boundary).

@@ -6,6 +6,8 @@ namespace ppk {
 
 // variable order of the reference (src/shared/enums.h:17-34)
 enum { ID = 0, IP = 1, IU = 2, IV = 3, IW = 4, IA = 5, IB = 6, IC = 7, NBVAR = 8 };
+// RiemannSolverType of the reference (src/shared/enums.h); the 3-D MHD path implements llf, hll and hlld
+enum { RIEMANN_APPROX = 0, RIEMANN_LLF = 1, RIEMANN_HLL = 2, RIEMANN_HLLC = 3, RIEMANN_HLLD = 4 };
 enum { BC_UNDEFINED = 0, BC_DIRICHLET = 1, BC_NEUMANN = 2, BC_PERIODIC = 3, BC_COPY = 4 };
 
 // "Trace basis": what ComputeTraceFunctor3D_MHD (MHDRunFunctors3D.h:543-856) would expand into
@@ -32,6 +34,7 @@ struct GridParams {
   double dx, dy, dz;
   double idx, idy, idz;  // 1/dx, 1/dy, 1/dz (fast-arithmetic build only)
   double gamma0, cfl, slope_type, smallr, smallc, smallp;
+  int riemann;  // face Riemann solver (the edge EMFs always use the 2-D HLLD solver, like the reference)
   int bc[6];  // effective BC of this slab's faces (BC_COPY on faces owned by the halo exchange)
 };
 

@@ -345,6 +345,75 @@ DEV void riemann_hlld(double gamma0, double rl, double pl, double ul, double vl,
   f_w = ro * uo * wo - a * co;
 }
 
+// find_mhd_flux (mhd_utils.h:175-231, cIso == 0), hydro part: conservative variables and fluxes of (rho, E, mn, mt1, mt2)
+DEV void mhd_flux5(double gamma0, double d, double p, double u, double v, double w, double a, double b, double c,
+                   double cv[5], double ff[5]) {
+  const double entho = 1.0 / (gamma0 - 1.0);
+  const double ecin = 0.5 * (u * u + v * v + w * w) * d;
+  const double emag = 0.5 * (a * a + b * b + c * c);
+  const double etot = p * entho + ecin + emag;
+  const double ptot = p + emag;
+  cv[0] = d; cv[1] = etot; cv[2] = d * u; cv[3] = d * v; cv[4] = d * w;
+  ff[0] = d * u;
+  ff[1] = (etot + ptot) * u - a * (a * u + b * v + c * w);
+  ff[2] = d * u * u - a * a + ptot;
+  ff[3] = d * u * v - a * b;
+  ff[4] = d * u * w - a * c;
+}
+// riemann_hll (RiemannSolvers_MHD.h:27-69) and riemann_llf (:83-111), hydro fluxes only (the induction components of
+// the flux vector are never read: the field is advanced by the edge EMFs). Same frame as riemann_hlld.
+DEV void riemann_hll(double gamma0, double rl, double pl, double ul, double vl, double wl, double al, double bl, double cl,
+                     double rr, double pr, double ur, double vr, double wr, double ar, double br, double cr, double f[5]) {
+  const double a = 0.5 * (al + ar);
+  double cl5[5], fl5[5], cr5[5], fr5[5];
+  mhd_flux5(gamma0, rl, pl, ul, vl, wl, a, bl, cl, cl5, fl5);
+  mhd_flux5(gamma0, rr, pr, ur, vr, wr, a, br, cr, cr5, fr5);
+  double c2, d2;
+  fast_speed_common(gamma0, rl, pl, a, bl, cl, c2, d2);
+  const double cfl_ = fast_speed_dir(c2, d2, rl, a);
+  fast_speed_common(gamma0, rr, pr, a, br, cr, c2, d2);
+  const double cfr = fast_speed_dir(c2, d2, rr, a);
+  const double sl = fmin(fmin(ul, ur) - fmax(cfl_, cfr), 0.0);
+  const double sr = fmax(fmax(ul, ur) + fmax(cfl_, cfr), 0.0);
+#pragma unroll
+  for (int v = 0; v < 5; ++v) f[v] = (sr * fl5[v] - sl * fr5[v] + sr * sl * (cr5[v] - cl5[v])) / (sr - sl);
+}
+DEV void riemann_llf(double gamma0, double rl, double pl, double ul, double vl, double wl, double al, double bl, double cl,
+                     double rr, double pr, double ur, double vr, double wr, double ar, double br, double cr, double f[5]) {
+  const double a = 0.5 * (al + ar);
+  double cl5[5], fl5[5], cr5[5], fr5[5];
+  mhd_flux5(gamma0, rl, pl, ul, vl, wl, a, bl, cl, cl5, fl5);
+  mhd_flux5(gamma0, rr, pr, ur, vr, wr, a, br, cr, cr5, fr5);
+  double c2, d2;
+  fast_speed_common(gamma0, rl, pl, a, bl, cl, c2, d2);
+  const double cleft = fast_speed_dir(c2, d2, rl, a) + fabs(ul);  // find_speed_info, mhd_utils.h:377-402
+  fast_speed_common(gamma0, rr, pr, a, br, cr, c2, d2);
+  const double cright = fast_speed_dir(c2, d2, rr, a) + fabs(ur);
+  const double vel_info = fmax(cleft, cright);
+#pragma unroll
+  for (int v = 0; v < 5; ++v) {
+    f[v] = (fl5[v] + fr5[v]) / 2;
+    f[v] -= vel_info * (cr5[v] - cl5[v]) / 2;
+  }
+}
+// riemann_mhd (RiemannSolvers_MHD.h:372-392): the solver [hydro] riemann= selects (uniform over the grid)
+DEV void riemann_face(const GridParams &g, double rl, double pl, double ul, double vl, double wl, double al, double bl, double cl,
+                      double rr, double pr, double ur, double vr, double wr, double ar, double br, double cr, double &f_d,
+                      double &f_p, double &f_u, double &f_v, double &f_w) {
+  if (g.riemann == RIEMANN_HLLD) {
+#if PPK_EXACT
+    riemann_hlld(g.gamma0, rl, pl, ul, vl, wl, al, bl, cl, rr, pr, ur, vr, wr, ar, br, cr, f_d, f_p, f_u, f_v, f_w);
+#else
+    riemann_hlld_fast(g.gamma0, rl, pl, ul, vl, wl, al, bl, cl, rr, pr, ur, vr, wr, ar, br, cr, f_d, f_p, f_u, f_v, f_w);
+#endif
+  } else {
+    double f[5];
+    if (g.riemann == RIEMANN_HLL) riemann_hll(g.gamma0, rl, pl, ul, vl, wl, al, bl, cl, rr, pr, ur, vr, wr, ar, br, cr, f);
+    else riemann_llf(g.gamma0, rl, pl, ul, vl, wl, al, bl, cl, rr, pr, ur, vr, wr, ar, br, cr, f);
+    f_d = f[0]; f_p = f[1]; f_u = f[2]; f_v = f[3]; f_w = f[4];
+  }
+}
+
 // comparison chains of mhd_utils.h:36-77 (not fmax/fmin)
 DEV double max4(double a0, double a1, double a2, double a3) {
   double r = a0; r = (a1 > r) ? a1 : r; r = (a2 > r) ? a2 : r; r = (a3 > r) ? a3 : r; return r;
@@ -888,11 +957,7 @@ DEV void flux_face(const GridParams &g, const double *__restrict__ BASIS, long l
   const double b1r = BR_[(BQ + IA + T1) * N] - BR_[(SB + slope_b(D, T1)) * N];
   const double b2r = BR_[(BQ + IA + T2) * N] - BR_[(SB + slope_b(D, T2)) * N];
 
-#if PPK_EXACT
-  riemann_hlld(g.gamma0, rl, pl, unl, t1l, t2l, bnl, b1l, b2l, rr, pr, unr, t1r, t2r, bnr, b1r, b2r, fd, fp, fu, fv, fw);
-#else
-  riemann_hlld_fast(g.gamma0, rl, pl, unl, t1l, t2l, bnl, b1l, b2l, rr, pr, unr, t1r, t2r, bnr, b1r, b2r, fd, fp, fu, fv, fw);
-#endif
+  riemann_face(g, rl, pl, unl, t1l, t2l, bnl, b1l, b2l, rr, pr, unr, t1r, t2r, bnr, b1r, b2r, fd, fp, fu, fv, fw);
 }
 
 // One direction per launch (the unfused pipeline). Only faces the update reads are computed:
@@ -1207,11 +1272,7 @@ __global__ void __launch_bounds__(FluxCfg<D>::THREADS, FluxCfg<D>::MINB)
   const double b1r = sm[5 * S + oR] - sm[12 * S + oR];
   const double b2r = sm[6 * S + oR] - sm[13 * S + oR];
   double fd, fp, fu, fv, fw;
-#if PPK_EXACT
-  riemann_hlld(g.gamma0, rl, pl, unl, t1l, t2l, bnl, b1l, b2l, rr, pr, unr, t1r, t2r, bnr, b1r, b2r, fd, fp, fu, fv, fw);
-#else
-  riemann_hlld_fast(g.gamma0, rl, pl, unl, t1l, t2l, bnl, b1l, b2l, rr, pr, unr, t1r, t2r, bnr, b1r, b2r, fd, fp, fu, fv, fw);
-#endif
+  riemann_face(g, rl, pl, unl, t1l, t2l, bnl, b1l, b2l, rr, pr, unr, t1r, t2r, bnr, b1r, b2r, fd, fp, fu, fv, fw);
   const long long N = g.ncell;
   double *Fo = F + cidx(g, i, j, k);
   Fo[0 * N] = fd; Fo[1 * N] = fp; Fo[2 * N] = fu; Fo[3 * N] = fv; Fo[4 * N] = fw;
@@ -1447,13 +1508,7 @@ DEV void benign_state(double q[7]) {  // operands of a solve whose result nobody
   q[0] = 1.0; q[1] = 1.0; q[2] = 0.0; q[3] = 0.0; q[4] = 0.0; q[5] = 0.0; q[6] = 0.0;
 }
 DEV void hlld7(const GridParams &g, const double L[7], const double R[7], const double bn, double f[5]) {
-#if PPK_EXACT
-  riemann_hlld(g.gamma0, L[0], L[1], L[2], L[3], L[4], bn, L[5], L[6], R[0], R[1], R[2], R[3], R[4], bn, R[5], R[6], f[0], f[1],
-               f[2], f[3], f[4]);
-#else
-  riemann_hlld_fast(g.gamma0, L[0], L[1], L[2], L[3], L[4], bn, L[5], L[6], R[0], R[1], R[2], R[3], R[4], bn, R[5], R[6], f[0],
-                    f[1], f[2], f[3], f[4]);
-#endif
+  riemann_face(g, L[0], L[1], L[2], L[3], L[4], bn, L[5], L[6], R[0], R[1], R[2], R[3], R[4], bn, R[5], R[6], f[0], f[1], f[2], f[3], f[4]);
 }
 
 // shared-memory layout of k_hydro (doubles): per-thread slots are [component][thread] so that a warp's access is

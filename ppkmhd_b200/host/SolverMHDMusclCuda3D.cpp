@@ -173,9 +173,10 @@ SolverMHDMusclCuda3D::SolverMHDMusclCuda3D(HydroParams &params_, ConfigMap &conf
   solver_type = SOLVER_MUSCL_HANCOCK;
   m_nCells = (long)params.isize * params.jsize * params.ksize;  // ghosts included, like the reference
   m_nDofsPerCell = 1;
-  if (params.riemannSolverType != RIEMANN_HLLD) {
-    fprintf(stderr, "MHD_Muscl_3D (CUDA): riemann=%s is not implemented; only hlld is "
-                    "(the reference silently computes a zero flux for 'approx')\n",
+  if (params.riemannSolverType != RIEMANN_HLLD && params.riemannSolverType != RIEMANN_HLL &&
+      params.riemannSolverType != RIEMANN_LLF) {
+    fprintf(stderr, "MHD_Muscl_3D (CUDA): riemann=%s is not implemented; hlld, hll and llf are "
+                    "(the reference silently leaves the flux unset for 'approx' and 'hllc')\n",
             configMap.getString("hydro", "riemann", "approx").c_str());
     std::abort();
   }

@@ -26,7 +26,7 @@ BLAST = "[blast]\nradius=0.25\ndensity_in=1.0\ndensity_out=1.2\npressure_in=10.0
 LOOP = "[FieldLoop]\nradius=0.3\namplitude=0.001\nvflow=3\ndensity_in=1\n"
 
 CASES = {
-    # name: (problem, (nx,ny,nz), nsteps, extra, bounds, cfl, bc)
+    # name: (problem, (nx,ny,nz), nsteps, extra, bounds, cfl, bc[, riemann])
     "ot_16x12x8": ("orszag_tang", (16, 12, 8), 5, OT, None, 0.8, 3),
     "ot2p5d_16x16x4": ("orszag_tang", (16, 16, 4), 5, "", (0, 1, 0, 1, 0, 0.25), 0.8, 3),
     "blast_12x12x12": ("blast", (12, 12, 12), 6, BLAST, None, 0.8, 3),
@@ -34,12 +34,18 @@ CASES = {
     "blast_neumann_10x12x8": ("blast", (10, 12, 8), 6, BLAST, None, 0.8, 2),
     "blast_mixedbc_12x12x8": ("blast", (12, 12, 8), 6, BLAST, None, 0.8, [1, 2, 3, 3, 2, 1]),
     "fieldloop_24x12x12": ("field_loop", (24, 12, 12), 5, LOOP, (-1, 1, -0.5, 0.5, -0.5, 0.5), 0.4, 3),
+    # the other face solvers of riemann_mhd (RiemannSolvers_MHD.h:372-392)
+    "blast_hll_12x12x12": ("blast", (12, 12, 12), 6, BLAST, None, 0.8, 3, "hll"),
+    "ot_llf_16x12x8": ("orszag_tang", (16, 12, 8), 5, OT, None, 0.8, 3, "llf"),
+    "blast_llf_dirichlet_12x10x8": ("blast", (12, 10, 8), 6, BLAST, None, 0.8, 1, "llf"),
+    "ot_hll_16x12x8": ("orszag_tang", (16, 12, 8), 5, OT, None, 0.8, 3, "hll"),
 }
 
 
 def run(case):
-    problem, n, nsteps, extra, bounds, cfl, bc = CASES[case]
-    kw = dict(problem=problem, n=n, extra=extra, bounds=bounds, cfl=cfl, bc=bc, nlog=1, tend=10.0)
+    problem, n, nsteps, extra, bounds, cfl, bc = CASES[case][:7]
+    riemann = CASES[case][7] if len(CASES[case]) > 7 else "hlld"
+    kw = dict(problem=problem, n=n, extra=extra, bounds=bounds, cfl=cfl, bc=bc, nlog=1, tend=10.0, riemann=riemann)
     out = {}
     for tag, ns in (("step1", 1), ("stepN", nsteps)):
         ini = O.make_ini(nstepmax=ns, **kw)
@@ -60,6 +66,8 @@ def run(case):
 if __name__ == "__main__":
     here = os.path.dirname(os.path.abspath(__file__))
     for case in CASES:
+        if len(sys.argv) > 1 and case not in sys.argv[1:]:
+            continue
         data = run(case)
         np.savez_compressed(os.path.join(here, case + ".npz"), **data)
         print(case, {k: getattr(v, "shape", None) for k, v in data.items()})

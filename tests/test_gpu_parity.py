@@ -196,9 +196,10 @@ def test_full_size_properties_256():
 def test_error_paths():
     g = np.load(f"{GOLDEN}/ot_16x12x8.npz")
     ini = str(g["ini"])
-    p, _, _ = ppk.params_from_ini(ini.replace("riemann=hlld", "riemann=hll"))
-    with pytest.raises(ppk.PpkError, match="hlld"):
-        ppk.Mhd3d(p)
+    for bad in ("hllc", "approx", "nonsense"):  # the reference leaves the MHD flux unset for these (RiemannSolvers_MHD.h:372-392)
+        p, _, _ = ppk.params_from_ini(ini.replace("riemann=hlld", "riemann=" + bad))
+        with pytest.raises(ppk.PpkError, match="hlld"):
+            ppk.Mhd3d(p)
     p, _, _ = ppk.params_from_ini(ini.replace("implementationVersion=0", "implementationVersion=2"))
     with pytest.raises(ppk.PpkError, match="implementationVersion"):
         ppk.Mhd3d(p)

@@ -37,7 +37,8 @@ def test_params_match_oracle_and_float_parsing(case, oracle_mod):
         assert getattr(p, f) == getattr(o, f), f
     assert list(p.boundary_type) == list(o.bc)
     assert p.gamma0 == 1.66600000858306884765625  # float-precision parse
-    assert p.ghost_width == 3 and p.riemann_solver == 4 and p.implementation_version == 0
+    assert p.ghost_width == 3 and p.riemann_solver == o.riemann and p.implementation_version == 0
+    assert p.riemann_solver == {"hll": 2, "llf": 1}.get(case.split("_")[1], 4)
     assert t_end == 10.0 and nstep == int(np.load(f"{GOLDEN}/{case}.npz")["nsteps"])
 
 
