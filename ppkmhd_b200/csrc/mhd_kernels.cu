@@ -396,11 +396,14 @@ DEV void riemann_llf(double gamma0, double rl, double pl, double ul, double vl, 
     f[v] -= vel_info * (cr5[v] - cl5[v]) / 2;
   }
 }
-// riemann_mhd (RiemannSolvers_MHD.h:372-392): the solver [hydro] riemann= selects (uniform over the grid)
+// riemann_mhd (RiemannSolvers_MHD.h:372-392): the solver [hydro] riemann= selects (uniform over the grid).
+// RS >= 0 fixes the solver at compile time (the hot TMA kernels are instantiated for HLLD alone), RS < 0 reads g.riemann.
+template <int RS = -1>
 DEV void riemann_face(const GridParams &g, double rl, double pl, double ul, double vl, double wl, double al, double bl, double cl,
                       double rr, double pr, double ur, double vr, double wr, double ar, double br, double cr, double &f_d,
                       double &f_p, double &f_u, double &f_v, double &f_w) {
-  if (g.riemann == RIEMANN_HLLD) {
+  const int rs = RS >= 0 ? RS : g.riemann;
+  if (rs == RIEMANN_HLLD) {
 #if PPK_EXACT
     riemann_hlld(g.gamma0, rl, pl, ul, vl, wl, al, bl, cl, rr, pr, ur, vr, wr, ar, br, cr, f_d, f_p, f_u, f_v, f_w);
 #else
@@ -408,7 +411,7 @@ DEV void riemann_face(const GridParams &g, double rl, double pl, double ul, doub
 #endif
   } else {
     double f[5];
-    if (g.riemann == RIEMANN_HLL) riemann_hll(g.gamma0, rl, pl, ul, vl, wl, al, bl, cl, rr, pr, ur, vr, wr, ar, br, cr, f);
+    if (rs == RIEMANN_HLL) riemann_hll(g.gamma0, rl, pl, ul, vl, wl, al, bl, cl, rr, pr, ur, vr, wr, ar, br, cr, f);
     else riemann_llf(g.gamma0, rl, pl, ul, vl, wl, al, bl, cl, rr, pr, ur, vr, wr, ar, br, cr, f);
     f_d = f[0]; f_p = f[1]; f_u = f[2]; f_v = f[3]; f_w = f[4];
   }
@@ -789,13 +792,13 @@ __global__ void k_advance_time(StepState *st) {
 // slope_unsplit_mhd_3d MHDBaseFunctor3D.h:561-668) on [1,size-1)^3.
 __global__ void __launch_bounds__(256) k_elec_dbf(const GridParams g, const double *__restrict__ U,
                                                   const double *__restrict__ Q, double *__restrict__ E,
-                                                  double *__restrict__ DBF) {
+                                                  double *__restrict__ DBF, const int jslab) {
   const int k = 1 + blockIdx.y;
   const unsigned ni = g.isize - 2;
   const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned jj = t / ni;
-  const int i = 1 + (int)(t - jj * ni), j = 1 + (int)jj;
-  if (j >= g.jsize - 1) return;
+  const int i = 1 + (int)(t - jj * ni), j = 1 + (int)(blockIdx.z * jslab + jj);  // y-slabs: see slab_rows()
+  if (jj >= (unsigned)jslab || j >= g.jsize - 1) return;
   const long long N = g.ncell, sj = g.isize, sk = (long long)g.isize * g.jsize;
   const long long c = cidx(g, i, j, k);
   const double *Qu = Q + IU * N, *Qv = Q + IV * N, *Qw = Q + IW * N;
@@ -836,13 +839,14 @@ __global__ void __launch_bounds__(256) k_elec_dbf(const GridParams g, const doub
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_trace(const GridParams g, const StepState *__restrict__ stp,
                                                      const double *__restrict__ U, const double *__restrict__ Q,
-                                                     const double *__restrict__ E, double *__restrict__ BASIS) {
+                                                     const double *__restrict__ E, double *__restrict__ BASIS,
+                                                     const int jslab) {
   const int k = 2 + blockIdx.y;
   const unsigned ni = g.isize - 4;
   const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned jj = t / ni;
-  const int i = 2 + (int)(t - jj * ni), j = 2 + (int)jj;
-  if (j >= g.jsize - 2) return;
+  const int i = 2 + (int)(t - jj * ni), j = 2 + (int)(blockIdx.z * jslab + jj);  // y-slabs: see slab_rows()
+  if (jj >= (unsigned)jslab || j >= g.jsize - 2) return;
   const long long N = g.ncell, sj = g.isize, sk = (long long)g.isize * g.jsize;
   const long long c = cidx(g, i, j, k);
   const double dtdx = stp->dtdx, dtdy = stp->dtdy, dtdz = stp->dtdz;
@@ -1184,17 +1188,24 @@ DEV Corner edge_state_smem(const GridParams &g, const double *__restrict__ sm, i
   return c;
 }
 
-template <int E>
+template <int E, bool SLAB>
 __global__ void __launch_bounds__(EmfCfg<E>::THREADS, EmfCfg<E>::MINB)
   k_emf_tma(const GridParams g, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapD,
-            double *__restrict__ EMF) {
+            double *__restrict__ EMF, const int yslab, const unsigned ymagic) {
   using Cfg = EmfCfg<E>;
   constexpr int D1 = (E + 1) % 3, D2 = (E + 2) % 3;
   extern __shared__ __align__(128) double sm[];
   __shared__ unsigned long long bar;
   const int tid = threadIdx.x;
   const int tx = tid % Cfg::TX, ty = (tid / Cfg::TX) % Cfg::TY, tz = tid / (Cfg::TX * Cfg::TY);
-  const int i0 = g.gw + blockIdx.x * Cfg::TX, j0 = g.gw + blockIdx.y * Cfg::TY, k0 = g.gw + blockIdx.z * Cfg::TZ;
+  // grid (x-tiles, y-tiles, z-tiles) when one y-slab covers the plane (!SLAB); otherwise x = x-tiles,
+  // y = (z-tile, y-tile inside a slab of `yslab` tiles), z = slab -- see slab_rows()
+  // (blockIdx.y / yslab by multiply-high: exact for 16-bit operands, keeps the prologue off the slow integer division)
+  const unsigned ydiv = SLAB ? __umulhi(blockIdx.y, ymagic) : 0u;
+  const int by = SLAB ? blockIdx.z * yslab + (int)(blockIdx.y - ydiv * yslab) : blockIdx.y;
+  const int bz = SLAB ? (int)ydiv : blockIdx.z;
+  const int i0 = g.gw + blockIdx.x * Cfg::TX, j0 = g.gw + by * Cfg::TY, k0 = g.gw + bz * Cfg::TZ;
+  if (SLAB && j0 >= g.gw + g.ny + (E == 1 ? 0 : 1)) return;  // the last slab may be short
   if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
   if (tid == 0) {
@@ -1230,15 +1241,23 @@ DEV constexpr int flux_slot_comp(int s) {
   return BFACE + D;
 }
 
-template <int D>
+template <int D, bool SLAB, int RS>
 __global__ void __launch_bounds__(FluxCfg<D>::THREADS, FluxCfg<D>::MINB)
-  k_flux_tma(const GridParams g, const __grid_constant__ CUtensorMap mapB, double *__restrict__ F) {
+  k_flux_tma(const GridParams g, const __grid_constant__ CUtensorMap mapB, double *__restrict__ F, const int yslab,
+             const unsigned ymagic) {
   using Cfg = FluxCfg<D>;
   extern __shared__ __align__(128) double sm[];
   __shared__ unsigned long long bar;
   const int tid = threadIdx.x;
   const int tx = tid % Cfg::TX, ty = (tid / Cfg::TX) % Cfg::TY, tz = tid / (Cfg::TX * Cfg::TY);
-  const int i0 = g.gw + blockIdx.x * Cfg::TX, j0 = g.gw + blockIdx.y * Cfg::TY, k0 = g.gw + blockIdx.z * Cfg::TZ;
+  // grid (x-tiles, y-tiles, z-tiles) when one y-slab covers the plane (!SLAB); otherwise x = x-tiles,
+  // y = (z-tile, y-tile inside a slab of `yslab` tiles), z = slab -- see slab_rows()
+  // (blockIdx.y / yslab by multiply-high: exact for 16-bit operands, keeps the prologue off the slow integer division)
+  const unsigned ydiv = SLAB ? __umulhi(blockIdx.y, ymagic) : 0u;
+  const int by = SLAB ? blockIdx.z * yslab + (int)(blockIdx.y - ydiv * yslab) : blockIdx.y;
+  const int bz = SLAB ? (int)ydiv : blockIdx.z;
+  const int i0 = g.gw + blockIdx.x * Cfg::TX, j0 = g.gw + by * Cfg::TY, k0 = g.gw + bz * Cfg::TZ;
+  if (SLAB && j0 >= g.gw + g.ny + (D == 1 ? 1 : 0)) return;  // the last slab may be short
   if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
   if (tid == 0) {
@@ -1272,7 +1291,7 @@ __global__ void __launch_bounds__(FluxCfg<D>::THREADS, FluxCfg<D>::MINB)
   const double b1r = sm[5 * S + oR] - sm[12 * S + oR];
   const double b2r = sm[6 * S + oR] - sm[13 * S + oR];
   double fd, fp, fu, fv, fw;
-  riemann_face(g, rl, pl, unl, t1l, t2l, bnl, b1l, b2l, rr, pr, unr, t1r, t2r, bnr, b1r, b2r, fd, fp, fu, fv, fw);
+  riemann_face<RS>(g, rl, pl, unl, t1l, t2l, bnl, b1l, b2l, rr, pr, unr, t1r, t2r, bnr, b1r, b2r, fd, fp, fu, fv, fw);
   const long long N = g.ncell;
   double *Fo = F + cidx(g, i, j, k);
   Fo[0 * N] = fd; Fo[1 * N] = fp; Fo[2 * N] = fu; Fo[3 * N] = fv; Fo[4 * N] = fw;
@@ -1284,12 +1303,13 @@ __global__ void __launch_bounds__(FluxCfg<D>::THREADS, FluxCfg<D>::MINB)
 __global__ void __launch_bounds__(256) k_update(const GridParams g, const StepState *__restrict__ stp,
                                                 const double *__restrict__ Uin, double *__restrict__ Uout,
                                                 const double *__restrict__ Fx, const double *__restrict__ Fy,
-                                                const double *__restrict__ Fz, const double *__restrict__ EMF, const int kb0) {
+                                                const double *__restrict__ Fz, const double *__restrict__ EMF, const int kb0,
+                                                const int jslab) {
   const int k = kb0 + blockIdx.y;
   const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned jj = t / (unsigned)g.isize;
-  const int i = (int)(t - jj * (unsigned)g.isize), j = (int)jj;
-  if (j >= g.jsize) return;
+  const int i = (int)(t - jj * (unsigned)g.isize), j = (int)(blockIdx.z * jslab + jj);  // y-slabs: see slab_rows()
+  if (jj >= (unsigned)jslab || j >= g.jsize) return;
   const long long N = g.ncell, sj = g.isize, sk = (long long)g.isize * g.jsize;
   const long long c = cidx(g, i, j, k);
   double u[NBVAR];
@@ -1796,23 +1816,36 @@ static void l_prim_dt(const GridParams &g, const double *U, double *Q, StepState
   dim3 grid(cdiv((long long)g.isize * g.jsize, bs), k1 - k0);
   k_prim_dt<<<grid, bs, 0, s>>>(g, U, Q, st, k0);
 }
+// The plane-sweeping kernels (grid x = cells of a k-plane, y = k) reuse the planes k-1, k, k+1 of their inputs from L2 --
+// as long as one k-plane of ALL their streams fits there. At 512^3 a plane of the trace kernel's 46 streams is 99 MB and
+// every z-neighbour is fetched from HBM again, so the sweep is cut into y-slabs of `rows` rows (grid z; CTAs are
+// dispatched x-fastest, then k, then slab) that keep ~24 MB per plane. At 256^3 one slab covers the plane.
+static int slab_rows(const GridParams &g, int nstreams, int nrows) {
+  static const int forced = getenv("PPK_SLAB_ROWS") ? atoi(getenv("PPK_SLAB_ROWS")) : 0;
+  long long rows = forced > 0 ? forced : (24LL << 20) / ((long long)nstreams * g.isize * 8);
+  if (rows >= nrows) return nrows;
+  rows &= ~7LL;
+  return rows < 8 ? 8 : (int)rows;
+}
 static void l_finalize_dt(const GridParams &g, StepState *st, cudaStream_t s) { k_finalize_dt<<<1, 1, 0, s>>>(g, st); }
 static void l_advance_time(StepState *st, cudaStream_t s) { k_advance_time<<<1, 1, 0, s>>>(st); }
 static void l_elec_dbf(const GridParams &g, const double *U, const double *Q, double *E, double *DBF, cudaStream_t s) {
   const int bs = 256;
-  dim3 grid(cdiv((long long)(g.isize - 2) * (g.jsize - 2), bs), g.ksize - 2);
-  k_elec_dbf<<<grid, bs, 0, s>>>(g, U, Q, E, DBF);
+  const int rows = slab_rows(g, 15, g.jsize - 2);
+  dim3 grid(cdiv((long long)(g.isize - 2) * rows, bs), g.ksize - 2, cdiv(g.jsize - 2, rows));
+  k_elec_dbf<<<grid, bs, 0, s>>>(g, U, Q, E, DBF, rows);
 }
 static void l_trace(const GridParams &g, const StepState *st, const double *U, const double *Q, const double *E,
                     double *BASIS, cudaStream_t s) {
   const int bs = 128;
-  dim3 grid(cdiv((long long)(g.isize - 4) * (g.jsize - 4), bs), g.ksize - 4);
+  const int rows = slab_rows(g, 46, g.jsize - 4);
+  dim3 grid(cdiv((long long)(g.isize - 4) * rows, bs), g.ksize - 4, cdiv(g.jsize - 4, rows));
   static const int minb = getenv("PPK_TRACE_MINB") ? atoi(getenv("PPK_TRACE_MINB")) : 4;
-  if (minb == 5) k_trace<5><<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS);
-  else if (minb == 6) k_trace<6><<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS);
-  else if (minb == 8) k_trace<8><<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS);
-  else if (minb == 3) k_trace<3><<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS);
-  else k_trace<4><<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS);
+  if (minb == 5) k_trace<5><<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS, rows);
+  else if (minb == 6) k_trace<6><<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS, rows);
+  else if (minb == 8) k_trace<8><<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS, rows);
+  else if (minb == 3) k_trace<3><<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS, rows);
+  else k_trace<4><<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS, rows);
 }
 // ---- TMA tensor maps (host) ---------------------------------------------------------------------
 struct TmaCtx {
@@ -1847,12 +1880,24 @@ static void *l_tma_create(const GridParams &g, const double *BASIS, const double
             encode_cfg<EmfCfg<1>>(enc, &c->emfD[1], g, DBF, NDBF) && encode_cfg<EmfCfg<2>>(enc, &c->emfD[2], g, DBF, NDBF) &&
             encode_cfg<FluxCfg<0>>(enc, &c->fluxB[0], g, BASIS, NBASIS) && encode_cfg<FluxCfg<1>>(enc, &c->fluxB[1], g, BASIS, NBASIS) &&
             encode_cfg<FluxCfg<2>>(enc, &c->fluxB[2], g, BASIS, NBASIS);
-  ok = ok && cudaFuncSetAttribute(k_emf_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, EmfCfg<0>::SMEM_BYTES) == cudaSuccess &&
-       cudaFuncSetAttribute(k_emf_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, EmfCfg<1>::SMEM_BYTES) == cudaSuccess &&
-       cudaFuncSetAttribute(k_emf_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, EmfCfg<2>::SMEM_BYTES) == cudaSuccess &&
-       cudaFuncSetAttribute(k_flux_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<0>::SMEM_BYTES) == cudaSuccess &&
-       cudaFuncSetAttribute(k_flux_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<1>::SMEM_BYTES) == cudaSuccess &&
-       cudaFuncSetAttribute(k_flux_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<2>::SMEM_BYTES) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_emf_tma<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EmfCfg<0>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_emf_tma<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EmfCfg<1>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_emf_tma<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EmfCfg<2>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_flux_tma<0, false, RIEMANN_HLLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<0>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_flux_tma<0, false, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<0>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_flux_tma<1, false, RIEMANN_HLLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<1>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_flux_tma<1, false, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<1>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_flux_tma<2, false, RIEMANN_HLLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<2>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_flux_tma<2, false, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<2>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_emf_tma<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EmfCfg<0>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_emf_tma<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EmfCfg<1>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_emf_tma<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EmfCfg<2>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_flux_tma<0, true, RIEMANN_HLLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<0>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_flux_tma<0, true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<0>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_flux_tma<1, true, RIEMANN_HLLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<1>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_flux_tma<1, true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<1>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_flux_tma<2, true, RIEMANN_HLLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<2>::SMEM_BYTES) == cudaSuccess &&
+       cudaFuncSetAttribute(k_flux_tma<2, true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<2>::SMEM_BYTES) == cudaSuccess;
   if (!ok) { delete c; return nullptr; }
   return c;
 }
@@ -1870,8 +1915,21 @@ static void launch_flux(const GridParams &g, const double *BASIS, double *F, con
     int ntx = ni / Cfg::TX;
     if (ni % Cfg::TX != 0 && ni % Cfg::TX < 8 && ntx > 1) --ntx;
     done = ntx * Cfg::TX;
-    dim3 grid(ntx, cdiv(nj, Cfg::TY), cdiv(nk, Cfg::TZ));
-    k_flux_tma<D><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(g, tma->fluxB[D], F);
+    const int nty = cdiv(nj, Cfg::TY), ntz = cdiv(nk, Cfg::TZ);
+    // y-slabs only pay where a tile has a z halo (the plane below is re-read by the next z-tile)
+    int yslab = Cfg::HZ > 0 ? slab_rows(g, 20 * Cfg::ZB, nj) / Cfg::TY : nty;
+    if (yslab < 1) yslab = 1;
+    if (yslab * Cfg::TY >= nj - Cfg::TY) yslab = nty;  // no sliver slabs
+    if ((long long)yslab * ntz > 65535) yslab = 65535 / ntz > 0 ? 65535 / ntz : 1;  // grid.y limit
+    dim3 grid(ntx, yslab * ntz, cdiv(nty, yslab));
+    const unsigned ymagic = 0xFFFFFFFFu / (unsigned)yslab + 1u;
+    if (g.riemann == RIEMANN_HLLD) {
+      if (yslab == nty) k_flux_tma<D, false, RIEMANN_HLLD><<<dim3(ntx, nty, ntz), Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(g, tma->fluxB[D], F, 0, 0u);
+      else k_flux_tma<D, true, RIEMANN_HLLD><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(g, tma->fluxB[D], F, yslab, ymagic);
+    } else {
+      if (yslab == nty) k_flux_tma<D, false, -1><<<dim3(ntx, nty, ntz), Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(g, tma->fluxB[D], F, 0, 0u);
+      else k_flux_tma<D, true, -1><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(g, tma->fluxB[D], F, yslab, ymagic);
+    }
   }
   if (done < ni) {
     const int bs = 128;
@@ -1896,8 +1954,15 @@ static void launch_emf(const GridParams &g, const double *BASIS, const double *D
     int ntx = ni / Cfg::TX;
     if (ni % Cfg::TX != 0 && ni % Cfg::TX < 8 && ntx > 1) --ntx;
     done = ntx * Cfg::TX;
-    dim3 grid(ntx, cdiv(nj, Cfg::TY), cdiv(nk, Cfg::TZ));
-    k_emf_tma<E><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(g, tma->emfB[E], tma->emfD[E], EMF);
+    const int nty = cdiv(nj, Cfg::TY), ntz = cdiv(nk, Cfg::TZ);
+    // y-slabs only pay where a tile has a z halo (the plane below is re-read by the next z-tile)
+    int yslab = Cfg::HZ > 0 ? slab_rows(g, 20 * Cfg::ZB, nj) / Cfg::TY : nty;
+    if (yslab < 1) yslab = 1;
+    if (yslab * Cfg::TY >= nj - Cfg::TY) yslab = nty;  // no sliver slabs
+    if ((long long)yslab * ntz > 65535) yslab = 65535 / ntz > 0 ? 65535 / ntz : 1;  // grid.y limit
+    dim3 grid(ntx, yslab * ntz, cdiv(nty, yslab));
+    if (yslab == nty) k_emf_tma<E, false><<<dim3(ntx, nty, ntz), Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(g, tma->emfB[E], tma->emfD[E], EMF, 0, 0u);
+    else k_emf_tma<E, true><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(g, tma->emfB[E], tma->emfD[E], EMF, yslab, 0xFFFFFFFFu / (unsigned)yslab + 1u);
   }
   if (done < ni) {
     const int bs = 128;
@@ -1916,8 +1981,9 @@ static void l_update(const GridParams &g, const StepState *st, const double *Uin
                      const double *Fy, const double *Fz, const double *EMF, int k0, int k1, cudaStream_t s) {
   if (k1 <= k0) return;
   const int bs = 256;
-  dim3 grid(cdiv((long long)g.isize * g.jsize, bs), k1 - k0);
-  k_update<<<grid, bs, 0, s>>>(g, st, Uin, Uout, Fx, Fy, Fz, EMF, k0);
+  const int rows = slab_rows(g, 34, g.jsize);
+  dim3 grid(cdiv((long long)g.isize * rows, bs), k1 - k0, cdiv(g.jsize, rows));
+  k_update<<<grid, bs, 0, s>>>(g, st, Uin, Uout, Fx, Fy, Fz, EMF, k0, rows);
 }
 static void l_consume(const GridParams &g, const StepState *st, const double *BASIS, const double *DBF, const double *Uin,
                       double *Uout, int split, cudaStream_t s) {
