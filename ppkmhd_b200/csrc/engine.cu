@@ -374,6 +374,8 @@ int ppk_mhd3d_create(const ppk_mhd3d_params *p, ppk_mhd3d **out) {
   g.gamma0 = p->gamma0; g.cfl = p->cfl; g.slope_type = p->slope_type;
   g.smallr = p->smallr; g.smallc = p->smallc; g.smallp = p->smallp;
   g.riemann = p->riemann_solver;
+  g.wrap_x = (p->boundary_type[0] == PPK_BC_PERIODIC && p->boundary_type[1] == PPK_BC_PERIODIC) ? 1 : 0;
+  if (const char *e = getenv("PPK_WRAP_X")) g.wrap_x = g.wrap_x && atoi(e) != 0;
   for (int f = 0; f < 6; ++f) g.bc[f] = p->boundary_type[f];
   // z faces of a decomposed run: inner faces, and outer faces of a periodic domain, belong to the halo
   // exchange (HydroParams.cpp:300-351: neighborsBC = BC_COPY unless on the outer boundary).
@@ -680,6 +682,10 @@ int ppk_mhd3d_debug_array(ppk_mhd3d *h, const char *name, double *host_out, int 
   else if (s == "Emf") { src = h->EMF; nc = NEMF; }
   else return fail(PPK_ERR_INVALID_ARGUMENT, "unknown array name " + s);
   if (!src) return fail(PPK_ERR_STATE, s + " exists only in the unfused pipeline (ppk_mhd3d_set_pipeline)");
+  // x periodic: the launchers skip the column i = nx+gw of the x-fluxes and of the z- / y-EMFs (the update reads the
+  // bit-identical column i = gw); complete the arrays for the caller
+  if (s == "Fluxes_x") h->kt->wrap_x_column(h->g, h->F[0], NFLUX, h->stream);
+  if (s == "Emf") h->kt->wrap_x_column(h->g, h->EMF, 2, h->stream);
   if (ncomp) *ncomp = nc;
   if (host_out) {
     CUDA_TRY(cudaMemcpyAsync(host_out, src, (size_t)nc * h->g.ncell * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

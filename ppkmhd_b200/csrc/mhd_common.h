@@ -34,6 +34,7 @@ struct GridParams {
   double dx, dy, dz;
   double idx, idy, idz;  // 1/dx, 1/dy, 1/dz (fast-arithmetic build only)
   double gamma0, cfl, slope_type, smallr, smallc, smallp;
+  int wrap_x;   // x periodic on both faces: values at i = nx+gw equal those at i = gw (see launch_flux / k_update)
   int riemann;  // face Riemann solver (the edge EMFs always use the 2-D HLLD solver, like the reference)
   int bc[6];  // effective BC of this slab's faces (BC_COPY on faces owned by the halo exchange)
 };
@@ -81,6 +82,8 @@ struct KernelTable {
   // streamed pipeline: z-marching HLLD fluxes + hydro update (no flux array), then the CT update alone
   void (*hydro)(const GridParams &g, const StepState *st, const double *BASIS, const double *Uin, double *Uout, cudaStream_t s);
   void (*update_ct)(const GridParams &g, const StepState *st, const double *Uin, double *Uout, const double *EMF, cudaStream_t s);
+  // A[comp][.., i = nx+gw] <- A[comp][.., i = gw] when x is periodic (debug arrays only)
+  void (*wrap_x_column)(const GridParams &g, double *A, int ncomp, cudaStream_t s);
 };
 
 const KernelTable *kernel_table_exact();

@@ -1318,11 +1318,24 @@ __global__ void __launch_bounds__(256) k_update(const GridParams g, const StepSt
   const int gw = g.gw;
   if (i >= gw && i < g.isize - gw && j >= gw && j < g.jsize - gw && k >= gw && k < g.ksize - gw) {
     const double dtdx = stp->dtdx, dtdy = stp->dtdy, dtdz = stp->dtdz;
+    // +x neighbour of the x-faces and of the y- / z-edges. With x periodic the values at i = nx+gw are bit-identical to
+    // those at i = gw and the flux / EMF launchers skip that column (see launch_flux): the one thread per row that
+    // needs it re-reads the wrapped column (a branch, so that every other thread keeps its immediate-offset loads).
+    const double *Ez = EMF, *Ey = EMF + N, *Ex = EMF + 2 * N;
+    double fxh[NFLUX], ezx = Ez[c + 1], eyx = Ey[c + 1];
+#pragma unroll
+    for (int v = 0; v < NFLUX; ++v) fxh[v] = Fx[c + 1 + v * N];
+    if (g.wrap_x && i + 1 == gw + g.nx) {
+      const long long cw = c + 1 - g.nx;
+#pragma unroll
+      for (int v = 0; v < NFLUX; ++v) fxh[v] = Fx[cw + v * N];
+      ezx = Ez[cw]; eyx = Ey[cw];
+    }
     // x faces: (rho,E,mx,my,mz) <- (0,1,2,3,4)
     u[ID] += Fx[c + 0 * N] * dtdx; u[IP] += Fx[c + 1 * N] * dtdx; u[IU] += Fx[c + 2 * N] * dtdx;
     u[IV] += Fx[c + 3 * N] * dtdx; u[IW] += Fx[c + 4 * N] * dtdx;
-    u[ID] -= Fx[c + 1 + 0 * N] * dtdx; u[IP] -= Fx[c + 1 + 1 * N] * dtdx; u[IU] -= Fx[c + 1 + 2 * N] * dtdx;
-    u[IV] -= Fx[c + 1 + 3 * N] * dtdx; u[IW] -= Fx[c + 1 + 4 * N] * dtdx;
+    u[ID] -= fxh[0] * dtdx; u[IP] -= fxh[1] * dtdx; u[IU] -= fxh[2] * dtdx;
+    u[IV] -= fxh[3] * dtdx; u[IW] -= fxh[4] * dtdx;
     // y faces, stored in the rotated frame: normal=my (2), t1=mx (3), t2=mz (4)
     u[ID] += Fy[c + 0 * N] * dtdy; u[IP] += Fy[c + 1 * N] * dtdy; u[IU] += Fy[c + 3 * N] * dtdy;
     u[IV] += Fy[c + 2 * N] * dtdy; u[IW] += Fy[c + 4 * N] * dtdy;
@@ -1334,13 +1347,12 @@ __global__ void __launch_bounds__(256) k_update(const GridParams g, const StepSt
     u[ID] -= Fz[c + sk + 0 * N] * dtdz; u[IP] -= Fz[c + sk + 1 * N] * dtdz; u[IU] -= Fz[c + sk + 4 * N] * dtdz;
     u[IV] -= Fz[c + sk + 3 * N] * dtdz; u[IW] -= Fz[c + sk + 2 * N] * dtdz;
     // constrained transport, exact expression order of MHDRunFunctors3D.h:2602-2616
-    const double *Ez = EMF, *Ey = EMF + N, *Ex = EMF + 2 * N;
     const double ez = Ez[c], ey = Ey[c], ex = Ex[c];
     u[IA] += (Ez[c + sj] - ez) * dtdy;
-    u[IB] -= (Ez[c + 1] - ez) * dtdx;
+    u[IB] -= (ezx - ez) * dtdx;
     u[IA] -= (Ey[c + sk] - ey) * dtdz;
     u[IB] += (Ex[c + sk] - ex) * dtdz;
-    u[IC] += (Ey[c + 1] - ey) * dtdx;
+    u[IC] += (eyx - ey) * dtdx;
     u[IC] -= (Ex[c + sj] - ex) * dtdy;
   }
 #pragma unroll
@@ -1735,12 +1747,25 @@ __global__ void __launch_bounds__(256) k_update_ct(const GridParams g, const Ste
   const double *Ez = EMF, *Ey = EMF + N, *Ex = EMF + 2 * N;
   const double ez = Ez[c], ey = Ey[c], ex = Ex[c];
   a += (Ez[c + sj] - ez) * dtdy;
-  b -= (Ez[c + 1] - ez) * dtdx;
+  const long long cx = (g.wrap_x && i + 1 == gw + g.nx) ? c + 1 - g.nx : c + 1;  // see k_update
+  b -= (Ez[cx] - ez) * dtdx;
   a -= (Ey[c + sk] - ey) * dtdz;
   b += (Ex[c + sk] - ex) * dtdz;
-  cc += (Ey[c + 1] - ey) * dtdx;
+  cc += (Ey[cx] - ey) * dtdx;
   cc -= (Ex[c + sj] - ex) * dtdy;
   Uout[c + IA * N] = a; Uout[c + IB * N] = b; Uout[c + IC * N] = cc;
+}
+
+// Column i = nx+gw of a flux / EMF component <- column i = gw (x periodic): only ppk_mhd3d_debug_array needs it, the
+// update reads the wrapped column directly.
+__global__ void k_wrap_x_column(const GridParams g, double *__restrict__ A, const int ncomp) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long rows = (long long)g.jsize * g.ksize;
+  if (t >= rows * ncomp) return;
+  const int comp = (int)(t / rows);
+  const long long r = t - comp * rows;
+  const long long c = (long long)g.isize * r + comp * g.ncell;
+  A[c + g.gw + g.nx] = A[c + g.gw];
 }
 
 // Diagnostics: per-variable sums over the interior and max |div B| (needs filled upper ghosts).
@@ -1913,8 +1938,15 @@ static void launch_flux(const GridParams &g, const double *BASIS, double *F, con
     // a remainder of a few columns would make the plain kernel fetch 32-byte sectors for 8 or 16 useful bytes:
     // hand it a whole extra tile instead so that its rows stay coalesced
     int ntx = ni / Cfg::TX;
-    if (ni % Cfg::TX != 0 && ni % Cfg::TX < 8 && ntx > 1) --ntx;
-    done = ntx * Cfg::TX;
+    if (ni - ntx * Cfg::TX == 1 && g.wrap_x && D == 0) {
+      // nx a multiple of 32 and x periodic on both sides: the faces at i = nx+gw are bit-identical to those at i = gw
+      // (ghost cells are copies, hence so are their basis numbers) and the update reads them there (k_update):
+      // no launch for that column, whose strided 32-byte sectors cost 0.1 ms per kernel
+      done = ni;
+    } else {
+      if (ni % Cfg::TX != 0 && ni % Cfg::TX < 8 && ntx > 1) --ntx;
+      done = ntx * Cfg::TX;
+    }
     const int nty = cdiv(nj, Cfg::TY), ntz = cdiv(nk, Cfg::TZ);
     // y-slabs only pay where a tile has a z halo (the plane below is re-read by the next z-tile)
     int yslab = Cfg::HZ > 0 ? slab_rows(g, 20 * Cfg::ZB, nj) / Cfg::TY : nty;
@@ -1952,8 +1984,15 @@ static void launch_emf(const GridParams &g, const double *BASIS, const double *D
   if (tma) {
     using Cfg = EmfCfg<E>;
     int ntx = ni / Cfg::TX;
-    if (ni % Cfg::TX != 0 && ni % Cfg::TX < 8 && ntx > 1) --ntx;
-    done = ntx * Cfg::TX;
+    if (ni - ntx * Cfg::TX == 1 && g.wrap_x && E != 0) {
+      // nx a multiple of 32 and x periodic on both sides: the edges at i = nx+gw are bit-identical to those at i = gw
+      // (ghost cells are copies, hence so are their basis numbers) and the update reads them there (k_update):
+      // no launch for that column, whose strided 32-byte sectors cost 0.1 ms per kernel
+      done = ni;
+    } else {
+      if (ni % Cfg::TX != 0 && ni % Cfg::TX < 8 && ntx > 1) --ntx;
+      done = ntx * Cfg::TX;
+    }
     const int nty = cdiv(nj, Cfg::TY), ntz = cdiv(nk, Cfg::TZ);
     // y-slabs only pay where a tile has a z halo (the plane below is re-read by the next z-tile)
     int yslab = Cfg::HZ > 0 ? slab_rows(g, 20 * Cfg::ZB, nj) / Cfg::TY : nty;
@@ -2030,6 +2069,11 @@ static void l_update_ct(const GridParams &g, const StepState *st, const double *
   dim3 grid(cdiv((long long)g.nx * g.ny, bs), g.nz);
   k_update_ct<<<grid, bs, 0, s>>>(g, st, Uin, Uout, EMF);
 }
+static void l_wrap_x_column(const GridParams &g, double *A, int ncomp, cudaStream_t s) {
+  if (!g.wrap_x) return;
+  const long long total = (long long)g.jsize * g.ksize * ncomp;
+  k_wrap_x_column<<<cdiv(total, 256), 256, 0, s>>>(g, A, ncomp);
+}
 static void l_diagnostics(const GridParams &g, const double *U, double *out9, cudaStream_t s) {
   const int bs = 256;
   dim3 grid(cdiv((long long)g.nx * g.ny, bs), g.nz);
@@ -2046,7 +2090,7 @@ static const KernelTable table = {
 #else
   "fast",
 #endif
-  l_boundary, l_prim_dt, l_finalize_dt, l_advance_time, l_elec_dbf, l_trace, l_flux, l_emf, l_update, l_diagnostics, l_fastmath_selftest, l_consume, l_tma_create, l_tma_destroy, l_hydro, l_update_ct,
+  l_boundary, l_prim_dt, l_finalize_dt, l_advance_time, l_elec_dbf, l_trace, l_flux, l_emf, l_update, l_diagnostics, l_fastmath_selftest, l_consume, l_tma_create, l_tma_destroy, l_hydro, l_update_ct, l_wrap_x_column,
 };
 
 }  // namespace PPK_NS

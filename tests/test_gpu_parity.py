@@ -73,6 +73,7 @@ def test_fast_mode_within_1e12_of_reference(case, pipeline):
 
 @pytest.mark.parametrize("problem,n,extra,bounds,cfl", [
     ("orszag_tang", (48, 40, 36), OT, None, 0.8),
+    ("orszag_tang", (64, 36, 40), OT, None, 0.8),  # nx a multiple of 32 + periodic x: the wrapped face / edge column
     ("blast", (40, 40, 40), BLAST, None, 0.8),
     ("field_loop", (64, 32, 32), "[FieldLoop]\nradius=0.3\namplitude=0.001\nvflow=3\ndensity_in=1\n", (-1, 1, -0.5, 0.5, -0.5, 0.5), 0.4),
 ])
