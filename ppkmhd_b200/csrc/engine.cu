@@ -351,8 +351,11 @@ int ppk_mhd3d_create(const ppk_mhd3d_params *p, ppk_mhd3d **out) {
   if (p->ghost_width != PPK_GHOST_WIDTH) return fail(PPK_ERR_UNSUPPORTED, "ghost_width must be 3 (MHD_Muscl_3D)");
   if (p->riemann_solver != PPK_RIEMANN_HLLD && p->riemann_solver != PPK_RIEMANN_HLL && p->riemann_solver != PPK_RIEMANN_LLF)
     return fail(PPK_ERR_UNSUPPORTED, "riemann must be hlld, hll or llf (the reference's 'approx' and 'hllc' are silent no-op fluxes for MHD, RiemannSolvers_MHD.h:372-392)");
-  if (p->implementation_version != 0)
-    return fail(PPK_ERR_UNSUPPORTED, "only implementationVersion=0 (the deterministic reference variant) is implemented");
+  // v1 of the reference is v0's arithmetic with the update scattered through atomic_add (SolverMHDMuscl.cpp:518-534):
+  // its result differs from v0 only by the (run-to-run varying) order of those additions, ~1e-15. Both versions map to
+  // the same deterministic kernels here. v2 is a different formulation (and faulty in 3-D).
+  if (p->implementation_version != 0 && p->implementation_version != 1)
+    return fail(PPK_ERR_UNSUPPORTED, "implementationVersion must be 0 or 1 (v1 runs v0's deterministic kernels; v2 is not implemented)");
   if (p->mx != 1 || p->my != 1 || p->mz < 1) return fail(PPK_ERR_UNSUPPORTED, "only z-slab decompositions (mx=my=1) are supported");
   if (p->rank_z < 0 || p->rank_z >= p->mz) return fail(PPK_ERR_INVALID_ARGUMENT, "rank_z out of range");
   if (p->nx < 3 || p->ny < 3 || p->nz < 3) return fail(PPK_ERR_INVALID_ARGUMENT, "nx, ny, nz must be >= 3 (ghost width)");

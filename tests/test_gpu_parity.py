@@ -242,6 +242,11 @@ def test_error_paths():
     p, _, _ = ppk.params_from_ini(ini.replace("implementationVersion=0", "implementationVersion=2"))
     with pytest.raises(ppk.PpkError, match="implementationVersion"):
         ppk.Mhd3d(p)
+    # v1 (the reference's atomic-scatter variant of the same arithmetic) is accepted and runs v0's kernels
+    s, nstep = make_solver(ini.replace("implementationVersion=0", "implementationVersion=1"), exact=True)
+    s.run(nstep)
+    assert np.array_equal(s.interior(), g["stepN"])
+    s.close()
 
 
 def test_fast_math_primitives_within_2ulp():
