@@ -1131,17 +1131,37 @@ struct TileCfg {
   static constexpr int SMEM_BYTES = NSLOT * SLOT * 8;
   static constexpr int THREADS = TX * TY * TZ;
 };
-// Measured on B200 at 256^3 (profiles/r1_tuning_notes.md): the staged EMF kernels gain from more resident CTAs
-// (z-edges: 128-thread CTAs x5 at 96 registers 0.73 ms vs 0.92 ms for 256 x2; y-edges 256 x3 at 80 registers
-// 0.78 vs 0.91 ms); the x-edge tile (z halo + the alignment column) only fits twice in shared memory.
+// Measured on B200 at 256^3: the staged EMF kernels gain from more, smaller resident CTAs (z-edges: 128-thread CTAs x5
+// at 96 registers 0.73 ms vs 0.92 ms for 256 x2). The tiles with a z halo take ONE plane of edges per CTA (box of 2 planes):
+// 32x4x2 tiles needed 62-78 KB and fitted 2-3 times per SM; 32x4x1 fits 4-5 times although it re-reads the lower plane
+// (x-edges 1.00 -> 0.80 ms, y-edges 0.77 -> 0.69 ms, A/B on one box).
 template <int E> struct EmfCfg;  // edge direction E: halo of one cell along d1 and d2
 template <> struct EmfCfg<2> : TileCfg<4, 1, 1, 1, 0, 19, 5> {};
-template <> struct EmfCfg<0> : TileCfg<4, 2, 1, 1, 1, 19, 3> {};
-template <> struct EmfCfg<1> : TileCfg<4, 2, 1, 0, 1, 19, 3> {};
+#ifndef PPK_EMFX_TY  // tile-shape experiments: -DPPK_EMFX_TY=.. -DPPK_EMFX_TZ=.. -DPPK_EMFX_MINB=.. (same for EMFY)
+#  define PPK_EMFX_TY 4
+#  define PPK_EMFX_TZ 1
+#  define PPK_EMFX_MINB 4
+#endif
+#ifndef PPK_EMFY_TY
+#  define PPK_EMFY_TY 4
+#  define PPK_EMFY_TZ 1
+#  define PPK_EMFY_MINB 5
+#endif
+template <> struct EmfCfg<0> : TileCfg<PPK_EMFX_TY, PPK_EMFX_TZ, 1, 1, 1, 19, PPK_EMFX_MINB> {};
+template <> struct EmfCfg<1> : TileCfg<PPK_EMFY_TY, PPK_EMFY_TZ, 1, 0, 1, 19, PPK_EMFY_MINB> {};
 template <int D> struct FluxCfg;  // face direction D: halo of one cell along D
-template <> struct FluxCfg<0> : TileCfg<8, 1, 1, 0, 0, 15, 3> {};
-template <> struct FluxCfg<1> : TileCfg<8, 1, 1, 1, 0, 15, 3> {};
-template <> struct FluxCfg<2> : TileCfg<4, 2, 1, 0, 1, 15, 3> {};
+#ifndef PPK_FLUXXY_TY
+#  define PPK_FLUXXY_TY 4  // 32x4 tiles, 5 CTAs/SM (<= 102 registers, no spills): 0.61 -> 0.55 ms against 32x8 tiles x3 (80 registers)
+#  define PPK_FLUXXY_MINB 5
+#endif
+template <> struct FluxCfg<0> : TileCfg<PPK_FLUXXY_TY, 1, 1, 0, 0, 15, PPK_FLUXXY_MINB> {};
+template <> struct FluxCfg<1> : TileCfg<PPK_FLUXXY_TY, 1, 1, 1, 0, 15, PPK_FLUXXY_MINB> {};
+#ifndef PPK_FLUXZ_TY
+#  define PPK_FLUXZ_TY 4
+#  define PPK_FLUXZ_TZ 1
+#  define PPK_FLUXZ_MINB 5
+#endif
+template <> struct FluxCfg<2> : TileCfg<PPK_FLUXZ_TY, PPK_FLUXZ_TZ, 1, 0, 1, 15, PPK_FLUXZ_MINB> {};
 
 // component (row of the 4-D tensor) staged in slot s of the EMF kernel: 0-4 q, 5-9 slopes along d1, 10-14 slopes
 // along d2, 15/16 lower-face field normal to d1/d2; slots 17,18 come from DBF
