@@ -836,6 +836,9 @@ __global__ void __launch_bounds__(256) k_elec_dbf(const GridParams g, const doub
 // ComputeTraceFunctor3D_MHD (MHDRunFunctors3D.h:543-856): hydro slopes (slope_unsplit_hydro_3d,
 // MHDBaseFunctor3D.h:362-495) + Hancock half step (trace_unsplit_mhd_3d_simpler, :688-896).
 // Writes the 32-number basis on [2,size-2)^3 (the cells whose states a face or an edge consumes).
+// (Measured alternative: accumulating the source terms direction by direction -- same summation order, 80-96 registers,
+// 5-6 CTAs/SM, no spills -- is SLOWER, 1.59-1.76 ms against 1.42 ms: three dependent load phases with the slope stores
+// between them lose more than the occupancy gains. One load burst at 128 registers stays.)
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_trace(const GridParams g, const StepState *__restrict__ stp,
                                                      const double *__restrict__ U, const double *__restrict__ Q,
