@@ -130,6 +130,99 @@ void orc_init_blast(const orc_params *p, double radius, double cx, double cy, do
       }
 }
 
+void orc_init_implode(const orc_params *p, const double outer[8], const double inner[8], int shape, double *U)
+{
+  /* src/muscl/MHDInitFunctors3D.h:52-143 ; outer/inner = rho, p, u, v, w, Bx, By, Bz (ImplodeParams.h:36-56).
+   * The momentum slots receive the VELOCITIES, as in the reference. */
+  const int gw = p->gw;
+  for (int k = 0; k < p->ksize; ++k)
+    for (int j = 0; j < p->jsize; ++j)
+      for (int i = 0; i < p->isize; ++i) {
+        double x = p->xmin + p->dx / 2 + (i + p->nx * p->px - gw) * p->dx;
+        double y = p->ymin + p->dy / 2 + (j + p->ny * p->py - gw) * p->dy;
+        double z = p->zmin + p->dz / 2 + (k + p->nz * p->pz - gw) * p->dz;
+        int tmp;
+        if (shape == 1) tmp = x + y + z > 0.5 && x + y + z < 2.5;
+        else tmp = x + y + z > (p->xmin + p->xmax) / 2. + p->ymin + p->zmin;
+        const double *s = tmp ? outer : inner;
+        U[AT(p, i, j, k, ID)] = s[0];
+        U[AT(p, i, j, k, IP)] = s[1] / (p->gamma0 - 1.0) + 0.5 * s[0] * (s[2] * s[2] + s[3] * s[3] + s[4] * s[4]) +
+                                0.5 * (s[5] * s[5] + s[6] * s[6] + s[7] * s[7]);
+        U[AT(p, i, j, k, IU)] = s[2];
+        U[AT(p, i, j, k, IV)] = s[3];
+        U[AT(p, i, j, k, IW)] = s[4];
+        U[AT(p, i, j, k, IA)] = s[5];
+        U[AT(p, i, j, k, IB)] = s[6];
+        U[AT(p, i, j, k, IC)] = s[7];
+      }
+}
+
+void orc_init_kelvin_helmholtz(const orc_params *p, double d_in, double d_out, double pressure, double vflow_in,
+                               double vflow_out, int mode, double w0, double delta, int sine_robertson, double *U)
+{
+  /* src/muscl/MHDInitFunctors3D.h:532-614 : the two deterministic perturbations (sine "a la Robertson" :532-573,
+   * plain sine :574-612); the random one (:492-530) draws from a per-thread Kokkos pool and is not reproducible. */
+  const int gw = p->gw;
+  const double z1 = 0.25, z2 = 0.75;
+  for (int k = 0; k < p->ksize; ++k)
+    for (int j = 0; j < p->jsize; ++j)
+      for (int i = 0; i < p->isize; ++i) {
+        double x = p->xmin + p->dx / 2 + (i + p->nx * p->px - gw) * p->dx;
+        double y = p->ymin + p->dy / 2 + (j + p->ny * p->py - gw) * p->dy;
+        double z = p->zmin + p->dz / 2 + (k + p->nz * p->pz - gw) * p->dz;
+        double d, u, v, w;
+        if (sine_robertson) {
+          const double rho1 = d_in, rho2 = d_out, v1x = vflow_in, v2x = vflow_out, v1y = vflow_in / 2, v2y = vflow_out / 2;
+          const double ramp = 1.0 / (1.0 + exp(2 * (z - z1) / delta)) + 1.0 / (1.0 + exp(2 * (z2 - z) / delta));
+          d = rho1 + ramp * (rho2 - rho1);
+          u = v1x + ramp * (v2x - v1x);
+          v = v1y + ramp * (v2y - v1y);
+          w = w0 * sin(mode * M_PI * x) * sin(mode * M_PI * y);
+        } else {
+          d = (z >= z1 && z <= z2) ? d_in : d_out;
+          u = (z >= z1 && z <= z2) ? vflow_in : vflow_out;
+          v = 0;
+          w = w0 * sin(mode * M_PI * x);
+        }
+        const double bx = 0.5, by = 0.0, bz = 0.0;
+        U[AT(p, i, j, k, ID)] = d;
+        U[AT(p, i, j, k, IU)] = d * u;
+        U[AT(p, i, j, k, IV)] = d * v;
+        U[AT(p, i, j, k, IW)] = d * w;
+        U[AT(p, i, j, k, IA)] = bx;
+        U[AT(p, i, j, k, IB)] = by;
+        U[AT(p, i, j, k, IC)] = bz;
+        U[AT(p, i, j, k, IP)] = pressure / (p->gamma0 - 1.0) + 0.5 * d * (u * u + v * v + w * w) + 0.5 * (bx * bx + by * by + bz * bz);
+      }
+}
+
+void orc_init_rotor(const orc_params *p, double r0, double r1, double u0, double p0, double b0, double *U)
+{
+  /* src/muscl/MHDInitFunctors3D.h:646-748 (velocities in the momentum slots, as in the reference) */
+  const int gw = p->gw;
+  const double xCenter = (p->xmax + p->xmin) / 2, yCenter = (p->ymax + p->ymin) / 2;
+  for (int k = 0; k < p->ksize; ++k)
+    for (int j = 0; j < p->jsize; ++j)
+      for (int i = 0; i < p->isize; ++i) {
+        double x = p->xmin + p->dx / 2 + (i + p->nx * p->px - gw) * p->dx;
+        double y = p->ymin + p->dy / 2 + (j + p->ny * p->py - gw) * p->dy;
+        double r = sqrt((x - xCenter) * (x - xCenter) + (y - yCenter) * (y - yCenter));
+        double f_r = (r1 - r) / (r1 - r0);
+        double d, mu, mv;
+        if (r <= r0) { d = 10.0; mu = -u0 * (y - yCenter) / r0; mv = u0 * (x - xCenter) / r0; }
+        else if (r <= r1) { d = 1 + 9 * f_r; mu = -f_r * u0 * (y - yCenter) / r; mv = f_r * u0 * (x - xCenter) / r; }
+        else { d = 1.0; mu = 0.0; mv = 0.0; }
+        U[AT(p, i, j, k, ID)] = d;
+        U[AT(p, i, j, k, IU)] = mu;
+        U[AT(p, i, j, k, IV)] = mv;
+        U[AT(p, i, j, k, IW)] = 0.0;
+        U[AT(p, i, j, k, IA)] = b0;
+        U[AT(p, i, j, k, IB)] = 0.0;
+        U[AT(p, i, j, k, IC)] = 0.0;
+        U[AT(p, i, j, k, IP)] = p0 / (p->gamma0 - 1.0) + (mu * mu + mv * mv + 0.0 * 0.0) / 2 / d + (b0 * b0) / 2;
+      }
+}
+
 void orc_init_field_loop(const orc_params *p, double radius, double density_in, double amplitude, double vflow,
                          double *U)
 {

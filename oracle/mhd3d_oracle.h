@@ -66,6 +66,13 @@ void orc_init_blast(const orc_params *p, double radius, double cx, double cy, do
                     double *U);                                                     /* MHDInitFunctors3D.h:155-259 */
 void orc_init_field_loop(const orc_params *p, double radius, double density_in, double amplitude,
                          double vflow, double *U);                                  /* MHDInitFunctors3D.h:759-1023 */
+void orc_init_implode(const orc_params *p, const double outer[8], const double inner[8], int shape,
+                      double *U);                                                   /* MHDInitFunctors3D.h:34-150 */
+void orc_init_kelvin_helmholtz(const orc_params *p, double d_in, double d_out, double pressure, double vflow_in,
+                               double vflow_out, int mode, double w0, double delta, int sine_robertson,
+                               double *U);                                          /* MHDInitFunctors3D.h:420-622 */
+void orc_init_rotor(const orc_params *p, double r0, double r1, double u0, double p0, double b0,
+                    double *U);                                                     /* MHDInitFunctors3D.h:627-757 */
 
 /* ---- the step, one function per reference functor ---- */
 void orc_make_boundary(const orc_params *p, double *U, int face);                   /* BoundariesFunctors.h:749-1053 */

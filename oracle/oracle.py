@@ -62,6 +62,9 @@ def lib():
         _lib.orc_init_orszag_tang.argtypes = [pp, C.c_double, dp]
         _lib.orc_init_blast.argtypes = [pp] + [C.c_double] * 8 + [dp]
         _lib.orc_init_field_loop.argtypes = [pp] + [C.c_double] * 4 + [dp]
+        _lib.orc_init_implode.argtypes = [pp, dp, dp, C.c_int, dp]
+        _lib.orc_init_kelvin_helmholtz.argtypes = [pp] + [C.c_double] * 5 + [C.c_int, C.c_double, C.c_double, C.c_int, dp]
+        _lib.orc_init_rotor.argtypes = [pp] + [C.c_double] * 5 + [dp]
         _lib.orc_make_boundary.argtypes = [pp, dp, C.c_int]
         _lib.orc_make_boundaries.argtypes = [pp, dp]
         _lib.orc_convert_to_primitives.argtypes = [pp, dp, dp]
@@ -128,6 +131,15 @@ class Config:
         except ValueError:
             return default
 
+    def b(self, sec, name, default=False):
+        """ConfigMap::getBool (src/utils/config/ConfigMap.cpp:64-82)"""
+        v = self.s(sec, name, "")
+        if v in ("1", "yes", "true", "on"):
+            return True
+        if v in ("0", "no", "false", "off"):
+            return False
+        return default
+
     def f(self, sec, name, default=0.0):
         v = self.s(sec, name, "")
         return parse_float(v, default) if v else float(np.float32(default))
@@ -191,6 +203,26 @@ def init_problem(p: OrcParams, cfg: Config) -> np.ndarray:
             cfg.f("FieldLoop", "vflow", 1.0),
             _dp(U),
         )
+    elif problem == "implode":
+        # src/shared/problems/ImplodeParams.h:36-58
+        names = ("density", "pressure", "vx", "vy", "vz", "Bx", "By", "Bz")
+        outer = np.array([cfg.f("implode", n + "_outer", d) for n, d in zip(names, (1.0, 1.0, 0, 0, 0, 0, 0, 0))])
+        inner = np.array([cfg.f("implode", n + "_inner", d) for n, d in zip(names, (0.125, 0.14, 0, 0, 0, 0, 0, 0))])
+        L.orc_init_implode(C.byref(p), _dp(outer), _dp(inner), cfg.i("implode", "shape_region", 0), _dp(U))
+    elif problem == "kelvin_helmholtz":
+        # src/shared/problems/KHParams.h:37-88
+        if cfg.b("KH", "perturbation_rand", False):
+            raise ValueError("perturbation_rand is not reproducible in the reference (per-thread Kokkos random pool)")
+        rob, sine = cfg.b("KH", "perturbation_sine_robertson", True), cfg.b("KH", "perturbation_sine", False)
+        if rob or sine:
+            L.orc_init_kelvin_helmholtz(
+                C.byref(p), cfg.f("KH", "d_in", 1.0), cfg.f("KH", "d_out", 1.0), cfg.f("KH", "pressure", 10.0),
+                cfg.f("KH", "vflow_in", -0.5), cfg.f("KH", "vflow_out", 0.5), cfg.i("KH", "mode", 2),
+                cfg.f("KH", "w0", 0.1), cfg.f("KH", "delta", 0.03), 1 if rob else 0, _dp(U))
+    elif problem == "rotor":
+        # src/shared/problems/RotorParams.h:17-24
+        L.orc_init_rotor(C.byref(p), cfg.f("rotor", "r0", 0.1), cfg.f("rotor", "r1", 0.115), cfg.f("rotor", "u0", 2.0),
+                         cfg.f("rotor", "p0", 1.0), cfg.f("rotor", "b0", 5.0 / np.sqrt(4 * np.pi)), _dp(U))
     else:
         L.orc_init_orszag_tang(C.byref(p), cfg.f("OrszagTang", "kt", 0.0), _dp(U))
     return U

@@ -43,6 +43,51 @@ FieldLoopParams::FieldLoopParams(ConfigMap &c) {  // src/shared/problems/FieldLo
   vflow = c.getFloat("FieldLoop", "vflow", 1.0);
 }
 
+ImplodeParams::ImplodeParams(ConfigMap &c) {
+  rho_out = c.getFloat("implode", "density_outer", 1.0);
+  p_out = c.getFloat("implode", "pressure_outer", 1.0);
+  u_out = c.getFloat("implode", "vx_outer", 0.0);
+  v_out = c.getFloat("implode", "vy_outer", 0.0);
+  w_out = c.getFloat("implode", "vz_outer", 0.0);
+  Bx_out = c.getFloat("implode", "Bx_outer", 0.0);
+  By_out = c.getFloat("implode", "By_outer", 0.0);
+  Bz_out = c.getFloat("implode", "Bz_outer", 0.0);
+  rho_in = c.getFloat("implode", "density_inner", 0.125);
+  p_in = c.getFloat("implode", "pressure_inner", 0.14);
+  u_in = c.getFloat("implode", "vx_inner", 0.0);
+  v_in = c.getFloat("implode", "vy_inner", 0.0);
+  w_in = c.getFloat("implode", "vz_inner", 0.0);
+  Bx_in = c.getFloat("implode", "Bx_inner", 0.0);
+  By_in = c.getFloat("implode", "By_inner", 0.0);
+  Bz_in = c.getFloat("implode", "Bz_inner", 0.0);
+  shape = (int)c.getInteger("implode", "shape_region", 0);
+}
+KHParams::KHParams(ConfigMap &c) {
+  d_in = c.getFloat("KH", "d_in", 1.0);
+  d_out = c.getFloat("KH", "d_out", 1.0);
+  pressure = c.getFloat("KH", "pressure", 10.0);
+  p_sine = c.getBool("KH", "perturbation_sine", false);
+  p_sine_rob = c.getBool("KH", "perturbation_sine_robertson", true);
+  p_rand = c.getBool("KH", "perturbation_rand", false);
+  vflow_in = c.getFloat("KH", "vflow_in", -0.5);
+  vflow_out = c.getFloat("KH", "vflow_out", 0.5);
+  if (p_rand) seed = (int)c.getInteger("KH", "rand_seed", 12);
+  amplitude = c.getFloat("KH", "amplitude", 0.1);
+  if (p_sine_rob || p_sine) {
+    inner_size = c.getFloat("KH", "inner_size", 0.2);
+    mode = (int)c.getInteger("KH", "mode", 2);
+    w0 = c.getFloat("KH", "w0", 0.1);
+    delta = c.getFloat("KH", "delta", 0.03);
+  }
+}
+RotorParams::RotorParams(ConfigMap &c) {
+  r0 = c.getFloat("rotor", "r0", 0.1);
+  r1 = c.getFloat("rotor", "r1", 0.115);
+  u0 = c.getFloat("rotor", "u0", 2.0);
+  p0 = c.getFloat("rotor", "p0", 1.0);
+  b0 = c.getFloat("rotor", "b0", 5.0 / sqrt(4 * M_PI));
+}
+
 // ---------------------------------------------------------------------------------------------
 // initial conditions (host, then uploaded)
 // ---------------------------------------------------------------------------------------------
@@ -106,6 +151,113 @@ void init_blast(const HydroParams &p, const BlastParams &b, DataArray3dHost &U) 
       }
 }
 
+// The reference stores VELOCITIES in the momentum slots of the implode and rotor problems (MHDInitFunctors3D.h:121-123,
+// 707-721) and divides by the density only in the rotor's energy: kept as is, this layer reproduces the reference's bits.
+void init_implode(const HydroParams &p, const ImplodeParams &ip, DataArray3dHost &U) {
+  const CellCoords cc{p};
+  const double gamma0 = p.settings.gamma0;
+  for (int k = 0; k < p.ksize; ++k)
+    for (int j = 0; j < p.jsize; ++j)
+      for (int i = 0; i < p.isize; ++i) {
+        const double x = cc.x(i), y = cc.y(j), z = cc.z(k);
+        bool outer;
+        if (ip.shape == 1) outer = x + y + z > 0.5 && x + y + z < 2.5;
+        else outer = x + y + z > (p.xmin + p.xmax) / 2. + p.ymin + p.zmin;
+        const double rho = outer ? ip.rho_out : ip.rho_in, pr = outer ? ip.p_out : ip.p_in;
+        const double u = outer ? ip.u_out : ip.u_in, v = outer ? ip.v_out : ip.v_in, w = outer ? ip.w_out : ip.w_in;
+        const double bx = outer ? ip.Bx_out : ip.Bx_in, by = outer ? ip.By_out : ip.By_in, bz = outer ? ip.Bz_out : ip.Bz_in;
+        U(i, j, k, ID) = rho;
+        U(i, j, k, IP) = pr / (gamma0 - 1.0) + 0.5 * rho * (u * u + v * v + w * w) + 0.5 * (bx * bx + by * by + bz * bz);
+        U(i, j, k, IU) = u;
+        U(i, j, k, IV) = v;
+        U(i, j, k, IW) = w;
+        U(i, j, k, IA) = bx;
+        U(i, j, k, IB) = by;
+        U(i, j, k, IC) = bz;
+      }
+}
+
+void init_kelvin_helmholtz(const HydroParams &p, const KHParams &kh, DataArray3dHost &U) {
+  if (kh.p_rand) {
+    // MHDInitFunctors3D.h:492-530 draws from a Kokkos XorShift64 pool whose states are handed out per thread: the reference
+    // itself is not reproducible from run to run there
+    fprintf(stderr, "kelvin_helmholtz: perturbation_rand draws from Kokkos' per-thread random pool in the reference and is not "
+                    "reproducible; use perturbation_sine or perturbation_sine_robertson\n");
+    std::abort();
+  }
+  const CellCoords cc{p};
+  const double gamma0 = p.settings.gamma0;
+  for (int k = 0; k < p.ksize; ++k)
+    for (int j = 0; j < p.jsize; ++j)
+      for (int i = 0; i < p.isize; ++i) {
+        const double x = cc.x(i), y = cc.y(j), z = cc.z(k);
+        double d, u, v, w;
+        if (kh.p_sine_rob) {
+          const int n = kh.mode;
+          const double z1 = 0.25, z2 = 0.75;
+          const double rho1 = kh.d_in, rho2 = kh.d_out, v1x = kh.vflow_in, v2x = kh.vflow_out;
+          const double v1y = kh.vflow_in / 2, v2y = kh.vflow_out / 2;
+          const double ramp = 1.0 / (1.0 + exp(2 * (z - z1) / kh.delta)) + 1.0 / (1.0 + exp(2 * (z2 - z) / kh.delta));
+          d = rho1 + ramp * (rho2 - rho1);
+          u = v1x + ramp * (v2x - v1x);
+          v = v1y + ramp * (v2y - v1y);
+          w = kh.w0 * sin(n * M_PI * x) * sin(n * M_PI * y);
+        } else if (kh.p_sine) {
+          const int n = kh.mode;
+          const double z1 = 0.25, z2 = 0.75;
+          d = (z >= z1 && z <= z2) ? kh.d_in : kh.d_out;
+          u = (z >= z1 && z <= z2) ? kh.vflow_in : kh.vflow_out;
+          v = 0;
+          w = kh.w0 * sin(n * M_PI * x);
+        } else {
+          continue;  // no perturbation flag set: the reference leaves the zero-initialised array untouched
+        }
+        const double bx = 0.5, by = 0.0, bz = 0.0;
+        U(i, j, k, ID) = d;
+        U(i, j, k, IU) = d * u;
+        U(i, j, k, IV) = d * v;
+        U(i, j, k, IW) = d * w;
+        U(i, j, k, IA) = bx;
+        U(i, j, k, IB) = by;
+        U(i, j, k, IC) = bz;
+        U(i, j, k, IP) = kh.pressure / (gamma0 - 1.0) + 0.5 * d * (u * u + v * v + w * w) + 0.5 * (bx * bx + by * by + bz * bz);
+      }
+}
+
+void init_rotor(const HydroParams &p, const RotorParams &rp, DataArray3dHost &U) {
+  const CellCoords cc{p};
+  const double gamma0 = p.settings.gamma0;
+  const double xCenter = (p.xmax + p.xmin) / 2, yCenter = (p.ymax + p.ymin) / 2;
+  for (int k = 0; k < p.ksize; ++k)
+    for (int j = 0; j < p.jsize; ++j)
+      for (int i = 0; i < p.isize; ++i) {
+        const double x = cc.x(i), y = cc.y(j);
+        const double r = sqrt((x - xCenter) * (x - xCenter) + (y - yCenter) * (y - yCenter));
+        const double f_r = (rp.r1 - r) / (rp.r1 - rp.r0);
+        if (r <= rp.r0) {
+          U(i, j, k, ID) = 10.0;
+          U(i, j, k, IU) = -rp.u0 * (y - yCenter) / rp.r0;
+          U(i, j, k, IV) = rp.u0 * (x - xCenter) / rp.r0;
+        } else if (r <= rp.r1) {
+          U(i, j, k, ID) = 1 + 9 * f_r;
+          U(i, j, k, IU) = -f_r * rp.u0 * (y - yCenter) / r;
+          U(i, j, k, IV) = f_r * rp.u0 * (x - xCenter) / r;
+        } else {
+          U(i, j, k, ID) = 1.0;
+          U(i, j, k, IU) = 0.0;
+          U(i, j, k, IV) = 0.0;
+        }
+        U(i, j, k, IW) = 0.0;
+        U(i, j, k, IA) = rp.b0;
+        U(i, j, k, IB) = 0.0;
+        U(i, j, k, IC) = 0.0;
+        U(i, j, k, IP) = rp.p0 / (gamma0 - 1.0) +
+                         (U(i, j, k, IU) * U(i, j, k, IU) + U(i, j, k, IV) * U(i, j, k, IV) + U(i, j, k, IW) * U(i, j, k, IW)) / 2 /
+                           U(i, j, k, ID) +
+                         (U(i, j, k, IA) * U(i, j, k, IA)) / 2;
+      }
+}
+
 void init_field_loop(const HydroParams &p, const FieldLoopParams &fl, DataArray3dHost &U) {
   const int gw = p.ghostWidth;
   const CellCoords cc{p};
@@ -158,8 +310,20 @@ std::string init_problem(const HydroParams &params, ConfigMap &configMap, const 
     init_field_loop(params, FieldLoopParams(configMap), U);
     return problem;
   }
-  // implode / kelvin_helmholtz / rotor / wave are "next" rows; like the reference's final else,
-  // an unknown name falls back to Orszag-Tang with a message (SolverMHDMuscl.h:701-709)
+  if (problem == "implode") {
+    init_implode(params, ImplodeParams(configMap), U);
+    return problem;
+  }
+  if (problem == "kelvin_helmholtz") {
+    init_kelvin_helmholtz(params, KHParams(configMap), U);
+    return problem;
+  }
+  if (problem == "rotor") {
+    init_rotor(params, RotorParams(configMap), U);
+    return problem;
+  }
+  // "wave" is a "next" row; like the reference's final else, an unknown name falls back to Orszag-Tang with a
+  // message (SolverMHDMuscl.h:701-709)
   std::cout << "Problem : " << problem << " is not recognized / implemented." << std::endl;
   std::cout << "Use default - Orszag-Tang vortex" << std::endl;
   init_orszag_tang(params, OrszagTangParams(configMap), U);

@@ -23,6 +23,25 @@ struct FieldLoopParams {
 
 // host-side initial conditions (libm sin/cos/sqrt like the reference's OpenMP build); they fill the
 // whole array, ghosts included, exactly where the reference's init functors do
+struct ImplodeParams {  // src/shared/problems/ImplodeParams.h:14-62
+  double rho_out, p_out, u_out, v_out, w_out, Bx_out, By_out, Bz_out;
+  double rho_in, p_in, u_in, v_in, w_in, Bx_in, By_in, Bz_in;
+  int shape;
+  explicit ImplodeParams(ConfigMap &configMap);
+};
+struct KHParams {  // src/shared/problems/KHParams.h:17-92
+  double d_in, d_out, pressure, vflow_in, vflow_out, amplitude, inner_size = 0.0, w0 = 0.0, delta = 0.0;
+  bool p_sine, p_sine_rob, p_rand;
+  int seed = 0, mode = 0;
+  explicit KHParams(ConfigMap &configMap);
+};
+struct RotorParams {  // src/shared/problems/RotorParams.h:13-26
+  double r0, r1, u0, p0, b0;
+  explicit RotorParams(ConfigMap &configMap);
+};
+void init_implode(const HydroParams &params, const ImplodeParams &ip, DataArray3dHost &U);            // MHDInitFunctors3D.h:34-150
+void init_kelvin_helmholtz(const HydroParams &params, const KHParams &kh, DataArray3dHost &U);        // MHDInitFunctors3D.h:420-622
+void init_rotor(const HydroParams &params, const RotorParams &rp, DataArray3dHost &U);                // MHDInitFunctors3D.h:627-757
 void init_orszag_tang(const HydroParams &params, const OrszagTangParams &ot, DataArray3dHost &U);  // MHDInitFunctors3D.h:264-415
 void init_blast(const HydroParams &params, const BlastParams &b, DataArray3dHost &U);              // MHDInitFunctors3D.h:155-259
 void init_field_loop(const HydroParams &params, const FieldLoopParams &fl, DataArray3dHost &U);    // MHDInitFunctors3D.h:759-1023

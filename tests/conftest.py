@@ -17,6 +17,13 @@ def golden_cases():
     return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
 
 
+def init_only_cases():
+    """Fixtures holding only the reference's step-0 state (problems the reference itself cannot step in 3-D: its rotor
+    run produces NaN from the first step on, tests/golden/make_golden.py)."""
+    d = os.path.join(GOLDEN, "init_only")
+    return sorted("init_only/" + f[:-4] for f in os.listdir(d) if f.endswith(".npz")) if os.path.isdir(d) else []
+
+
 @pytest.fixture(scope="session")
 def oracle_mod():
     from oracle import oracle as O

@@ -39,6 +39,17 @@ CASES = {
     "ot_llf_16x12x8": ("orszag_tang", (16, 12, 8), 5, OT, None, 0.8, 3, "llf"),
     "blast_llf_dirichlet_12x10x8": ("blast", (12, 10, 8), 6, BLAST, None, 0.8, 1, "llf"),
     "ot_hll_16x12x8": ("orszag_tang", (16, 12, 8), 5, OT, None, 0.8, 3, "hll"),
+    # the other initial conditions of SolverMHDMuscl<3>::init (SolverMHDMuscl.h:653-713)
+    "implode_12x12x12": ("implode", (12, 12, 12), 5, "[implode]\nBx_outer=0.3\nBy_inner=0.2\nvx_inner=0.1\n", None, 0.8, 1),
+    "kh_robertson_12x12x16": ("kelvin_helmholtz", (12, 12, 16), 5, "[KH]\nd_in=2.0\n", None, 0.8, 3),
+    "kh_sine_12x10x16": ("kelvin_helmholtz", (12, 10, 16), 5,
+                         "[KH]\nperturbation_sine=true\nperturbation_sine_robertson=false\nd_in=2.0\nw0=0.05\nmode=4\n", None, 0.8, [3, 3, 3, 3, 2, 2]),
+}
+# Step-0 state only (written to tests/golden/init_only/): the reference's 3-D rotor run turns NaN at the first step
+# (By = Bz = 0 exactly: 0/0 in riemann_hlld's star states), so there is nothing to step against.
+INIT_ONLY = {
+    "rotor_16x16x4": ("rotor", (16, 16, 4), 1, "[rotor]\nr0=0.2\nr1=0.3\n", None, 0.8, 3),
+    "rotor_default_24x20x4": ("rotor", (24, 20, 4), 1, "", None, 0.8, 3),
 }
 
 
@@ -63,8 +74,22 @@ def run(case):
     return out
 
 
+def run_init_only(case):
+    problem, n, nsteps, extra, bounds, cfl, bc = INIT_ONLY[case][:7]
+    ini = O.make_ini(nstepmax=1, problem=problem, n=n, extra=extra, bounds=bounds, cfl=cfl, bc=bc, nlog=1, tend=10.0)
+    stdout, states = O.run_reference(ini, threads=4)
+    return {"init": states[0], "ini": np.array(ini)}
+
+
 if __name__ == "__main__":
     here = os.path.dirname(os.path.abspath(__file__))
+    os.makedirs(os.path.join(here, "init_only"), exist_ok=True)
+    for case in INIT_ONLY:
+        if len(sys.argv) > 1 and case not in sys.argv[1:]:
+            continue
+        data = run_init_only(case)
+        np.savez_compressed(os.path.join(here, "init_only", case + ".npz"), **data)
+        print(case, {k: getattr(v, "shape", None) for k, v in data.items()})
     for case in CASES:
         if len(sys.argv) > 1 and case not in sys.argv[1:]:
             continue

@@ -7,7 +7,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, ROOT, golden_cases
+from conftest import GOLDEN, ROOT, golden_cases, init_only_cases
 
 import ppkmhd_b200 as ppk
 from ppkmhd_b200 import capi
@@ -42,7 +42,7 @@ def test_params_match_oracle_and_float_parsing(case, oracle_mod):
     assert t_end == 10.0 and nstep == int(np.load(f"{GOLDEN}/{case}.npz")["nsteps"])
 
 
-@pytest.mark.parametrize("case", golden_cases())
+@pytest.mark.parametrize("case", golden_cases() + init_only_cases())
 def test_initial_condition_bitwise(case, oracle_mod):
     g = np.load(f"{GOLDEN}/{case}.npz")
     ini = str(g["ini"])
