@@ -223,6 +223,105 @@ void orc_init_rotor(const orc_params *p, double r0, double r1, double u0, double
       }
 }
 
+int orc_init_wave(const orc_params *p, double wave_amplitude, int wave_type, double *U)
+{
+  /* Linear MHD wave on a rotated axis: src/shared/problems/WaveParams.h:30-150 (eigenvector table, angles, k_par) and
+   * src/muscl/MHDInitFunctors3D.h:1034-1308 (vector potential on edges -> face B by a discrete curl -> interior cells).
+   * Cells outside the ranges written below stay zero, like the reference's zero-initialised View. Returns -1 for an
+   * unknown wave type (the reference exits). */
+  double rev[7], wave_V0 = 0.0;
+  if (wave_type == 0) {
+    const double r[7] = {4.472136e-01, -8.944272e-01, 4.216370e-01, 1.490712e-01, 2.012461e+00, 8.432740e-01, 2.981424e-01};
+    memcpy(rev, r, sizeof(r));
+  } else if (wave_type == 1) {
+    const double r[7] = {0.0, 0.0, -3.333333e-01, 9.428090e-01, 0.0, -3.333333e-01, 9.428090e-01};
+    memcpy(rev, r, sizeof(r));
+  } else if (wave_type == 2) {
+    const double r[7] = {8.944272e-01, -4.472136e-01, -8.432740e-01, -2.981424e-01, 6.708204e-01, -4.216370e-01, -1.490712e-01};
+    memcpy(rev, r, sizeof(r));
+  } else if (wave_type == 3) {
+    const double r[7] = {1.0, 1.0, 0.0, 0.0, 0.5, 0.0, 0.0};
+    memcpy(rev, r, sizeof(r));
+    wave_V0 = 1.0;
+  } else {
+    return -1;
+  }
+  const double Lx = p->xmax - p->xmin, Ly = p->ymax - p->ymin, Lz = p->zmax - p->zmin;
+  const double d0 = 1.0, p0 = 1.0 / p->gamma0;
+  const double TwoPi = 4.0 * asin(1.0);
+  const double ang_3 = atan(Lx / Ly);
+  const double sin_a3 = sin(ang_3), cos_a3 = cos(ang_3);
+  const double ang_2 = atan(0.5 * (Lx * cos_a3 + Ly * sin_a3) / Lz);
+  const double sin_a2 = sin(ang_2), cos_a2 = cos(ang_2);
+  const double x1l = Lx * cos_a2 * cos_a3, x2l = Ly * cos_a2 * sin_a3, x3l = Lz * sin_a2;
+  double lambda = x1l;
+  if (ang_3 != 0.0) lambda = fmin(lambda, x2l);
+  if (ang_2 != 0.) lambda = fmin(lambda, x3l);
+  const double k_par = TwoPi / lambda;
+  const double dby = wave_amplitude * rev[5], dbz = wave_amplitude * rev[6];
+  const double bx0 = 1.0, by0 = sqrt(2.0), bz0 = 0.5;
+
+  const int gw = p->gw;
+  const long n = orc_ncells(p);
+  const double dx = p->dx, dy = p->dy, dz = p->dz;
+  double *A = (double *)calloc((size_t)(3 * n), sizeof(double));
+  memset(U, 0, sizeof(double) * NV * (size_t)n);
+#define AV(i, j, k, c) A[(size_t)(i) + (size_t)p->isize * ((size_t)(j) + (size_t)p->jsize * ((size_t)(k) + (size_t)p->ksize * (size_t)(c)))]
+  for (int k = 0; k < p->ksize; ++k)
+    for (int j = 0; j < p->jsize; ++j)
+      for (int i = 0; i < p->isize; ++i) { /* :1098-1148 */
+        double x = p->xmin + dx / 2 + (i + p->nx * p->px - gw) * dx;
+        double y = p->ymin + dy / 2 + (j + p->ny * p->py - gw) * dy;
+        double z = p->zmin + dz / 2 + (k + p->nz * p->pz - gw) * dz;
+        double Ay, Az, tmpx, tmpy, x1, x2, x3;
+        x1 = x; x2 = y - dy / 2; x3 = z - dz / 2;
+        tmpx = x1 * cos_a2 * cos_a3 + x2 * cos_a2 * sin_a3 + x3 * sin_a2;
+        tmpy = -x1 * sin_a3 + x2 * cos_a3;
+        Ay = bz0 * tmpx - (dbz / k_par) * cos(k_par * tmpx);
+        Az = -by0 * tmpx + (dby / k_par) * cos(k_par * tmpx) + bx0 * tmpy;
+        AV(i, j, k, 0) = -Ay * sin_a3 - Az * sin_a2 * cos_a3;
+        x1 = x - dx / 2; x2 = y; x3 = z - dz / 2;
+        tmpx = x1 * cos_a2 * cos_a3 + x2 * cos_a2 * sin_a3 + x3 * sin_a2;
+        tmpy = -x1 * sin_a3 + x2 * cos_a3;
+        Ay = bz0 * tmpx - (dbz / k_par) * cos(k_par * tmpx);
+        Az = -by0 * tmpx + (dby / k_par) * cos(k_par * tmpx) + bx0 * tmpy;
+        AV(i, j, k, 1) = Ay * cos_a3 - Az * sin_a2 * sin_a3;
+        x1 = x - dx / 2; x2 = y - dy / 2; x3 = z;
+        tmpx = x1 * cos_a2 * cos_a3 + x2 * cos_a2 * sin_a3 + x3 * sin_a2;
+        tmpy = -x1 * sin_a3 + x2 * cos_a3;
+        Az = -by0 * tmpx + (dby / k_par) * cos(k_par * tmpx) + bx0 * tmpy;
+        AV(i, j, k, 2) = Az * cos_a2;
+      }
+  for (int k = gw - 1; k < p->ksize - gw + 1; ++k)
+    for (int j = gw - 1; j < p->jsize - gw + 1; ++j)
+      for (int i = gw - 1; i < p->isize - gw + 1; ++i) { /* :1166-1178 */
+        U[AT(p, i, j, k, IA)] = (AV(i, j + 1, k, 2) - AV(i, j, k, 2)) / dy - (AV(i, j, k + 1, 1) - AV(i, j, k, 1)) / dz;
+        U[AT(p, i, j, k, IB)] = (AV(i, j, k + 1, 0) - AV(i, j, k, 0)) / dz - (AV(i + 1, j, k, 2) - AV(i, j, k, 2)) / dx;
+        U[AT(p, i, j, k, IC)] = (AV(i + 1, j, k, 1) - AV(i, j, k, 1)) / dx - (AV(i, j + 1, k, 0) - AV(i, j, k, 0)) / dy;
+      }
+  for (int k = gw; k < p->ksize - gw; ++k)
+    for (int j = gw; j < p->jsize - gw; ++j)
+      for (int i = gw; i < p->isize - gw; ++i) { /* :1236-1262 */
+        double x = p->xmin + dx / 2 + (i + p->nx * p->px - gw) * dx;
+        double y = p->ymin + dy / 2 + (j + p->ny * p->py - gw) * dy;
+        double z = p->zmin + dz / 2 + (k + p->nz * p->pz - gw) * dz;
+        double X = cos_a2 * (x * cos_a3 + y * sin_a3) + z * sin_a2;
+        double sn = sin(k_par * X);
+        double Mx = d0 * wave_V0 + wave_amplitude * sn * rev[1];
+        double My = wave_amplitude * sn * rev[2];
+        double Mz = wave_amplitude * sn * rev[3];
+        U[AT(p, i, j, k, ID)] = d0 + wave_amplitude * sn * rev[0];
+        U[AT(p, i, j, k, IU)] = Mx * cos_a2 * cos_a3 - My * sin_a3 - Mz * sin_a2 * cos_a3;
+        U[AT(p, i, j, k, IV)] = Mx * cos_a2 * sin_a3 + My * cos_a3 - Mz * sin_a2 * sin_a3;
+        U[AT(p, i, j, k, IW)] = Mx * sin_a2 + Mz * cos_a2;
+        U[AT(p, i, j, k, IP)] = p0 / (p->gamma0 - 1.0) + 0.5 * d0 * wave_V0 * wave_V0 + 0.5 * (bx0 * bx0 + by0 * by0 + bz0 * bz0) +
+                                wave_amplitude * sn * rev[4];
+      }
+#undef AV
+  free(A);
+  return 0;
+}
+
 void orc_init_field_loop(const orc_params *p, double radius, double density_in, double amplitude, double vflow,
                          double *U)
 {

@@ -73,6 +73,7 @@ void orc_init_kelvin_helmholtz(const orc_params *p, double d_in, double d_out, d
                                double *U);                                          /* MHDInitFunctors3D.h:420-622 */
 void orc_init_rotor(const orc_params *p, double r0, double r1, double u0, double p0, double b0,
                     double *U);                                                     /* MHDInitFunctors3D.h:627-757 */
+int orc_init_wave(const orc_params *p, double wave_amplitude, int wave_type, double *U); /* MHDInitFunctors3D.h:1034-1308, WaveParams.h */
 
 /* ---- the step, one function per reference functor ---- */
 void orc_make_boundary(const orc_params *p, double *U, int face);                   /* BoundariesFunctors.h:749-1053 */

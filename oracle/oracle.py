@@ -65,6 +65,7 @@ def lib():
         _lib.orc_init_implode.argtypes = [pp, dp, dp, C.c_int, dp]
         _lib.orc_init_kelvin_helmholtz.argtypes = [pp] + [C.c_double] * 5 + [C.c_int, C.c_double, C.c_double, C.c_int, dp]
         _lib.orc_init_rotor.argtypes = [pp] + [C.c_double] * 5 + [dp]
+        _lib.orc_init_wave.argtypes = [pp, C.c_double, C.c_int, dp]
         _lib.orc_make_boundary.argtypes = [pp, dp, C.c_int]
         _lib.orc_make_boundaries.argtypes = [pp, dp]
         _lib.orc_convert_to_primitives.argtypes = [pp, dp, dp]
@@ -223,6 +224,10 @@ def init_problem(p: OrcParams, cfg: Config) -> np.ndarray:
         # src/shared/problems/RotorParams.h:17-24
         L.orc_init_rotor(C.byref(p), cfg.f("rotor", "r0", 0.1), cfg.f("rotor", "r1", 0.115), cfg.f("rotor", "u0", 2.0),
                          cfg.f("rotor", "p0", 1.0), cfg.f("rotor", "b0", 5.0 / np.sqrt(4 * np.pi)), _dp(U))
+    elif problem == "wave":
+        # src/shared/problems/WaveParams.h:47-49 (gamma0 and the mesh bounds are the ones already in p)
+        if L.orc_init_wave(C.byref(p), cfg.f("wave", "amplitude", 1.0e-6), cfg.i("wave", "type", 0), _dp(U)) != 0:
+            raise ValueError("wave type not implemented (the reference aborts)")
     else:
         L.orc_init_orszag_tang(C.byref(p), cfg.f("OrszagTang", "kt", 0.0), _dp(U))
     return U

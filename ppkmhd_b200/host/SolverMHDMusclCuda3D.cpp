@@ -80,6 +80,45 @@ KHParams::KHParams(ConfigMap &c) {
     delta = c.getFloat("KH", "delta", 0.03);
   }
 }
+WaveParams::WaveParams(ConfigMap &c) {
+  // the struct has its own defaults for the box (3 x 1.5 x 1.5) and for gamma0
+  const double Lx = c.getFloat("mesh", "xmax", 3.0) - c.getFloat("mesh", "xmin", 0.0);
+  const double Ly = c.getFloat("mesh", "ymax", 1.5) - c.getFloat("mesh", "ymin", 0.0);
+  const double Lz = c.getFloat("mesh", "zmax", 1.5) - c.getFloat("mesh", "zmin", 0.0);
+  const double gamma0 = c.getFloat("hydro", "gamma0", 1.66667);
+  wave_amplitude = c.getFloat("wave", "amplitude", 1.0e-6);
+  wave_type = (int)c.getInteger("wave", "type", 0);
+  // right eigenvectors of the fast, Alfven, slow and contact waves for d0 = 1, p0 = 1/gamma, B0 = (1, sqrt 2, 1/2)
+  static const double table[4][7] = {
+    {4.472136e-01, -8.944272e-01, 4.216370e-01, 1.490712e-01, 2.012461e+00, 8.432740e-01, 2.981424e-01},
+    {0.0, 0.0, -3.333333e-01, 9.428090e-01, 0.0, -3.333333e-01, 9.428090e-01},
+    {8.944272e-01, -4.472136e-01, -8.432740e-01, -2.981424e-01, 6.708204e-01, -4.216370e-01, -1.490712e-01},
+    {1.0, 1.0, 0.0, 0.0, 0.5, 0.0, 0.0}};
+  if (wave_type < 0 || wave_type > 3) {
+    std::cerr << "wave_type = " << wave_type << " not implemented!\nABORT!\n";
+    exit(EXIT_FAILURE);
+  }
+  for (int v = 0; v < 7; ++v) rev[v] = table[wave_type][v];
+  wave_V0 = wave_type == 3 ? 1.0 : 0.0;
+  d0 = 1.0;
+  p0 = 1.0 / gamma0;
+  const double TwoPi = 4.0 * asin(1.0);
+  const double ang_3 = atan(Lx / Ly);
+  sin_a3 = sin(ang_3);
+  cos_a3 = cos(ang_3);
+  const double ang_2 = atan(0.5 * (Lx * cos_a3 + Ly * sin_a3) / Lz);
+  sin_a2 = sin(ang_2);
+  cos_a2 = cos(ang_2);
+  double lambda = Lx * cos_a2 * cos_a3;
+  if (ang_3 != 0.0) lambda = fmin(lambda, Ly * cos_a2 * sin_a3);
+  if (ang_2 != 0.) lambda = fmin(lambda, Lz * sin_a2);
+  k_par = TwoPi / lambda;
+  dby = wave_amplitude * rev[5];
+  dbz = wave_amplitude * rev[6];
+  bx0 = 1.0;
+  by0 = sqrt(2.0);
+  bz0 = 0.5;
+}
 RotorParams::RotorParams(ConfigMap &c) {
   r0 = c.getFloat("rotor", "r0", 0.1);
   r1 = c.getFloat("rotor", "r1", 0.115);
@@ -258,6 +297,60 @@ void init_rotor(const HydroParams &p, const RotorParams &rp, DataArray3dHost &U)
       }
 }
 
+// Vector potential on the cell edges -> face-centred B by a discrete curl (div B = 0 to round-off) -> hydro variables
+// of the interior cells; everything else stays zero until the first ghost fill.
+void init_wave(const HydroParams &p, const WaveParams &wp, DataArray3dHost &U) {
+  const CellCoords cc{p};
+  const int gw = p.ghostWidth;
+  const double dx = p.dx, dy = p.dy, dz = p.dz;
+  const size_t ncell = (size_t)p.isize * p.jsize * p.ksize;
+  std::vector<double> pot(3 * ncell, 0.0);
+  auto A = [&](int i, int j, int k, int c) -> double & { return pot[(size_t)i + (size_t)p.isize * ((size_t)j + (size_t)p.jsize * ((size_t)k + (size_t)p.ksize * c))]; };
+  // potential of the rotated wave at one point: (Ay, Az) in the wave frame
+  auto rotated = [&](double x1, double x2, double x3, double &Ay, double &Az) {
+    const double tmpx = x1 * wp.cos_a2 * wp.cos_a3 + x2 * wp.cos_a2 * wp.sin_a3 + x3 * wp.sin_a2;
+    const double tmpy = -x1 * wp.sin_a3 + x2 * wp.cos_a3;
+    Ay = wp.bz0 * tmpx - (wp.dbz / wp.k_par) * cos(wp.k_par * tmpx);
+    Az = -wp.by0 * tmpx + (wp.dby / wp.k_par) * cos(wp.k_par * tmpx) + wp.bx0 * tmpy;
+  };
+  for (int k = 0; k < p.ksize; ++k)
+    for (int j = 0; j < p.jsize; ++j)
+      for (int i = 0; i < p.isize; ++i) {
+        const double x = cc.x(i), y = cc.y(j), z = cc.z(k);
+        double Ay, Az;
+        rotated(x, y - dy / 2, z - dz / 2, Ay, Az);
+        A(i, j, k, 0) = -Ay * wp.sin_a3 - Az * wp.sin_a2 * wp.cos_a3;
+        rotated(x - dx / 2, y, z - dz / 2, Ay, Az);
+        A(i, j, k, 1) = Ay * wp.cos_a3 - Az * wp.sin_a2 * wp.sin_a3;
+        rotated(x - dx / 2, y - dy / 2, z, Ay, Az);
+        A(i, j, k, 2) = Az * wp.cos_a2;
+      }
+  for (int k = gw - 1; k < p.ksize - gw + 1; ++k)
+    for (int j = gw - 1; j < p.jsize - gw + 1; ++j)
+      for (int i = gw - 1; i < p.isize - gw + 1; ++i) {
+        U(i, j, k, IA) = (A(i, j + 1, k, 2) - A(i, j, k, 2)) / dy - (A(i, j, k + 1, 1) - A(i, j, k, 1)) / dz;
+        U(i, j, k, IB) = (A(i, j, k + 1, 0) - A(i, j, k, 0)) / dz - (A(i + 1, j, k, 2) - A(i, j, k, 2)) / dx;
+        U(i, j, k, IC) = (A(i + 1, j, k, 1) - A(i, j, k, 1)) / dx - (A(i, j + 1, k, 0) - A(i, j, k, 0)) / dy;
+      }
+  const double gamma0 = p.settings.gamma0;
+  for (int k = gw; k < p.ksize - gw; ++k)
+    for (int j = gw; j < p.jsize - gw; ++j)
+      for (int i = gw; i < p.isize - gw; ++i) {
+        const double x = cc.x(i), y = cc.y(j), z = cc.z(k);
+        const double X = wp.cos_a2 * (x * wp.cos_a3 + y * wp.sin_a3) + z * wp.sin_a2;
+        const double sn = sin(wp.k_par * X);
+        const double Mx = wp.d0 * wp.wave_V0 + wp.wave_amplitude * sn * wp.rev[1];
+        const double My = wp.wave_amplitude * sn * wp.rev[2];
+        const double Mz = wp.wave_amplitude * sn * wp.rev[3];
+        U(i, j, k, ID) = wp.d0 + wp.wave_amplitude * sn * wp.rev[0];
+        U(i, j, k, IU) = Mx * wp.cos_a2 * wp.cos_a3 - My * wp.sin_a3 - Mz * wp.sin_a2 * wp.cos_a3;
+        U(i, j, k, IV) = Mx * wp.cos_a2 * wp.sin_a3 + My * wp.cos_a3 - Mz * wp.sin_a2 * wp.sin_a3;
+        U(i, j, k, IW) = Mx * wp.sin_a2 + Mz * wp.cos_a2;
+        U(i, j, k, IP) = wp.p0 / (gamma0 - 1.0) + 0.5 * wp.d0 * wp.wave_V0 * wp.wave_V0 +
+                         0.5 * (wp.bx0 * wp.bx0 + wp.by0 * wp.by0 + wp.bz0 * wp.bz0) + wp.wave_amplitude * sn * wp.rev[4];
+      }
+}
+
 void init_field_loop(const HydroParams &p, const FieldLoopParams &fl, DataArray3dHost &U) {
   const int gw = p.ghostWidth;
   const CellCoords cc{p};
@@ -322,8 +415,11 @@ std::string init_problem(const HydroParams &params, ConfigMap &configMap, const 
     init_rotor(params, RotorParams(configMap), U);
     return problem;
   }
-  // "wave" is a "next" row; like the reference's final else, an unknown name falls back to Orszag-Tang with a
-  // message (SolverMHDMuscl.h:701-709)
+  if (problem == "wave") {
+    init_wave(params, WaveParams(configMap), U);
+    return problem;
+  }
+  // like the reference's final else, an unknown name falls back to Orszag-Tang with a message (SolverMHDMuscl.h:701-709)
   std::cout << "Problem : " << problem << " is not recognized / implemented." << std::endl;
   std::cout << "Use default - Orszag-Tang vortex" << std::endl;
   init_orszag_tang(params, OrszagTangParams(configMap), U);

@@ -39,6 +39,12 @@ struct RotorParams {  // src/shared/problems/RotorParams.h:13-26
   double r0, r1, u0, p0, b0;
   explicit RotorParams(ConfigMap &configMap);
 };
+struct WaveParams {  // src/shared/problems/WaveParams.h:13-150 (linear wave on an axis rotated by (a2, a3))
+  double wave_amplitude, wave_V0 = 0.0, rev[7], d0, p0, sin_a2, cos_a2, sin_a3, cos_a3, dby, dbz, bx0, by0, bz0, k_par;
+  int wave_type;
+  explicit WaveParams(ConfigMap &configMap);
+};
+void init_wave(const HydroParams &params, const WaveParams &wp, DataArray3dHost &U);                  // MHDInitFunctors3D.h:1034-1308
 void init_implode(const HydroParams &params, const ImplodeParams &ip, DataArray3dHost &U);            // MHDInitFunctors3D.h:34-150
 void init_kelvin_helmholtz(const HydroParams &params, const KHParams &kh, DataArray3dHost &U);        // MHDInitFunctors3D.h:420-622
 void init_rotor(const HydroParams &params, const RotorParams &rp, DataArray3dHost &U);                // MHDInitFunctors3D.h:627-757

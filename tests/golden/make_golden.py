@@ -44,6 +44,9 @@ CASES = {
     "kh_robertson_12x12x16": ("kelvin_helmholtz", (12, 12, 16), 5, "[KH]\nd_in=2.0\n", None, 0.8, 3),
     "kh_sine_12x10x16": ("kelvin_helmholtz", (12, 10, 16), 5,
                          "[KH]\nperturbation_sine=true\nperturbation_sine_robertson=false\nd_in=2.0\nw0=0.05\nmode=4\n", None, 0.8, [3, 3, 3, 3, 2, 2]),
+    # linear wave on the rotated axis (the reference's convergence test problem): fast wave and Alfven wave
+    "wave_fast_16x8x8": ("wave", (16, 8, 8), 5, "[wave]\namplitude=1e-3\ntype=0\n", (0, 3, 0, 1.5, 0, 1.5), 0.8, 3),
+    "wave_alfven_16x8x12": ("wave", (16, 8, 12), 5, "[wave]\namplitude=1e-2\ntype=1\n", (0, 3, 0, 1.5, 0, 2.0), 0.8, 3),
 }
 # Step-0 state only (written to tests/golden/init_only/): the reference's 3-D rotor run turns NaN at the first step
 # (By = Bz = 0 exactly: 0/0 in riemann_hlld's star states), so there is nothing to step against.
