@@ -232,6 +232,47 @@ def test_full_size_properties_512_blast_and_field_loop():
         s.close()
 
 
+def test_linear_wave_convergence_and_tend_clamp(oracle_mod):
+    """The reference's only physics test (test/convergence/: fulltest.sh + plot-results.py): a fast magnetosonic wave on
+    the rotated axis of a 3 x 1.5 x 1.5 periodic box runs for one period (tEnd = 0.5) and the L1 distance to the initial
+    state must fall at second order. Also the only case that runs to tEnd: the last step's dt is clamped
+    (SolverBase.cpp:174-177) and the loop stops on `t >= tEnd - 1e-14` (:199)."""
+    O = oracle_mod
+    wave = "[wave]\ntype=0\n"
+
+    def ini_for(nx):
+        ini = O.make_ini("wave", (nx, nx // 2, nx // 2), nstepmax=10000, extra=wave, bounds=(0, 3, 0, 1.5, 0, 1.5), cfl=0.4, tend=0.5)
+        return ini.replace("gamma0=1.666", "gamma0=1.6666666667")
+
+    def run_to_tend(s, t_end):
+        while True:
+            t, dt, it = s.get_time()
+            if t >= t_end - 1e-14:
+                return t, it
+            s.step()
+
+    def l1(a, b):  # plot-results.py: sqrt(sum over variables of (mean |difference|)^2)
+        return float(np.sqrt(sum(np.abs(a[v] - b[v]).mean() ** 2 for v in range(8))))
+
+    # 16 x 8 x 8: the exact build against the oracle, to the end time, bit for bit (t, iteration count and state)
+    ini = ini_for(16)
+    orc = O.Oracle(ini).run()
+    s, _ = make_solver(ini, exact=True)
+    t, it = run_to_tend(s, 0.5)
+    assert it == orc.iteration and t == orc.t, (it, orc.iteration, t, orc.t)
+    assert np.array_equal(s.interior(), orc.interior())
+    s.close()
+    errs = {}
+    for nx in (16, 32, 64):
+        s, _ = make_solver(ini_for(nx), exact=False)
+        u0 = s.interior().copy()
+        run_to_tend(s, 0.5)
+        errs[nx] = l1(s.interior(), u0)
+        s.close()
+    order = np.log2(errs[32] / errs[64])
+    assert errs[16] > errs[32] > errs[64] and order > 1.7, (errs, order)
+
+
 def test_error_paths():
     g = np.load(f"{GOLDEN}/ot_16x12x8.npz")
     ini = str(g["ini"])
