@@ -30,6 +30,12 @@ namespace ppk {
 namespace PPK_NS {
 
 #define DEV __device__ __forceinline__
+// write-once streams (basis, fluxes, EMFs, the new state): optionally stored with the evict-first hint (st.global.cs)
+#ifdef PPK_STREAM_STORES
+#  define ST(lhs, val) __stcs(&(lhs), (val))
+#else
+#  define ST(lhs, val) ((lhs) = (val))
+#endif
 
 DEV long long cidx(const GridParams &g, int i, int j, int k) {
   return (long long)i + (long long)g.isize * ((long long)j + (long long)g.jsize * (long long)k);
@@ -914,15 +920,15 @@ __global__ void __launch_bounds__(128, MINB) k_trace(const GridParams g, const S
   AL = AL + sAL0; BL = BL + sBL0; CL = CL + sCL0;
 
   double *Bs = BASIS + c;
-  Bs[(BQ + ID) * N] = r; Bs[(BQ + IP) * N] = p; Bs[(BQ + IU) * N] = u; Bs[(BQ + IV) * N] = v; Bs[(BQ + IW) * N] = w;
-  Bs[(BQ + IA) * N] = A; Bs[(BQ + IB) * N] = B; Bs[(BQ + IC) * N] = C;
-  Bs[(BSX + 0) * N] = drx; Bs[(BSX + 1) * N] = dpx; Bs[(BSX + 2) * N] = dux; Bs[(BSX + 3) * N] = dvx; Bs[(BSX + 4) * N] = dwx;
-  Bs[(BSX + 5) * N] = dBx; Bs[(BSX + 6) * N] = dCx;
-  Bs[(BSY + 0) * N] = dry; Bs[(BSY + 1) * N] = dpy; Bs[(BSY + 2) * N] = duy; Bs[(BSY + 3) * N] = dvy; Bs[(BSY + 4) * N] = dwy;
-  Bs[(BSY + 5) * N] = dAy; Bs[(BSY + 6) * N] = dCy;
-  Bs[(BSZ + 0) * N] = drz; Bs[(BSZ + 1) * N] = dpz; Bs[(BSZ + 2) * N] = duz; Bs[(BSZ + 3) * N] = dvz; Bs[(BSZ + 4) * N] = dwz;
-  Bs[(BSZ + 5) * N] = dAz; Bs[(BSZ + 6) * N] = dBz;
-  Bs[(BFACE + 0) * N] = AL; Bs[(BFACE + 1) * N] = BL; Bs[(BFACE + 2) * N] = CL;
+  ST(Bs[(BQ + ID) * N], r); ST(Bs[(BQ + IP) * N], p); ST(Bs[(BQ + IU) * N], u); ST(Bs[(BQ + IV) * N], v); ST(Bs[(BQ + IW) * N], w);
+  ST(Bs[(BQ + IA) * N], A); ST(Bs[(BQ + IB) * N], B); ST(Bs[(BQ + IC) * N], C);
+  ST(Bs[(BSX + 0) * N], drx); ST(Bs[(BSX + 1) * N], dpx); ST(Bs[(BSX + 2) * N], dux); ST(Bs[(BSX + 3) * N], dvx); ST(Bs[(BSX + 4) * N], dwx);
+  ST(Bs[(BSX + 5) * N], dBx); ST(Bs[(BSX + 6) * N], dCx);
+  ST(Bs[(BSY + 0) * N], dry); ST(Bs[(BSY + 1) * N], dpy); ST(Bs[(BSY + 2) * N], duy); ST(Bs[(BSY + 3) * N], dvy); ST(Bs[(BSY + 4) * N], dwy);
+  ST(Bs[(BSY + 5) * N], dAy); ST(Bs[(BSY + 6) * N], dCy);
+  ST(Bs[(BSZ + 0) * N], drz); ST(Bs[(BSZ + 1) * N], dpz); ST(Bs[(BSZ + 2) * N], duz); ST(Bs[(BSZ + 3) * N], dvz); ST(Bs[(BSZ + 4) * N], dwz);
+  ST(Bs[(BSZ + 5) * N], dAz); ST(Bs[(BSZ + 6) * N], dBz);
+  ST(Bs[(BFACE + 0) * N], AL); ST(Bs[(BFACE + 1) * N], BL); ST(Bs[(BFACE + 2) * N], CL);
 }
 
 // index, inside the 7 slopes of direction D, of field component m (m != D): r,p,u,v,w then the two
@@ -1248,7 +1254,7 @@ __global__ void __launch_bounds__(EmfCfg<E>::THREADS, EmfCfg<E>::MINB)
   const Corner RB = edge_state_smem<E, Cfg>(g, sm, o - st[D1], true, false);
   const Corner LT = edge_state_smem<E, Cfg>(g, sm, o - st[D2], false, true);
   const Corner LB = edge_state_smem<E, Cfg>(g, sm, o, false, false);
-  EMF[cidx(g, i, j, k) + (2 - E) * g.ncell] = emf_from_corners(g, RT, RB, LT, LB);
+  ST(EMF[cidx(g, i, j, k) + (2 - E) * g.ncell], emf_from_corners(g, RT, RB, LT, LB));
 }
 
 // component staged in slot s of the flux kernel: 0-6 q (r,p,un,t1,t2,b1,b2), 7-13 their slopes along D,
@@ -1317,7 +1323,7 @@ __global__ void __launch_bounds__(FluxCfg<D>::THREADS, FluxCfg<D>::MINB)
   riemann_face<RS>(g, rl, pl, unl, t1l, t2l, bnl, b1l, b2l, rr, pr, unr, t1r, t2r, bnr, b1r, b2r, fd, fp, fu, fv, fw);
   const long long N = g.ncell;
   double *Fo = F + cidx(g, i, j, k);
-  Fo[0 * N] = fd; Fo[1 * N] = fp; Fo[2 * N] = fu; Fo[3 * N] = fv; Fo[4 * N] = fw;
+  ST(Fo[0 * N], fd); ST(Fo[1 * N], fp); ST(Fo[2 * N], fu); ST(Fo[3 * N], fv); ST(Fo[4 * N], fw);
 }
 
 // Kokkos::deep_copy(data_out, data_in) (SolverMHDMuscl.cpp:477) + UpdateFunctor3D_MHD
@@ -1379,7 +1385,7 @@ __global__ void __launch_bounds__(256) k_update(const GridParams g, const StepSt
     u[IC] -= (Ex[c + sj] - ex) * dtdy;
   }
 #pragma unroll
-  for (int v = 0; v < NBVAR; ++v) Uout[c + v * N] = u[v];
+  for (int v = 0; v < NBVAR; ++v) ST(Uout[c + v * N], u[v]);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -82,3 +82,20 @@ def test_create_without_gpu_fails_loudly():
     p, _, _ = ppk.params_from_ini(str(np.load(f"{GOLDEN}/ot_16x12x8.npz")["ini"]))
     with pytest.raises(ppk.PpkError):
         ppk.Mhd3d(p)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the unmodified reference on the host cores) needs no GPU: one JSON line on stdout with the
+    contract's keys, nothing else."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--ref-n", "24"], capture_output=True, text=True, timeout=300, check=True).stdout
+    lines = [ln for ln in out.splitlines() if ln.strip()]
+    assert len(lines) == 1, out
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "Mcell-updates/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
