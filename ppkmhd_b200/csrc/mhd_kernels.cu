@@ -796,7 +796,8 @@ __global__ void k_advance_time(StepState *st) {
 
 // ComputeElecFieldFunctor3D (MHDRunFunctors3D.h:278-362) + ComputeMagSlopesFunctor3D (:441-538,
 // slope_unsplit_mhd_3d MHDBaseFunctor3D.h:561-668) on [1,size-1)^3.
-__global__ void __launch_bounds__(256) k_elec_dbf(const GridParams g, const double *__restrict__ U,
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_elec_dbf(const GridParams g, const double *__restrict__ U,
                                                   const double *__restrict__ Q, double *__restrict__ E,
                                                   double *__restrict__ DBF, const int jslab) {
   const int k = 1 + blockIdx.y;
@@ -1329,7 +1330,8 @@ __global__ void __launch_bounds__(FluxCfg<D>::THREADS, FluxCfg<D>::MINB)
 // Kokkos::deep_copy(data_out, data_in) (SolverMHDMuscl.cpp:477) + UpdateFunctor3D_MHD
 // (MHDRunFunctors3D.h:2430-2544) + UpdateEmfFunctor3D (:2549-2628) in one pass over the array:
 // ghost cells are copied, interior cells receive the 6 face fluxes (fixed order) and the CT update.
-__global__ void __launch_bounds__(256) k_update(const GridParams g, const StepState *__restrict__ stp,
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_update(const GridParams g, const StepState *__restrict__ stp,
                                                 const double *__restrict__ Uin, double *__restrict__ Uout,
                                                 const double *__restrict__ Fx, const double *__restrict__ Fy,
                                                 const double *__restrict__ Fz, const double *__restrict__ EMF, const int kb0,
@@ -1887,7 +1889,11 @@ static void l_elec_dbf(const GridParams &g, const double *U, const double *Q, do
   const int bs = 256;
   const int rows = slab_rows(g, 15, g.jsize - 2);
   dim3 grid(cdiv((long long)(g.isize - 2) * rows, bs), g.ksize - 2, cdiv(g.jsize - 2, rows));
-  k_elec_dbf<<<grid, bs, 0, s>>>(g, U, Q, E, DBF, rows);
+  static const int minb = getenv("PPK_ELEC_MINB") ? atoi(getenv("PPK_ELEC_MINB")) : 0;
+  if (minb == 8) k_elec_dbf<8><<<grid, bs, 0, s>>>(g, U, Q, E, DBF, rows);
+  else if (minb == 6) k_elec_dbf<6><<<grid, bs, 0, s>>>(g, U, Q, E, DBF, rows);
+  else if (minb == 1) k_elec_dbf<1><<<grid, bs, 0, s>>>(g, U, Q, E, DBF, rows);
+  else k_elec_dbf<0><<<grid, bs, 0, s>>>(g, U, Q, E, DBF, rows);
 }
 static void l_trace(const GridParams &g, const StepState *st, const double *U, const double *Q, const double *E,
                     double *BASIS, cudaStream_t s) {
@@ -2051,7 +2057,10 @@ static void l_update(const GridParams &g, const StepState *st, const double *Uin
   const int bs = 256;
   const int rows = slab_rows(g, 34, g.jsize);
   dim3 grid(cdiv((long long)g.isize * rows, bs), k1 - k0, cdiv(g.jsize, rows));
-  k_update<<<grid, bs, 0, s>>>(g, st, Uin, Uout, Fx, Fy, Fz, EMF, k0, rows);
+  static const int minb = getenv("PPK_UPDATE_MINB") ? atoi(getenv("PPK_UPDATE_MINB")) : 0;
+  if (minb == 6) k_update<6><<<grid, bs, 0, s>>>(g, st, Uin, Uout, Fx, Fy, Fz, EMF, k0, rows);
+  else if (minb == 5) k_update<5><<<grid, bs, 0, s>>>(g, st, Uin, Uout, Fx, Fy, Fz, EMF, k0, rows);
+  else k_update<0><<<grid, bs, 0, s>>>(g, st, Uin, Uout, Fx, Fy, Fz, EMF, k0, rows);
 }
 static void l_consume(const GridParams &g, const StepState *st, const double *BASIS, const double *DBF, const double *Uin,
                       double *Uout, int split, cudaStream_t s) {

@@ -14,7 +14,7 @@ OBJ = os.path.join(ROOT, "ppkmhd_b200", "_build", "kernels_fast.o")
 STEP = {  # kernel-name regex -> launches per step
     r"k_prim_dt": 1, r"k_elec_dbf": 1, r"k_traceILi4": 1,
     r"k_flux_tmaILi0ELb0ELi4": 1, r"k_flux_tmaILi1ELb0ELi4": 1, r"k_flux_tmaILi2ELb0ELi4": 1,
-    r"k_emf_tmaILi0ELb0": 1, r"k_emf_tmaILi1ELb0": 1, r"k_emf_tmaILi2ELb0": 1, r"8k_updateE": 1,
+    r"k_emf_tmaILi0ELb0": 1, r"k_emf_tmaILi1ELb0": 1, r"k_emf_tmaILi2ELb0": 1, r"8k_updateILi0": 1,
 }
 sass = subprocess.run(["cuobjdump", "-sass", OBJ], capture_output=True, text=True, check=True).stdout
 stats, name = {}, None
