@@ -71,16 +71,19 @@ def test_fast_mode_within_1e12_of_reference(case, pipeline):
     s.close()
 
 
-@pytest.mark.parametrize("problem,n,extra,bounds,cfl", [
-    ("orszag_tang", (48, 40, 36), OT, None, 0.8),
-    ("orszag_tang", (64, 36, 40), OT, None, 0.8),  # nx a multiple of 32 + periodic x: the wrapped face / edge column
-    ("blast", (40, 40, 40), BLAST, None, 0.8),
-    ("field_loop", (64, 32, 32), "[FieldLoop]\nradius=0.3\namplitude=0.001\nvflow=3\ndensity_in=1\n", (-1, 1, -0.5, 0.5, -0.5, 0.5), 0.4),
+@pytest.mark.parametrize("problem,n,extra,bounds,cfl,bc", [
+    ("orszag_tang", (48, 40, 36), OT, None, 0.8, 3),
+    ("orszag_tang", (64, 36, 40), OT, None, 0.8, 3),  # nx a multiple of 32 + periodic x: the wrapped face / edge column
+    ("blast", (40, 40, 40), BLAST, None, 0.8, 3),
+    ("field_loop", (64, 32, 32), "[FieldLoop]\nradius=0.3\namplitude=0.001\nvflow=3\ndensity_in=1\n", (-1, 1, -0.5, 0.5, -0.5, 0.5), 0.4, 3),
+    # TMA-sized tiles with non-periodic faces: the left-over x column goes through the plain-load kernels (no wrap)
+    ("blast", (64, 36, 34), BLAST, None, 0.8, [1, 2, 2, 1, 3, 3]),
+    ("implode", (32, 40, 36), "[implode]\nBx_outer=0.3\nBy_inner=0.2\n", None, 0.8, 1),
 ])
-def test_exact_mode_vs_oracle_with_intermediates(problem, n, extra, bounds, cfl, oracle_mod):
+def test_exact_mode_vs_oracle_with_intermediates(problem, n, extra, bounds, cfl, bc, oracle_mod):
     """Larger grids than the fixtures, against the C oracle, including every intermediate array."""
     O = oracle_mod
-    ini = O.make_ini(problem, n, nstepmax=4, extra=extra, bounds=bounds, cfl=cfl, tend=10.0)
+    ini = O.make_ini(problem, n, nstepmax=4, extra=extra, bounds=bounds, cfl=cfl, tend=10.0, bc=bc)
     orc = O.Oracle(ini)
     s, _ = make_solver(ini, exact=True, pipeline="unfused")   # the pipeline that stores Fluxes_* and Emf
     f, _ = make_solver(ini, exact=True, pipeline="fused")
