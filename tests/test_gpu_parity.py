@@ -339,8 +339,8 @@ def _slab_worker(rank, world, port, ini, nsteps, exact, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_z_slabs_bit_identical_to_single_gpu(tmp_path, world):
+@pytest.mark.parametrize("world,nxy,nzl", [(2, (24, 20), 12), (4, (24, 20), 12), (2, (64, 36), 16)])
+def test_z_slabs_bit_identical_to_single_gpu(tmp_path, world, nxy, nzl):
     """Decomposition invariance: N z-slabs over NCCL == the undecomposed run, bit for bit, dt included."""
     import socket
 
@@ -351,10 +351,11 @@ def test_z_slabs_bit_identical_to_single_gpu(tmp_path, world):
         pytest.skip(f"needs {world} GPUs")
     from oracle import oracle as O  # ini text helper only
 
-    nsteps, nzl = 6, 12
+    # (64, 36): TMA-staged tiles, the wrapped x column and the early halo exchange in the decomposed run
+    nsteps = 6
     kw = dict(nstepmax=nsteps, extra="[OrszagTang]\nkt=0.5\n", tend=10.0)
-    ini_n = O.make_ini("orszag_tang", (24, 20, nzl), mz=world, **kw)
-    ini_1 = O.make_ini("orszag_tang", (24, 20, nzl * world), **kw)
+    ini_n = O.make_ini("orszag_tang", (*nxy, nzl), mz=world, **kw)
+    ini_1 = O.make_ini("orszag_tang", (*nxy, nzl * world), **kw)
     sock = socket.socket()
     sock.bind(("127.0.0.1", 0))
     port = sock.getsockname()[1]
