@@ -1118,6 +1118,9 @@ DEV void mbar_wait(unsigned long long *bar, unsigned parity) {
     "DONE:\n"
     "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+DEV void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 DEV void tma_load_box(double *dst, const CUtensorMap *map, int x, int y, int z, int comp, unsigned long long *bar) {
   asm volatile(
     "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
@@ -1584,7 +1587,7 @@ struct HydroSmem {
   double fy[SHY + 1][5][32];                               // y-face fluxes of rows j0 .. j0+SHY
   double xcol[SHY][7];                                     // qm_x of the last cell of each row (left state, far x-face)
   double fxx[SHY][5];                                      // far x-face fluxes
-  int fxx_plane;                                           // last plane whose far x-face fluxes are in fxx
+  unsigned long long fxx_bar;                              // mbarrier: one phase per plane, completed by the extra warp
 };
 
 template <int MAXREG>
@@ -1593,7 +1596,6 @@ __global__ void __launch_bounds__(SH_THREADS) __maxnreg__(MAXREG)
           const double *__restrict__ Uin, double *__restrict__ Uout, const int zchunk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   HydroSmem &S = *reinterpret_cast<HydroSmem *>(smem_raw);
-  volatile int *fxx_plane = &S.fxx_plane;
 
   const int gw = g.gw;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -1614,7 +1616,7 @@ __global__ void __launch_bounds__(SH_THREADS) __maxnreg__(MAXREG)
   const bool ex_ok = !main_warp && lane < SHY && i0 + 32 <= ie && j0 + lane < je;
   long long c = cidx(g, i, j, k0);                               // tile warps: own cell; extra warp: far-row cell
   long long cx = cidx(g, i0 + 32, j0 + (lane & (SHY - 1)), k0);  // extra warp: far-column cell
-  if (tid == 0) *fxx_plane = k0 - 1;
+  if (tid == 0) mbar_init(&S.fxx_bar, 1);  // (visible to the CTA after barrier (1) of the first plane)
 
   if (main_warp) {  // prologue: left state of the lowest z-face
     double qm[7], qp[7];
@@ -1717,10 +1719,9 @@ __global__ void __launch_bounds__(SH_THREADS) __maxnreg__(MAXREG)
 #pragma unroll
       for (int v = 0; v < 5; ++v) fh[v] = __shfl_down_sync(0xffffffffu, f[v], 1);
       if (lane == 31) {  // the far x-face comes from the extra warp, which solved it while this warp did its own
-        while (*fxx_plane < k) {}
-        __threadfence_block();
+        mbar_wait(&S.fxx_bar, (unsigned)(k - k0) & 1u);
 #pragma unroll
-        for (int v = 0; v < 5; ++v) fh[v] = ((volatile double *)&S.fxx[w][0])[v];
+        for (int v = 0; v < 5; ++v) fh[v] = S.fxx[w][v];
       }
       // x faces: (rho,E,mx,my,mz) <- (0,1,2,3,4)
       u[0] += f[0] * dtdx; u[1] += f[1] * dtdx; u[2] += f[2] * dtdx; u[3] += f[3] * dtdx; u[4] += f[4] * dtdx;
@@ -1730,9 +1731,8 @@ __global__ void __launch_bounds__(SH_THREADS) __maxnreg__(MAXREG)
 #pragma unroll
         for (int v = 0; v < 5; ++v) S.fxx[lane][v] = f[v];
       }
-      __threadfence_block();
       __syncwarp();
-      if (lane == 0) *fxx_plane = k;
+      if (lane == 0) mbar_arrive(&S.fxx_bar);  // release: the fluxes above are visible to whoever observes the phase
     }
     // ---- y faces ----
     if (main_warp) {
