@@ -845,7 +845,9 @@ __global__ void __launch_bounds__(256, MINB) k_elec_dbf(const GridParams g, cons
 // Writes the 32-number basis on [2,size-2)^3 (the cells whose states a face or an edge consumes).
 // (Measured alternative: accumulating the source terms direction by direction -- same summation order, 80-96 registers,
 // 5-6 CTAs/SM, no spills -- is SLOWER, 1.59-1.76 ms against 1.42 ms: three dependent load phases with the slope stores
-// between them lose more than the occupancy gains. One load burst at 128 registers stays.)
+// between them lose more than the occupancy gains. Hoisting the face-field block (15 loads, 3 stores) to the top of the
+// kernel, to remove the last dependent load phase the profile shows, is slower too (1.77 ms). One load burst at 128
+// registers in this source order stays.)
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_trace(const GridParams g, const StepState *__restrict__ stp,
                                                      const double *__restrict__ U, const double *__restrict__ Q,
