@@ -66,6 +66,12 @@ def lib():
         _lib.orc_init_kelvin_helmholtz.argtypes = [pp] + [C.c_double] * 5 + [C.c_int, C.c_double, C.c_double, C.c_int, dp]
         _lib.orc_init_rotor.argtypes = [pp] + [C.c_double] * 5 + [dp]
         _lib.orc_init_wave.argtypes = [pp, C.c_double, C.c_int, dp]
+        # 2-D path (mhd2d_oracle.c)
+        _lib.orc2d_params_finalize.argtypes = [pp]
+        _lib.orc2d_init_orszag_tang.argtypes = [pp, dp]
+        _lib.orc2d_make_boundaries.argtypes = [pp, dp]
+        _lib.orc2d_step.restype = C.c_double
+        _lib.orc2d_step.argtypes = [pp, dp, dp, dp, C.c_double, C.c_double]
         _lib.orc_make_boundary.argtypes = [pp, dp, C.c_int]
         _lib.orc_make_boundaries.argtypes = [pp, dp]
         _lib.orc_convert_to_primitives.argtypes = [pp, dp, dp]
@@ -300,6 +306,62 @@ class Oracle:
         return sums, m.value
 
 
+class Oracle2D:
+    """The 2-D path (MHD_Muscl_2D, implementationVersion 0): oracle only, no CUDA counterpart yet.
+    Arrays are (8, jsize, isize)."""
+
+    def __init__(self, ini_text: str):
+        cfg = self.cfg = Config(ini_text)
+        p = self.p = OrcParams()
+        p.nx, p.ny, p.nz, p.gw = cfg.i("mesh", "nx", 1), cfg.i("mesh", "ny", 1), 1, 3
+        p.xmin, p.ymin, p.zmin = (cfg.f("mesh", k, 0.0) for k in ("xmin", "ymin", "zmin"))
+        p.xmax, p.ymax, p.zmax = (cfg.f("mesh", k, 1.0) for k in ("xmax", "ymax", "zmax"))
+        p.mx = p.my = p.mz = 1
+        for f, nm in enumerate(("xmin", "xmax", "ymin", "ymax")):
+            p.bc[f] = cfg.i("mesh", "boundary_type_" + nm, 1)
+        p.gamma0, p.cfl = cfg.f("hydro", "gamma0", 1.4), cfg.f("hydro", "cfl", 0.5)
+        p.slope_type = cfg.f("hydro", "slope_type", 1.0)
+        p.smallc, p.smallr = cfg.f("hydro", "smallc", 1e-10), cfg.f("hydro", "smallr", 1e-10)
+        p.riemann = {"approx": 0, "llf": 1, "hll": 2, "hllc": 3, "hlld": 4}.get(cfg.s("hydro", "riemann", "approx"), 0)
+        lib().orc2d_params_finalize(C.byref(p))
+        self.t_end = cfg.f("run", "tEnd", 0.0)
+        self.nstepmax = cfg.i("run", "nstepmax", 1000)
+        self.t, self.iteration, self.dt = 0.0, 0, self.t_end
+        self.U = np.zeros((8, p.jsize, p.isize))
+        problem = cfg.s("hydro", "problem", "unknown")
+        if problem != "orszag_tang":
+            raise ValueError("the 2-D oracle has the Orszag-Tang initial condition only")
+        lib().orc2d_init_orszag_tang(C.byref(p), _dp(self.U))
+        lib().orc2d_make_boundaries(C.byref(p), _dp(self.U))  # constructor sequence, SolverMHDMuscl.h:390-402
+        self.U2 = self.U.copy()
+        self.Q = np.zeros_like(self.U)
+
+    @property
+    def current(self):
+        return self.U if self.iteration % 2 == 0 else self.U2
+
+    def finished(self):
+        return self.t >= (self.t_end - 1e-14) or self.iteration >= self.nstepmax
+
+    def step(self):
+        a, b = (self.U, self.U2) if self.iteration % 2 == 0 else (self.U2, self.U)
+        self.dt = lib().orc2d_step(C.byref(self.p), _dp(a), _dp(b), _dp(self.Q), self.t, self.t_end)
+        self.iteration += 1
+        self.t += self.dt
+        return self.dt
+
+    def run(self, nsteps=None):
+        n = 0
+        while not self.finished() and (nsteps is None or n < nsteps):
+            self.step()
+            n += 1
+        return self
+
+    def interior(self):
+        g = self.p.gw
+        return self.current[:, g:-g, g:-g]
+
+
 # ---------------------------------------------------------------------------------------------
 # reference binary + VTI
 # ---------------------------------------------------------------------------------------------
@@ -311,6 +373,7 @@ def read_vti(path: str) -> np.ndarray:
     header = blob[:head_end].decode()
     ext = re.search(r'WholeExtent="0 (\d+) 0 (\d+) 0 (\d+)"', header)
     nx, ny, nz = (int(ext.group(i)) for i in (1, 2, 3))
+    nz = max(nz, 1)  # 2-D files carry "0 nx 0 ny 0 0"
     names = re.findall(r'Name="([^"]+)"', header)
     pos = blob.index(b"_", head_end) + 1
     out = {}
