@@ -169,6 +169,26 @@ int ppk_selftest_fastmath(int n, const double *x_host, double *rcp_out, double *
 const char *ppk_last_error_string(void);
 const char *ppk_version_string(void);
 
+/* ---- 2-D path: SolverMHDMuscl<2> registered as "MHD_Muscl_2D" (src/shared/SolverFactory.cpp:26-30) ------------------------
+ * One step = SolverMHDMuscl<2>::godunov_unsplit_impl, implementationVersion 0 (src/muscl/SolverMHDMuscl.cpp:373-417):
+ * make_boundaries, deep_copy, ConvertToPrimitivesFunctor2D_MHD, ComputeDtFunctor2D_MHD + SolverBase::compute_dt,
+ * ComputeTraceFunctor2D_MHD, ComputeFluxesAndStoreFunctor2D_MHD, ComputeEmfAndStoreFunctor2D, UpdateFunctor2D_MHD,
+ * UpdateEmfFunctor2D (src/muscl/MHDRunFunctors2D.h), then ++m_iteration, m_t += m_dt. Single GPU. The parameter block is
+ * the 3-D one; nz, dz, the z bounds and the z faces are ignored. Arrays are u[var][j][i] with ghosts:
+ * 8 * (ny+6) * (nx+6) doubles. Same status codes and error string as the 3-D entry points. */
+typedef struct ppk_mhd2d ppk_mhd2d;
+int ppk_mhd2d_create(const ppk_mhd3d_params *params, ppk_mhd2d **handle);
+int ppk_mhd2d_destroy(ppk_mhd2d *handle);
+int ppk_mhd2d_upload(ppk_mhd2d *handle, const double *u_host);
+int ppk_mhd2d_download(ppk_mhd2d *handle, double *u_host);
+int ppk_mhd2d_set_time(ppk_mhd2d *handle, double t, double t_end, long iteration);
+int ppk_mhd2d_get_time(ppk_mhd2d *handle, double *t, double *dt, long *iteration);
+int ppk_mhd2d_make_boundaries(ppk_mhd2d *handle);
+int ppk_mhd2d_step(ppk_mhd2d *handle);
+int ppk_mhd2d_run(ppk_mhd2d *handle, int nsteps);
+int ppk_mhd2d_synchronize(ppk_mhd2d *handle);
+long ppk_mhd2d_launch_count(ppk_mhd2d *handle);
+
 #ifdef __cplusplus
 }
 #endif

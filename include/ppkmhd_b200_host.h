@@ -20,9 +20,14 @@ extern "C" {
  * nStepmax. */
 int ppk_params_from_ini(const char *ini_text, int rank_z, ppk_mhd3d_params *params, double *t_end, int *nstepmax);
 
-/* Evaluate the initial condition selected by [hydro] problem on the host (orszag_tang, blast, field_loop;
- * anything else falls back to orszag_tang like the reference) into u_host (8*isize*jsize*ksize doubles). */
+/* Evaluate the initial condition selected by [hydro] problem on the host (orszag_tang, blast, field_loop, implode,
+ * kelvin_helmholtz, rotor, wave: SolverMHDMuscl<3>::init, src/muscl/SolverMHDMuscl.h:653-713; anything else falls back
+ * to orszag_tang like the reference) into u_host (8*isize*jsize*ksize doubles). */
 int ppk_init_condition_from_ini(const char *ini_text, int rank_z, double *u_host);
+
+/* 2-D path ([run] solver_name=MHD_Muscl_2D): InitOrszagTangFunctor2D (src/muscl/MHDInitFunctors2D.h:241-385) into
+ * u_host (8*isize*jsize doubles). PPK_ERR_UNSUPPORTED for another [hydro] problem (the other 2-D problems are not built). */
+int ppk_init_condition_2d_from_ini(const char *ini_text, double *u_host);
 
 /* The whole program of src/main.cpp: read the ini file, create the solver through SolverFactory, run the
  * time loop, write VTK output, print the monitoring table. rank < 0: take RANK / WORLD_SIZE from the env. */

@@ -3,6 +3,7 @@ solver interface.  The product is the C-ABI shared library (include/ppkmhd_b200.
 layer in ppkmhd_b200/host/; this Python package is only a thin ctypes binding used by the tests and
 bench.py.  It never imports oracle/ and has no CPU fallback."""
 from .capi import (  # noqa: F401
+    Mhd2d,
     Mhd3d,
     Params,
     PpkError,
@@ -10,6 +11,7 @@ from .capi import (  # noqa: F401
     halo_plan,
     selftest_fastmath,
     init_condition_from_ini,
+    init_condition_2d_from_ini,
     lib_path,
     load_library,
     nccl_unique_id,
@@ -17,6 +19,6 @@ from .capi import (  # noqa: F401
 )
 
 __all__ = [
-    "Mhd3d", "Params", "PpkError", "lib_path", "load_library", "build_library",
-    "params_from_ini", "init_condition_from_ini", "nccl_unique_id", "halo_plan", "selftest_fastmath",
+    "Mhd3d", "Mhd2d", "Params", "PpkError", "lib_path", "load_library", "build_library",
+    "params_from_ini", "init_condition_from_ini", "init_condition_2d_from_ini", "nccl_unique_id", "halo_plan", "selftest_fastmath",
 ]

@@ -65,7 +65,9 @@ EXPORTS = [
     "ppk_mhd3d_set_stream", "ppk_mhd3d_profile", "ppk_mhd3d_kernel_times", "ppk_mhd3d_launch_count",
     "ppk_mhd3d_debug_array", "ppk_mhd3d_device_bytes", "ppk_last_error_string", "ppk_version_string",
     "ppk_mhd3d_halo_plan", "ppk_selftest_fastmath", "ppk_mhd3d_set_pipeline",
-    "ppk_params_from_ini", "ppk_init_condition_from_ini", "ppk_run_ini",
+    "ppk_params_from_ini", "ppk_init_condition_from_ini", "ppk_run_ini", "ppk_init_condition_2d_from_ini",
+    "ppk_mhd2d_create", "ppk_mhd2d_destroy", "ppk_mhd2d_upload", "ppk_mhd2d_download", "ppk_mhd2d_set_time", "ppk_mhd2d_get_time",
+    "ppk_mhd2d_make_boundaries", "ppk_mhd2d_step", "ppk_mhd2d_run", "ppk_mhd2d_synchronize", "ppk_mhd2d_launch_count",
 ]
 
 
@@ -110,6 +112,17 @@ def load_library():
     L.ppk_params_from_ini.argtypes = [C.c_char_p, C.c_int, C.POINTER(Params), dp, ip]
     L.ppk_init_condition_from_ini.argtypes = [C.c_char_p, C.c_int, vp]
     L.ppk_run_ini.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    L.ppk_init_condition_2d_from_ini.argtypes = [C.c_char_p, vp]
+    L.ppk_mhd2d_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    for name in ("destroy", "make_boundaries", "step", "synchronize"):
+        getattr(L, "ppk_mhd2d_" + name).argtypes = [vp]
+    L.ppk_mhd2d_upload.argtypes = [vp, vp]
+    L.ppk_mhd2d_download.argtypes = [vp, vp]
+    L.ppk_mhd2d_set_time.argtypes = [vp, C.c_double, C.c_double, C.c_long]
+    L.ppk_mhd2d_get_time.argtypes = [vp, dp, dp, C.POINTER(C.c_long)]
+    L.ppk_mhd2d_run.argtypes = [vp, C.c_int]
+    L.ppk_mhd2d_launch_count.argtypes = [vp]
+    L.ppk_mhd2d_launch_count.restype = C.c_long
     _lib = L
     return L
 
@@ -138,6 +151,66 @@ def init_condition_from_ini(ini_text: str, rank_z: int = 0) -> np.ndarray:
     U = np.zeros(p.shape, dtype=np.float64)
     _check(L.ppk_init_condition_from_ini(ini_text.encode(), rank_z, U.ctypes.data))
     return U
+
+
+def init_condition_2d_from_ini(ini_text: str) -> np.ndarray:
+    """Host-side Orszag-Tang initial condition of the 2-D path: (8, jsize, isize)."""
+    L = load_library()
+    p, _, _ = params_from_ini(ini_text)
+    U = np.zeros((8, p.ny + 6, p.nx + 6), dtype=np.float64)
+    _check(L.ppk_init_condition_2d_from_ini(ini_text.encode(), U.ctypes.data))
+    return U
+
+
+class Mhd2d:
+    """The 2-D MHD solver (a ppk_mhd2d handle): MHD_Muscl_2D, implementationVersion 0, single GPU."""
+
+    def __init__(self, params: Params):
+        self.L = load_library()
+        self.params = params
+        self.shape = (8, params.ny + 6, params.nx + 6)
+        self.h = C.c_void_p()
+        _check(self.L.ppk_mhd2d_create(C.byref(params), C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ppk_mhd2d_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, U: np.ndarray):
+        assert U.dtype == np.float64 and U.flags["C_CONTIGUOUS"] and U.shape == self.shape
+        _check(self.L.ppk_mhd2d_upload(self.h, U.ctypes.data))
+
+    def download(self) -> np.ndarray:
+        out = np.empty(self.shape, dtype=np.float64)
+        _check(self.L.ppk_mhd2d_download(self.h, out.ctypes.data))
+        return out
+
+    def interior(self) -> np.ndarray:
+        return self.download()[:, 3:-3, 3:-3]
+
+    def set_time(self, t, t_end, iteration=0):
+        _check(self.L.ppk_mhd2d_set_time(self.h, t, t_end, iteration))
+
+    def get_time(self):
+        t, dt, it = C.c_double(0), C.c_double(0), C.c_long(0)
+        _check(self.L.ppk_mhd2d_get_time(self.h, C.byref(t), C.byref(dt), C.byref(it)))
+        return t.value, dt.value, it.value
+
+    def step(self):
+        _check(self.L.ppk_mhd2d_step(self.h))
+
+    def run(self, nsteps):
+        _check(self.L.ppk_mhd2d_run(self.h, nsteps))
+
+    def launch_count(self):
+        return self.L.ppk_mhd2d_launch_count(self.h)
 
 
 class Mhd3d:

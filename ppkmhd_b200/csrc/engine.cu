@@ -552,6 +552,172 @@ int ppk_mhd3d_diagnostics(ppk_mhd3d *h, double sums[8], double *max_divb) {
   return 0;
 }
 
+// =================================================================================================
+// 2-D path (MHD_Muscl_2D, implementationVersion 0): SolverMHDMuscl<2>::godunov_unsplit_impl
+// (src/muscl/SolverMHDMuscl.cpp:373-417) as boundary x, boundary y, primitives + CFL, dt, trace, fluxes + EMF, update
+// =================================================================================================
+struct ppk_mhd2d {
+  GridParams g{};
+  const KernelTable *kt = nullptr;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  double *U[2] = {nullptr, nullptr}, *Q = nullptr, *S = nullptr, *FX = nullptr, *FY = nullptr, *EMF = nullptr;
+  StepState *st = nullptr;
+  long launches = 0, host_iteration = 0;
+  double *cur() { return U[host_iteration & 1]; }
+  double *nxt() { return U[(host_iteration + 1) & 1]; }
+};
+
+int ppk_mhd2d_create(const ppk_mhd3d_params *p, ppk_mhd2d **out) {
+  if (!p || !out) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  if (p->ghost_width != PPK_GHOST_WIDTH) return fail(PPK_ERR_UNSUPPORTED, "ghost_width must be 3 (MHD_Muscl_2D)");
+  if (p->riemann_solver != PPK_RIEMANN_HLLD && p->riemann_solver != PPK_RIEMANN_HLL && p->riemann_solver != PPK_RIEMANN_LLF)
+    return fail(PPK_ERR_UNSUPPORTED, "riemann must be hlld, hll or llf");
+  if (p->implementation_version != 0 && p->implementation_version != 1)
+    return fail(PPK_ERR_UNSUPPORTED, "implementationVersion must be 0 or 1 in 2-D (the reference's v2 is a different formulation)");
+  if (p->mx != 1 || p->my != 1) return fail(PPK_ERR_UNSUPPORTED, "the 2-D path is single-GPU (mx = my = 1)");
+  if (p->nx < 3 || p->ny < 3) return fail(PPK_ERR_INVALID_ARGUMENT, "nx, ny must be >= 3 (ghost width)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(PPK_ERR_NO_DEVICE, "no CUDA device: ppkmhd_b200 has no CPU fallback");
+  if (p->device < 0 || p->device >= ndev) return fail(PPK_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+  ppk_mhd2d *h = new ppk_mhd2d();
+  h->device = p->device;
+  h->kt = p->exact_arithmetic ? kernel_table_exact() : kernel_table_fast();
+  GridParams &g = h->g;
+  g.nx = p->nx; g.ny = p->ny; g.nz = 1; g.gw = p->ghost_width;
+  g.isize = p->nx + 2 * g.gw; g.jsize = p->ny + 2 * g.gw; g.ksize = 1;
+  g.ncell = (long long)g.isize * g.jsize;
+  g.dx = p->dx; g.dy = p->dy; g.dz = 1.0;
+  g.idx = 1.0 / p->dx; g.idy = 1.0 / p->dy; g.idz = 1.0;
+  g.gamma0 = p->gamma0; g.cfl = p->cfl; g.slope_type = p->slope_type;
+  g.smallr = p->smallr; g.smallc = p->smallc; g.smallp = p->smallp;
+  g.riemann = p->riemann_solver;
+  g.wrap_x = 0;
+  for (int f = 0; f < 6; ++f) g.bc[f] = p->boundary_type[f];
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  const size_t n = (size_t)g.ncell * sizeof(double);
+  for (double **a : {&h->U[0], &h->U[1], &h->Q}) {
+    CUDA_TRY(cudaMalloc((void **)a, NBVAR * n));
+    CUDA_TRY(cudaMemsetAsync(*a, 0, NBVAR * n, h->stream));
+  }
+  CUDA_TRY(cudaMalloc((void **)&h->S, 8 * NBVAR * n));
+  CUDA_TRY(cudaMemsetAsync(h->S, 0, 8 * NBVAR * n, h->stream));
+  CUDA_TRY(cudaMalloc((void **)&h->FX, 6 * n));
+  CUDA_TRY(cudaMalloc((void **)&h->FY, 6 * n));
+  CUDA_TRY(cudaMalloc((void **)&h->EMF, n));
+  CUDA_TRY(cudaMemsetAsync(h->FX, 0, 6 * n, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->FY, 0, 6 * n, h->stream));
+  CUDA_TRY(cudaMemsetAsync(h->EMF, 0, n, h->stream));
+  CUDA_TRY(cudaMalloc((void **)&h->st, sizeof(StepState)));
+  StepState st0{};
+  st0.t_end = 1e300;
+  CUDA_TRY(cudaMemcpyAsync(h->st, &st0, sizeof(st0), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return 0;
+}
+
+int ppk_mhd2d_destroy(ppk_mhd2d *h) {
+  if (!h) return 0;
+  DeviceGuard guard(h->device);
+  cudaDeviceSynchronize();
+  for (double *p : {h->U[0], h->U[1], h->Q, h->S, h->FX, h->FY, h->EMF})
+    if (p) cudaFree(p);
+  if (h->st) cudaFree(h->st);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int ppk_mhd2d_upload(ppk_mhd2d *h, const double *u_host) {
+  if (!h || !u_host) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaMemcpyAsync(h->cur(), u_host, (size_t)NBVAR * h->g.ncell * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int ppk_mhd2d_download(ppk_mhd2d *h, double *u_host) {
+  if (!h || !u_host) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaMemcpyAsync(u_host, h->cur(), (size_t)NBVAR * h->g.ncell * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int ppk_mhd2d_set_time(ppk_mhd2d *h, double t, double t_end, long iteration) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  DeviceGuard guard(h->device);
+  if (((iteration ^ h->host_iteration) & 1) != 0) std::swap(h->U[0], h->U[1]);
+  StepState st{};
+  st.t = t; st.t_end = t_end; st.iteration = iteration;
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaMemcpy(h->st, &st, sizeof(st), cudaMemcpyHostToDevice));
+  h->host_iteration = iteration;
+  return 0;
+}
+
+int ppk_mhd2d_get_time(ppk_mhd2d *h, double *t, double *dt, long *iteration) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  DeviceGuard guard(h->device);
+  StepState st{};
+  CUDA_TRY(cudaMemcpyAsync(&st, h->st, sizeof(st), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (t) *t = st.t;
+  if (dt) *dt = st.dt;
+  if (iteration) *iteration = (long)st.iteration;
+  return 0;
+}
+
+int ppk_mhd2d_make_boundaries(ppk_mhd2d *h) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  DeviceGuard guard(h->device);
+  h->kt->boundary2d(h->g, h->cur(), 0, h->stream);
+  h->kt->boundary2d(h->g, h->cur(), 1, h->stream);
+  h->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int ppk_mhd2d_step(ppk_mhd2d *h) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  DeviceGuard guard(h->device);
+  const GridParams &g = h->g;
+  cudaStream_t s = h->stream;
+  double *Uin = h->cur(), *Uout = h->nxt();
+  h->kt->boundary2d(g, Uin, 0, s);
+  h->kt->boundary2d(g, Uin, 1, s);
+  h->kt->prim_dt2d(g, Uin, h->Q, h->st, s);
+  h->kt->finalize_dt(g, h->st, s);
+  h->kt->trace2d(g, h->st, Uin, h->Q, h->S, s);
+  h->kt->flux_emf2d(g, h->S, h->FX, h->FY, h->EMF, s);
+  h->kt->update2d(g, h->st, Uin, Uout, h->FX, h->FY, h->EMF, s);
+  h->kt->advance_time(h->st, s);
+  h->launches += 8;
+  h->host_iteration += 1;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int ppk_mhd2d_run(ppk_mhd2d *h, int nsteps) {
+  for (int s = 0; s < nsteps; ++s)
+    if (int rc = ppk_mhd2d_step(h)) return rc;
+  return 0;
+}
+
+int ppk_mhd2d_synchronize(ppk_mhd2d *h) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  DeviceGuard guard(h->device);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+long ppk_mhd2d_launch_count(ppk_mhd2d *h) { return h ? h->launches : 0; }
+
 int ppk_mhd3d_halo_plan(const ppk_mhd3d_params *p, int capacity, ppk_halo_msg *msgs) {
   if (!p || (capacity > 0 && !msgs)) return -1;
   if (p->mz <= 1) return 0;

@@ -84,6 +84,14 @@ struct KernelTable {
   void (*update_ct)(const GridParams &g, const StepState *st, const double *Uin, double *Uout, const double *EMF, cudaStream_t s);
   // A[comp][.., i = nx+gw] <- A[comp][.., i = gw] when x is periodic (debug arrays only)
   void (*wrap_x_column)(const GridParams &g, double *A, int ncomp, cudaStream_t s);
+  // 2-D path (MHD_Muscl_2D, v0): mhd2d_kernels.inc. S = the 8 state arrays of the trace (64 numbers per cell),
+  // FX / FY = 6 flux components per face, EMF = 1 number per corner
+  void (*boundary2d)(const GridParams &g, double *U, int dir, cudaStream_t s);
+  void (*prim_dt2d)(const GridParams &g, const double *U, double *Q, StepState *st, cudaStream_t s);
+  void (*trace2d)(const GridParams &g, const StepState *st, const double *U, const double *Q, double *S, cudaStream_t s);
+  void (*flux_emf2d)(const GridParams &g, const double *S, double *FX, double *FY, double *EMF, cudaStream_t s);
+  void (*update2d)(const GridParams &g, const StepState *st, const double *Uin, double *Uout, const double *FX,
+                   const double *FY, const double *EMF, cudaStream_t s);
 };
 
 const KernelTable *kernel_table_exact();

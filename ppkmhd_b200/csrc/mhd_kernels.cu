@@ -138,7 +138,8 @@ DEV double clamp_hi0(double x) {
 // inside the 1e-12 per-cell tolerance (tests/test_gpu_parity.py::test_fast_mode_*).
 DEV void riemann_hlld_fast(double gamma0, double rl, double pl, double ul, double vl, double wl, double al, double bl,
                            double cl, double rr, double pr, double ur, double vr, double wr, double ar, double br,
-                           double cr, double &f_d, double &f_p, double &f_u, double &f_v, double &f_w) {
+                           double cr, double &f_d, double &f_p, double &f_u, double &f_v, double &f_w,
+                           double *f_bz = nullptr) {
   const double entho = frcp(gamma0 - 1.0);
   const double a = 0.5 * (al + ar);
   const double a2 = a * a;
@@ -238,6 +239,7 @@ DEV void riemann_hlld_fast(double gamma0, double rl, double pl, double ul, doubl
   f_u = ro * uo * uo - a2 + ptoto;
   f_v = ro * uo * vo - a * bo;
   f_w = ro * uo * wo - a * co;
+  if (f_bz) *f_bz = co * uo - a * wo;  // induction flux of the out-of-plane field: the 2-D path only (:366)
 }
 #endif
 
@@ -246,7 +248,7 @@ DEV void riemann_hlld_fast(double gamma0, double rl, double pl, double ul, doubl
 // the reference's flux vector is never used (the field is advanced by the edge EMFs).
 DEV void riemann_hlld(double gamma0, double rl, double pl, double ul, double vl, double wl, double al, double bl,
                       double cl, double rr, double pr, double ur, double vr, double wr, double ar, double br,
-                      double cr, double &f_d, double &f_p, double &f_u, double &f_v, double &f_w) {
+                      double cr, double &f_d, double &f_p, double &f_u, double &f_v, double &f_w, double *f_bz = nullptr) {
   const double entho = 1.0 / (gamma0 - 1.0);
   const double a = 0.5 * (al + ar);
   const double sgnm = (a >= 0) ? 1.0 : -1.0;
@@ -349,6 +351,7 @@ DEV void riemann_hlld(double gamma0, double rl, double pl, double ul, double vl,
   f_u = ro * uo * uo - a * a + ptoto;
   f_v = ro * uo * vo - a * bo;
   f_w = ro * uo * wo - a * co;
+  if (f_bz) *f_bz = co * uo - a * wo;  // flux[IBZ], RiemannSolvers_MHD.h:366 (2-D path only)
 }
 
 // find_mhd_flux (mhd_utils.h:175-231, cIso == 0), hydro part: conservative variables and fluxes of (rho, E, mn, mt1, mt2)
@@ -369,7 +372,8 @@ DEV void mhd_flux5(double gamma0, double d, double p, double u, double v, double
 // riemann_hll (RiemannSolvers_MHD.h:27-69) and riemann_llf (:83-111), hydro fluxes only (the induction components of
 // the flux vector are never read: the field is advanced by the edge EMFs). Same frame as riemann_hlld.
 DEV void riemann_hll(double gamma0, double rl, double pl, double ul, double vl, double wl, double al, double bl, double cl,
-                     double rr, double pr, double ur, double vr, double wr, double ar, double br, double cr, double f[5]) {
+                     double rr, double pr, double ur, double vr, double wr, double ar, double br, double cr, double f[5],
+                     double *f_bz = nullptr) {
   const double a = 0.5 * (al + ar);
   double cl5[5], fl5[5], cr5[5], fr5[5];
   mhd_flux5(gamma0, rl, pl, ul, vl, wl, a, bl, cl, cl5, fl5);
@@ -383,9 +387,12 @@ DEV void riemann_hll(double gamma0, double rl, double pl, double ul, double vl, 
   const double sr = fmax(fmax(ul, ur) + fmax(cfl_, cfr), 0.0);
 #pragma unroll
   for (int v = 0; v < 5; ++v) f[v] = (sr * fl5[v] - sl * fr5[v] + sr * sl * (cr5[v] - cl5[v])) / (sr - sl);
+  // out-of-plane field (2-D path only): conservative variable c, flux c*u - a*w (mhd_utils.h:219, 229)
+  if (f_bz) *f_bz = (sr * (cl * ul - a * wl) - sl * (cr * ur - a * wr) + sr * sl * (cr - cl)) / (sr - sl);
 }
 DEV void riemann_llf(double gamma0, double rl, double pl, double ul, double vl, double wl, double al, double bl, double cl,
-                     double rr, double pr, double ur, double vr, double wr, double ar, double br, double cr, double f[5]) {
+                     double rr, double pr, double ur, double vr, double wr, double ar, double br, double cr, double f[5],
+                     double *f_bz = nullptr) {
   const double a = 0.5 * (al + ar);
   double cl5[5], fl5[5], cr5[5], fr5[5];
   mhd_flux5(gamma0, rl, pl, ul, vl, wl, a, bl, cl, cl5, fl5);
@@ -401,24 +408,29 @@ DEV void riemann_llf(double gamma0, double rl, double pl, double ul, double vl, 
     f[v] = (fl5[v] + fr5[v]) / 2;
     f[v] -= vel_info * (cr5[v] - cl5[v]) / 2;
   }
+  if (f_bz) {
+    double fb = ((cl * ul - a * wl) + (cr * ur - a * wr)) / 2;
+    fb -= vel_info * (cr - cl) / 2;
+    *f_bz = fb;
+  }
 }
 // riemann_mhd (RiemannSolvers_MHD.h:372-392): the solver [hydro] riemann= selects (uniform over the grid).
 // RS >= 0 fixes the solver at compile time (the hot TMA kernels are instantiated for HLLD alone), RS < 0 reads g.riemann.
 template <int RS = -1>
 DEV void riemann_face(const GridParams &g, double rl, double pl, double ul, double vl, double wl, double al, double bl, double cl,
                       double rr, double pr, double ur, double vr, double wr, double ar, double br, double cr, double &f_d,
-                      double &f_p, double &f_u, double &f_v, double &f_w) {
+                      double &f_p, double &f_u, double &f_v, double &f_w, double *f_bz = nullptr) {
   const int rs = RS >= 0 ? RS : g.riemann;
   if (rs == RIEMANN_HLLD) {
 #if PPK_EXACT
-    riemann_hlld(g.gamma0, rl, pl, ul, vl, wl, al, bl, cl, rr, pr, ur, vr, wr, ar, br, cr, f_d, f_p, f_u, f_v, f_w);
+    riemann_hlld(g.gamma0, rl, pl, ul, vl, wl, al, bl, cl, rr, pr, ur, vr, wr, ar, br, cr, f_d, f_p, f_u, f_v, f_w, f_bz);
 #else
-    riemann_hlld_fast(g.gamma0, rl, pl, ul, vl, wl, al, bl, cl, rr, pr, ur, vr, wr, ar, br, cr, f_d, f_p, f_u, f_v, f_w);
+    riemann_hlld_fast(g.gamma0, rl, pl, ul, vl, wl, al, bl, cl, rr, pr, ur, vr, wr, ar, br, cr, f_d, f_p, f_u, f_v, f_w, f_bz);
 #endif
   } else {
     double f[5];
-    if (rs == RIEMANN_HLL) riemann_hll(g.gamma0, rl, pl, ul, vl, wl, al, bl, cl, rr, pr, ur, vr, wr, ar, br, cr, f);
-    else riemann_llf(g.gamma0, rl, pl, ul, vl, wl, al, bl, cl, rr, pr, ur, vr, wr, ar, br, cr, f);
+    if (rs == RIEMANN_HLL) riemann_hll(g.gamma0, rl, pl, ul, vl, wl, al, bl, cl, rr, pr, ur, vr, wr, ar, br, cr, f, f_bz);
+    else riemann_llf(g.gamma0, rl, pl, ul, vl, wl, al, bl, cl, rr, pr, ur, vr, wr, ar, br, cr, f, f_bz);
     f_d = f[0]; f_p = f[1]; f_u = f[2]; f_v = f[3]; f_w = f[4];
   }
 }
@@ -2124,6 +2136,8 @@ static void l_fastmath_selftest(int n, const double *x, double *rcp, double *sq,
   k_fastmath_selftest<<<(n + 255) / 256, 256, 0, s>>>(n, x, rcp, sq, rsq);
 }
 
+#include "mhd2d_kernels.inc"
+
 static const KernelTable table = {
 #if PPK_EXACT
   "exact",
@@ -2131,6 +2145,7 @@ static const KernelTable table = {
   "fast",
 #endif
   l_boundary, l_prim_dt, l_finalize_dt, l_advance_time, l_elec_dbf, l_trace, l_flux, l_emf, l_update, l_diagnostics, l_fastmath_selftest, l_consume, l_tma_create, l_tma_destroy, l_hydro, l_update_ct, l_wrap_x_column,
+  l2_boundary, l2_prim_dt, l2_trace, l2_flux_emf, l2_update,
 };
 
 }  // namespace PPK_NS

@@ -390,6 +390,32 @@ void init_field_loop(const HydroParams &p, const FieldLoopParams &fl, DataArray3
                            U(i, j, k, ID);
 }
 
+void init_orszag_tang_2d(const HydroParams &p, DataArray3dHost &U) {
+  // all variables but the energy on every cell, then the energy from the face-averaged field where both faces exist
+  const CellCoords cc{p};
+  const double twopi = 2 * 3.141592653589793238462643383279502884L;  // TWOPI_F (src/shared/real_type.h)
+  const double gamma0 = p.settings.gamma0;
+  const double B0 = 1.0 / sqrt(2 * twopi), p0 = gamma0 / (2 * twopi), d0 = gamma0 * p0, v0 = 1.0;
+  for (int j = 0; j < p.jsize; ++j)
+    for (int i = 0; i < p.isize; ++i) {
+      const double x = cc.x(i), y = cc.y(j);
+      U(i, j, 0, ID) = d0;
+      U(i, j, 0, IU) = -d0 * v0 * sin(y * twopi);
+      U(i, j, 0, IV) = d0 * v0 * sin(x * twopi);
+      U(i, j, 0, IW) = 0.0;
+      U(i, j, 0, IA) = -B0 * sin(y * twopi);
+      U(i, j, 0, IB) = B0 * sin(2.0 * x * twopi);
+      U(i, j, 0, IC) = 0.0;
+    }
+  const double TwoPi = 4.0 * asin(1.0);
+  const double p0e = gamma0 / (2.0 * TwoPi);
+  for (int j = 0; j < p.jsize - 1; ++j)
+    for (int i = 0; i < p.isize - 1; ++i)
+      U(i, j, 0, IP) = p0e / (gamma0 - 1.0) +
+                       0.5 * (sqr(U(i, j, 0, IU)) / U(i, j, 0, ID) + sqr(U(i, j, 0, IV)) / U(i, j, 0, ID) +
+                              0.25 * sqr(U(i, j, 0, IA) + U(i + 1, j, 0, IA)) + 0.25 * sqr(U(i, j, 0, IB) + U(i, j + 1, 0, IB)));
+}
+
 std::string init_problem(const HydroParams &params, ConfigMap &configMap, const std::string &problem, DataArray3dHost &U) {
   if (problem == "blast") {
     init_blast(params, BlastParams(configMap), U);

@@ -53,6 +53,8 @@ void init_blast(const HydroParams &params, const BlastParams &b, DataArray3dHost
 void init_field_loop(const HydroParams &params, const FieldLoopParams &fl, DataArray3dHost &U);    // MHDInitFunctors3D.h:759-1023
 // SolverMHDMuscl<dim>::init dispatch (SolverMHDMuscl.h:653-713); returns the problem name actually used
 std::string init_problem(const HydroParams &params, ConfigMap &configMap, const std::string &problem, DataArray3dHost &U);
+// 2-D path (MHD_Muscl_2D): U is (isize, jsize, 1, 8). InitOrszagTangFunctor2D, src/muscl/MHDInitFunctors2D.h:241-385
+void init_orszag_tang_2d(const HydroParams &params, DataArray3dHost &U);
 
 class SolverMHDMusclCuda3D : public SolverBase {
 public:

@@ -62,6 +62,17 @@ int ppk_init_condition_from_ini(const char *ini_text, int rank_z, double *u_host
   return 0;
 }
 
+int ppk_init_condition_2d_from_ini(const char *ini_text, double *u_host) {
+  if (!ini_text || !u_host) return PPK_ERR_INVALID_ARGUMENT;
+  ConfigMap cfg(ini_text, (int)strlen(ini_text));
+  HydroParams p = params_for(cfg, 0);
+  if (cfg.getString("hydro", "problem", "unknown") != "orszag_tang") return PPK_ERR_UNSUPPORTED;
+  DataArray3dHost U(p.isize, p.jsize, 1, p.nbvar);
+  init_orszag_tang_2d(p, U);
+  memcpy(u_host, U.data(), U.size() * sizeof(double));
+  return 0;
+}
+
 int ppk_run_ini(const char *ini_path, int rank, int nranks) {
   if (!ini_path) return PPK_ERR_INVALID_ARGUMENT;
   ConfigMap configMap = broadcast_parameters(ini_path);

@@ -99,3 +99,19 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "Mcell-updates/s" and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_initial_condition_2d_bitwise(oracle_mod):
+    """Host-layer Orszag-Tang 2-D initial condition == the reference's step-0 .vti == the 2-D oracle, ghosts included."""
+    g2 = os.path.join(ROOT, "tests", "golden2d")
+    for f in sorted(os.listdir(g2)):
+        if not f.endswith(".npz"):
+            continue
+        g = np.load(os.path.join(g2, f))
+        ini = str(g["ini"])
+        U = ppk.init_condition_2d_from_ini(ini)
+        assert np.array_equal(U[:, 3:-3, 3:-3], g["init"]), f
+        orc = oracle_mod.Oracle2D(ini)
+        Uo = np.zeros_like(U)
+        oracle_mod.lib().orc2d_init_orszag_tang(oracle_mod.C.byref(orc.p), oracle_mod._dp(Uo))
+        assert np.array_equal(U, Uo), f
