@@ -184,6 +184,8 @@ int ppk_mhd2d_download(ppk_mhd2d *handle, double *u_host);
 int ppk_mhd2d_set_time(ppk_mhd2d *handle, double t, double t_end, long iteration);
 int ppk_mhd2d_get_time(ppk_mhd2d *handle, double *t, double *dt, long *iteration);
 int ppk_mhd2d_make_boundaries(ppk_mhd2d *handle);
+/* convertToPrimitives + SolverBase::compute_dt on the current array, as the constructor does (SolverMHDMuscl.h:399-402) */
+int ppk_mhd2d_compute_dt(ppk_mhd2d *handle, double *dt);
 int ppk_mhd2d_step(ppk_mhd2d *handle);
 int ppk_mhd2d_run(ppk_mhd2d *handle, int nsteps);
 int ppk_mhd2d_synchronize(ppk_mhd2d *handle);

@@ -67,7 +67,7 @@ EXPORTS = [
     "ppk_mhd3d_halo_plan", "ppk_selftest_fastmath", "ppk_mhd3d_set_pipeline",
     "ppk_params_from_ini", "ppk_init_condition_from_ini", "ppk_run_ini", "ppk_init_condition_2d_from_ini",
     "ppk_mhd2d_create", "ppk_mhd2d_destroy", "ppk_mhd2d_upload", "ppk_mhd2d_download", "ppk_mhd2d_set_time", "ppk_mhd2d_get_time",
-    "ppk_mhd2d_make_boundaries", "ppk_mhd2d_step", "ppk_mhd2d_run", "ppk_mhd2d_synchronize", "ppk_mhd2d_launch_count",
+    "ppk_mhd2d_make_boundaries", "ppk_mhd2d_compute_dt", "ppk_mhd2d_step", "ppk_mhd2d_run", "ppk_mhd2d_synchronize", "ppk_mhd2d_launch_count",
 ]
 
 
@@ -121,6 +121,7 @@ def load_library():
     L.ppk_mhd2d_set_time.argtypes = [vp, C.c_double, C.c_double, C.c_long]
     L.ppk_mhd2d_get_time.argtypes = [vp, dp, dp, C.POINTER(C.c_long)]
     L.ppk_mhd2d_run.argtypes = [vp, C.c_int]
+    L.ppk_mhd2d_compute_dt.argtypes = [vp, dp]
     L.ppk_mhd2d_launch_count.argtypes = [vp]
     L.ppk_mhd2d_launch_count.restype = C.c_long
     _lib = L

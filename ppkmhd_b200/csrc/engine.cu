@@ -682,6 +682,18 @@ int ppk_mhd2d_make_boundaries(ppk_mhd2d *h) {
   return 0;
 }
 
+int ppk_mhd2d_compute_dt(ppk_mhd2d *h, double *dt) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  DeviceGuard guard(h->device);
+  h->kt->boundary2d(h->g, h->cur(), 0, h->stream);
+  h->kt->boundary2d(h->g, h->cur(), 1, h->stream);
+  h->kt->prim_dt2d(h->g, h->cur(), h->Q, h->st, h->stream);
+  h->kt->finalize_dt(h->g, h->st, h->stream);
+  h->launches += 4;
+  CUDA_TRY(cudaGetLastError());
+  return ppk_mhd2d_get_time(h, nullptr, dt, nullptr);
+}
+
 int ppk_mhd2d_step(ppk_mhd2d *h) {
   if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
   DeviceGuard guard(h->device);

@@ -128,6 +128,61 @@ void save_VTK_3D_slab(const DataArray3dHost &Uhost, HydroParams &params, ConfigM
   write_vti(filename, Uhost, params, ascii, nbvar, variables_names, piece);
 }
 
+// save_VTK_2D (src/utils/io/IO_VTK.cpp:24-206): version "1.0" header also in a serial run, z extent "0 0", spacing "dx dy 0",
+// a blank before the closing quote of the piece extent
+void save_VTK_2D(const DataArray3dHost &U, HydroParams &p, ConfigMap &configMap, int nbvar,
+                 const std::map<int, std::string> &names, int iStep, const std::string &debug_name) {
+  const std::string dir = configMap.getString("output", "outputDir", "./");
+  const std::string prefix = configMap.getString("output", "outputPrefix", "output");
+  const bool ascii = configMap.getBool("output", "outputVtkAscii", false);
+  const std::string filename = debug_name.empty() ? dir + "/" + prefix + "_" + padded(iStep, 7) + ".vti"
+                                                  : dir + "/" + prefix + "_" + debug_name + "_" + padded(iStep, 7) + ".vti";
+  const int gw = p.ghostWidth;
+  std::fstream out(filename.c_str(), std::ios_base::out);
+  if (ascii) out << "<?xml version=\"1.0\"?>\n";
+  out << "<VTKFile type=\"ImageData\" version=\"1.0\" byte_order=\"LittleEndian\" header_type=\"UInt64\">\n";
+  out << "  <ImageData WholeExtent=\"" << 0 << " " << p.nx << " " << 0 << " " << p.ny << " " << 0 << " " << 0 << "\" "
+      << "Origin=\"" << p.xmin << " " << p.ymin << " " << 0 << "\" " << "Spacing=\"" << p.dx << " " << p.dy << " " << 0.0
+      << "\">\n";
+  out << "  <Piece Extent=\"" << 0 << " " << p.nx << " " << 0 << " " << p.ny << " " << 0 << " " << 0 << " " << "\">\n";
+  out << "    <PointData>\n";
+  out << "    </PointData>\n";
+  if (ascii) {
+    out << "    <CellData>\n";
+    for (int v = 0; v < nbvar; ++v) {
+      out << "    <DataArray type=\"Float64\" Name=\"" << names.at(v) << "\" format=\"ascii\" >\n";
+      for (int j = gw; j < p.jsize - gw; ++j)
+        for (int i = gw; i < p.isize - gw; ++i) out << U(i, j, 0, v) << " ";
+      out << "\n    </DataArray>\n";
+    }
+    out << "    </CellData>\n";
+    out << "  </Piece>\n";
+    out << "  </ImageData>\n";
+    out << "</VTKFile>\n";
+    return;
+  }
+  const uint64_t nbytes = (uint64_t)p.nx * p.ny * sizeof(real_t);
+  out << "    <CellData>" << std::endl;
+  for (int v = 0; v < nbvar; ++v)
+    out << "     <DataArray type=\"Float64\" Name=\"" << names.at(v) << "\" format=\"appended\" offset=\""
+        << (uint64_t)v * nbytes + (uint64_t)v * sizeof(uint64_t) << "\" />" << std::endl;
+  out << "    </CellData>" << std::endl;
+  out << "  </Piece>" << std::endl;
+  out << "  </ImageData>" << std::endl;
+  out << "  <AppendedData encoding=\"raw\">" << std::endl;
+  out << "_";
+  for (int v = 0; v < nbvar; ++v) {
+    out.write((const char *)&nbytes, sizeof(uint64_t));
+    for (int j = gw; j < p.jsize - gw; ++j)
+      for (int i = gw; i < p.isize - gw; ++i) {
+        const real_t tmp = U(i, j, 0, v);
+        out.write((const char *)&tmp, sizeof(real_t));
+      }
+  }
+  out << "  </AppendedData>" << std::endl;
+  out << "</VTKFile>" << std::endl;
+}
+
 IO_ReadWrite::IO_ReadWrite(HydroParams &params_, ConfigMap &configMap_, std::map<int, std::string> &names)
   : params(params_), configMap(configMap_), variables_names(names) {
   vtk_enabled = configMap.getBool("output", "vtk_enabled", true);    // IO_ReadWrite.cpp:37
@@ -136,7 +191,8 @@ IO_ReadWrite::IO_ReadWrite(HydroParams &params_, ConfigMap &configMap_, std::map
 
 void IO_ReadWrite::save_data(DataArray3dHost &Uhost, int iStep, real_t /*time*/, const std::string &debug_name) {
   if (vtk_enabled) {
-    if (params.nProcs > 1) save_VTK_3D_slab(Uhost, params, configMap, params.nbvar, variables_names, iStep, debug_name);
+    if (params.dimType == TWO_D) save_VTK_2D(Uhost, params, configMap, params.nbvar, variables_names, iStep, debug_name);
+    else if (params.nProcs > 1) save_VTK_3D_slab(Uhost, params, configMap, params.nbvar, variables_names, iStep, debug_name);
     else save_VTK_3D(Uhost, params, configMap, params.nbvar, variables_names, iStep, debug_name);
   }
   // HDF5: libhdf5 is not available in this build (same situation as the reference built without USE_HDF5)

@@ -79,6 +79,7 @@ SolverFactory &SolverFactory::Instance() {
 SolverFactory::SolverFactory() {
   // the key is the reference's: it is what makes HydroParams::setup choose nbvar=8, ghostWidth=3
   registerSolver("MHD_Muscl_3D", &SolverMHDMusclCuda3D::create);
+  registerSolver("MHD_Muscl_2D", &SolverMHDMusclCuda2D::create);
 }
 
 SolverBase *SolverFactory::create(const std::string &solver_name, HydroParams &params, ConfigMap &configMap) {

@@ -124,6 +124,9 @@ private:
 };
 void save_VTK_3D(const DataArray3dHost &Uhost, HydroParams &params, ConfigMap &configMap, int nbvar,
                  const std::map<int, std::string> &variables_names, int iStep, const std::string &debug_name);
+// 2-D files of save_VTK_2D (src/utils/io/IO_VTK.cpp:24-206): Uhost is (isize, jsize, 1, nbvar)
+void save_VTK_2D(const DataArray3dHost &Uhost, HydroParams &params, ConfigMap &configMap, int nbvar,
+                 const std::map<int, std::string> &variables_names, int iStep, const std::string &debug_name);
 void save_VTK_3D_slab(const DataArray3dHost &Uhost, HydroParams &params, ConfigMap &configMap, int nbvar,
                       const std::map<int, std::string> &variables_names, int iStep, const std::string &debug_name);
 }  // namespace io

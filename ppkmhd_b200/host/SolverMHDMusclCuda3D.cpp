@@ -545,4 +545,82 @@ void SolverMHDMusclCuda3D::save_solution_impl() {  // SolverMHDMuscl.h:896-907
   timers[TIMER_IO]->stop();
 }
 
+// ---------------------------------------------------------------------------------------------
+// the 2-D solver
+// ---------------------------------------------------------------------------------------------
+SolverMHDMusclCuda2D::SolverMHDMusclCuda2D(HydroParams &params_, ConfigMap &configMap_) : SolverBase(params_, configMap_) {
+  solver_type = SOLVER_MUSCL_HANCOCK;
+  m_nCells = (long)params.isize * params.jsize;  // ghosts included, like the reference
+  m_nDofsPerCell = 1;
+  if (params.riemannSolverType != RIEMANN_HLLD && params.riemannSolverType != RIEMANN_HLL &&
+      params.riemannSolverType != RIEMANN_LLF) {
+    fprintf(stderr, "MHD_Muscl_2D (CUDA): riemann=%s is not implemented; hlld, hll and llf are\n",
+            configMap.getString("hydro", "riemann", "approx").c_str());
+    std::abort();
+  }
+  if (params.implementationVersion == 2)
+    std::cout << "MHD_Muscl_2D (CUDA): implementationVersion=2 of the reference is a different formulation of the same "
+                 "scheme; running the v0 formulation\n";
+  ppk_mhd3d_params cp = params.to_c_params();
+  if (cp.implementation_version == 2) cp.implementation_version = 0;
+  PPK_CALL(ppk_mhd2d_create(&cp, &m_handle));
+  Uhost = DataArray3dHost(params.isize, params.jsize, 1, params.nbvar);
+  if (m_problem_name != "orszag_tang") {
+    // SolverMHDMuscl<2>::init falls back to Orszag-Tang for an unknown name; the other 2-D problems are not built here
+    std::cout << "Problem : " << m_problem_name << " is not recognized / implemented." << std::endl;
+    std::cout << "Use default - Orszag-Tang vortex" << std::endl;
+    m_problem_name = "orszag_tang";
+  }
+  init_orszag_tang_2d(params, Uhost);
+  PPK_CALL(ppk_mhd2d_upload(m_handle, Uhost.data()));
+  PPK_CALL(ppk_mhd2d_set_time(m_handle, m_t, m_tEnd, 0));
+  make_boundaries();
+  compute_dt();
+  if (params.myRank == 0) {
+    std::cout << "##########################" << "\n";
+    std::cout << "Solver is " << m_solver_name << " (B200-native CUDA, " << ppk_version_string() << ")\n";
+    std::cout << "Problem (init condition) is " << m_problem_name << "\n";
+    std::cout << "##########################" << "\n";
+    params.print();
+    std::cout << "##########################" << "\n";
+  }
+}
+
+SolverMHDMusclCuda2D::~SolverMHDMusclCuda2D() { ppk_mhd2d_destroy(m_handle); }
+
+void SolverMHDMusclCuda2D::make_boundaries() {
+  timers[TIMER_BOUNDARIES]->start();
+  PPK_CALL(ppk_mhd2d_make_boundaries(m_handle));
+  timers[TIMER_BOUNDARIES]->stop();
+}
+
+double SolverMHDMusclCuda2D::compute_dt_local() {
+  double dt = 0.0;
+  PPK_CALL(ppk_mhd2d_compute_dt(m_handle, &dt));
+  return dt;
+}
+
+void SolverMHDMusclCuda2D::next_iteration_impl() {  // SolverMHDMuscl.h:747-784
+  if (m_iteration % m_nlog == 0 && params.myRank == 0)
+    printf("time step=%7d (dt=% 10.8f t=% 10.8f)\n", m_iteration, m_dt, m_t);
+  if (params.enableOutput && should_save_solution()) {
+    if (params.myRank == 0)
+      std::cout << "Output results at time t=" << m_t << " step " << m_iteration << " dt=" << m_dt << std::endl;
+    save_solution();
+  }
+  timers[TIMER_NUM_SCHEME]->start();
+  PPK_CALL(ppk_mhd2d_step(m_handle));
+  double dt = 0.0;
+  PPK_CALL(ppk_mhd2d_get_time(m_handle, nullptr, &dt, nullptr));
+  timers[TIMER_NUM_SCHEME]->stop();
+  m_dt = dt;  // SolverBase::next_iteration then does m_t += m_dt, the same addition the device did
+}
+
+void SolverMHDMusclCuda2D::save_solution_impl() {
+  timers[TIMER_IO]->start();
+  PPK_CALL(ppk_mhd2d_download(m_handle, Uhost.data()));
+  save_data(Uhost, m_times_saved, m_t);
+  timers[TIMER_IO]->stop();
+}
+
 }  // namespace ppkMHD

@@ -77,4 +77,22 @@ private:
   ppk_mhd3d *m_handle = nullptr;
 };
 
+// Drop-in for SolverMHDMuscl<2> (src/muscl/SolverMHDMuscl.h, dim = 2) registered under "MHD_Muscl_2D": the 2-D time
+// loop on one GPU through the ppk_mhd2d_* C ABI. Uhost is (isize, jsize, 1, 8).
+class SolverMHDMusclCuda2D : public SolverBase {
+public:
+  SolverMHDMusclCuda2D(HydroParams &params, ConfigMap &configMap);
+  ~SolverMHDMusclCuda2D() override;
+  static SolverBase *create(HydroParams &params, ConfigMap &configMap) { return new SolverMHDMusclCuda2D(params, configMap); }
+
+  double compute_dt_local() override;
+  void next_iteration_impl() override;
+  void save_solution_impl() override;
+  void make_boundaries() override;
+  DataArray3dHost Uhost;
+
+private:
+  ppk_mhd2d *m_handle = nullptr;
+};
+
 }  // namespace ppkMHD

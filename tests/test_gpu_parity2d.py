@@ -70,3 +70,30 @@ def test_config0_orszag_tang_256_against_oracle(oracle_mod):
     assert it == orc.iteration and t == orc.t
     assert np.array_equal(s.interior(), orc.interior())
     s.close()
+
+
+def test_executable_2d_writes_the_reference_vti(oracle_mod):
+    """`ppkMHD_b200 run.ini` with solver_name=MHD_Muscl_2D (SolverFactory -> SolverMHDMusclCuda2D -> ppk_mhd2d_*): the .vti
+    files hold the reference's states and, where the reference binary is present, are byte-identical to its files."""
+    import subprocess
+    import tempfile
+
+    O = oracle_mod
+    g = np.load(f"{GOLDEN2D}/ot2d_16x12.npz")
+    ini = str(g["ini"])
+    exe = os.path.join(ROOT, "ppkmhd_b200", "bin", "ppkMHD_b200")
+    with tempfile.TemporaryDirectory() as tmp:
+        open(os.path.join(tmp, "run.ini"), "w").write(ini)
+        out = subprocess.run([exe, "run.ini"], cwd=tmp, capture_output=True, text=True, check=True).stdout
+        files = sorted(f for f in os.listdir(tmp) if f.endswith(".vti"))
+        assert len(files) == 2, out
+        assert np.array_equal(O.read_vti(os.path.join(tmp, files[0]))[:, 0], g["init"])
+        assert np.array_equal(O.read_vti(os.path.join(tmp, files[1]))[:, 0], g["stepN"])
+        assert "final time is %f" % float(g["final_time"]) in out
+        assert "time step=      0 (dt=% 10.8f t=% 10.8f)" % (g["log_dt"][0], 0.0) in out
+        if O.have_reference():
+            with tempfile.TemporaryDirectory() as tmp2:
+                open(os.path.join(tmp2, "run.ini"), "w").write(ini)
+                subprocess.run([O.REF_BIN, "run.ini"], cwd=tmp2, capture_output=True, check=True, env=dict(os.environ, OMP_NUM_THREADS="4"))
+                for f in files:
+                    assert open(os.path.join(tmp, f), "rb").read() == open(os.path.join(tmp2, f), "rb").read(), f
