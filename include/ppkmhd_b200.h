@@ -175,7 +175,8 @@ const char *ppk_version_string(void);
  * ComputeTraceFunctor2D_MHD, ComputeFluxesAndStoreFunctor2D_MHD, ComputeEmfAndStoreFunctor2D, UpdateFunctor2D_MHD,
  * UpdateEmfFunctor2D (src/muscl/MHDRunFunctors2D.h), then ++m_iteration, m_t += m_dt. Single GPU. The parameter block is
  * the 3-D one; nz, dz, the z bounds and the z faces are ignored. Arrays are u[var][j][i] with ghosts:
- * 8 * (ny+6) * (nx+6) doubles. Same status codes and error string as the 3-D entry points. */
+ * 8 * (ny+6) * (nx+6) doubles. implementationVersion 0, 1 and 2 all run the v0 formulation (the reference's own three variants
+ * agree to ~1e-15 in 2-D). Same status codes and error string as the 3-D entry points. */
 typedef struct ppk_mhd2d ppk_mhd2d;
 int ppk_mhd2d_create(const ppk_mhd3d_params *params, ppk_mhd2d **handle);
 int ppk_mhd2d_destroy(ppk_mhd2d *handle);

@@ -574,8 +574,10 @@ int ppk_mhd2d_create(const ppk_mhd3d_params *p, ppk_mhd2d **out) {
   if (p->ghost_width != PPK_GHOST_WIDTH) return fail(PPK_ERR_UNSUPPORTED, "ghost_width must be 3 (MHD_Muscl_2D)");
   if (p->riemann_solver != PPK_RIEMANN_HLLD && p->riemann_solver != PPK_RIEMANN_HLL && p->riemann_solver != PPK_RIEMANN_LLF)
     return fail(PPK_ERR_UNSUPPORTED, "riemann must be hlld, hll or llf");
-  if (p->implementation_version != 0 && p->implementation_version != 1)
-    return fail(PPK_ERR_UNSUPPORTED, "implementationVersion must be 0 or 1 in 2-D (the reference's v2 is a different formulation)");
+  // v0, v1 (atomic scatter) and v2 (slopes + updated primitives) of the reference are three formulations of the same 2-D
+  // scheme: its own outputs differ by ~1e-15 between them (tests/golden2d_v2/README.md). All three run the v0 kernels.
+  if (p->implementation_version < 0 || p->implementation_version > 2)
+    return fail(PPK_ERR_UNSUPPORTED, "implementationVersion must be 0, 1 or 2");
   if (p->mx != 1 || p->my != 1) return fail(PPK_ERR_UNSUPPORTED, "the 2-D path is single-GPU (mx = my = 1)");
   if (p->nx < 3 || p->ny < 3) return fail(PPK_ERR_INVALID_ARGUMENT, "nx, ny must be >= 3 (ghost width)");
   int ndev = 0;

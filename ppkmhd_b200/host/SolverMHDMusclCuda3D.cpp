@@ -562,7 +562,6 @@ SolverMHDMusclCuda2D::SolverMHDMusclCuda2D(HydroParams &params_, ConfigMap &conf
     std::cout << "MHD_Muscl_2D (CUDA): implementationVersion=2 of the reference is a different formulation of the same "
                  "scheme; running the v0 formulation\n";
   ppk_mhd3d_params cp = params.to_c_params();
-  if (cp.implementation_version == 2) cp.implementation_version = 0;
   PPK_CALL(ppk_mhd2d_create(&cp, &m_handle));
   Uhost = DataArray3dHost(params.isize, params.jsize, 1, params.nbvar);
   if (m_problem_name != "orszag_tang") {

@@ -97,3 +97,17 @@ def test_executable_2d_writes_the_reference_vti(oracle_mod):
                 subprocess.run([O.REF_BIN, "run.ini"], cwd=tmp2, capture_output=True, check=True, env=dict(os.environ, OMP_NUM_THREADS="4"))
                 for f in files:
                     assert open(os.path.join(tmp, f), "rb").read() == open(os.path.join(tmp2, f), "rb").read(), f
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_config0_v2_fixture_within_1e12(exact):
+    """BASELINE configs[0] as shipped (implementationVersion=2): the GPU path runs the v0 formulation and must agree with
+    the reference's v2 output within 1e-12 of the field maximum (tests/golden2d_v2/README.md)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden2d_v2", "ot2d_v2_64x64.npz"))
+    s, nstep = make_solver2d(str(g["ini"]), exact=exact)   # the ini says implementationVersion=2
+    assert np.array_equal(s.interior(), g["init"])
+    s.run(nstep)
+    t, dt, it = s.get_time()
+    assert it == int(g["nsteps"]) and abs(t - float(g["final_time"])) <= 0.5e-6 + 1e-12
+    assert np.abs(s.interior() - g["stepN"]).max() <= 1e-12 * np.abs(g["stepN"]).max()
+    s.close()

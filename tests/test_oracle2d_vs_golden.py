@@ -52,3 +52,17 @@ def test_oracle2d_config0_divb_and_conservation(oracle_mod):
     s1, d1 = sums_and_divb(orc)
     assert orc.iteration == 20 and d1 < 1e-12, (d0, d1)
     assert np.allclose(s1, s0, rtol=1e-12, atol=1e-9), (s0, s1)
+
+
+def test_v2_fixture_within_roundoff(oracle_mod):
+    """BASELINE configs[0] selects implementationVersion=2 (settings/test_mhd_orszag_tang_2D.ini). The reference's v0 and v2
+    are two formulations of the same scheme and differ by 1.4e-15 on this case; the oracle (v0) must stay within 1e-12 of
+    the v2 fixture (tests/golden2d_v2/, written by the reference: make_ini2d(n=(64, 64), nstepmax=20, smallr="1e-7",
+    version=2), one thread)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden2d_v2", "ot2d_v2_64x64.npz"))
+    orc = oracle_mod.Oracle2D(str(g["ini"]).replace("implementationVersion=2", "implementationVersion=0"))
+    assert np.array_equal(orc.interior(), g["init"])
+    orc.run()
+    assert orc.iteration == int(g["nsteps"])
+    scale = np.abs(g["stepN"]).max()
+    assert np.abs(orc.interior() - g["stepN"]).max() <= 1e-12 * scale
