@@ -25,8 +25,9 @@ int ppk_params_from_ini(const char *ini_text, int rank_z, ppk_mhd3d_params *para
  * to orszag_tang like the reference) into u_host (8*isize*jsize*ksize doubles). */
 int ppk_init_condition_from_ini(const char *ini_text, int rank_z, double *u_host);
 
-/* 2-D path ([run] solver_name=MHD_Muscl_2D): InitOrszagTangFunctor2D (src/muscl/MHDInitFunctors2D.h:241-385) into
- * u_host (8*isize*jsize doubles). PPK_ERR_UNSUPPORTED for another [hydro] problem (the other 2-D problems are not built). */
+/* 2-D path ([run] solver_name=MHD_Muscl_2D): the initial condition selected by [hydro] problem (orszag_tang, blast, rotor,
+ * field_loop, kelvin_helmholtz: src/muscl/MHDInitFunctors2D.h; anything else falls back to orszag_tang with a message) into
+ * u_host (8*isize*jsize doubles). */
 int ppk_init_condition_2d_from_ini(const char *ini_text, double *u_host);
 
 /* The whole program of src/main.cpp: read the ini file, create the solver through SolverFactory, run the

@@ -75,6 +75,132 @@ void orc2d_init_orszag_tang(const orc_params *p, double *U)
     }
 }
 
+void orc2d_init_blast(const orc_params *p, double radius, double cx, double cy, double density_in, double density_out,
+                      double pressure_in, double pressure_out, double *U)
+{
+  /* InitBlastFunctor2D_MHD, src/muscl/MHDInitFunctors2D.h:144-236 (uniform field 0.5, 0.5, 0.5 hard-coded) */
+  const int gw = p->gw;
+  const double radius2 = radius * radius;
+  for (int j = 0; j < p->jsize; ++j)
+    for (int i = 0; i < p->isize; ++i) {
+      double x = p->xmin + p->dx / 2 + (i + p->nx * p->px - gw) * p->dx;
+      double y = p->ymin + p->dy / 2 + (j + p->ny * p->py - gw) * p->dy;
+      double d2 = (x - cx) * (x - cx) + (y - cy) * (y - cy);
+      int in = d2 < radius2;
+      double a = 0.5, b = 0.5, c = 0.5;
+      U[AT2(p, i, j, ID)] = in ? density_in : density_out;
+      U[AT2(p, i, j, IU)] = 0.0;
+      U[AT2(p, i, j, IV)] = 0.0;
+      U[AT2(p, i, j, IW)] = 0.0;
+      U[AT2(p, i, j, IA)] = a;
+      U[AT2(p, i, j, IB)] = b;
+      U[AT2(p, i, j, IC)] = c;
+      U[AT2(p, i, j, IP)] = (in ? pressure_in : pressure_out) / (p->gamma0 - 1.0) + 0.5 * (a * a + b * b + c * c);
+    }
+}
+
+void orc2d_init_rotor(const orc_params *p, double r0, double r1, double u0, double p0, double b0, double *U)
+{
+  /* InitRotorFunctor2D_MHD, src/muscl/MHDInitFunctors2D.h:588-668 (momenta = rho * f_r * u0 * ..., also inside r0) */
+  const int gw = p->gw;
+  const double xCenter = (p->xmax + p->xmin) / 2, yCenter = (p->ymax + p->ymin) / 2;
+  for (int j = 0; j < p->jsize; ++j)
+    for (int i = 0; i < p->isize; ++i) {
+      double x = p->xmin + p->dx / 2 + (i + p->nx * p->px - gw) * p->dx;
+      double y = p->ymin + p->dy / 2 + (j + p->ny * p->py - gw) * p->dy;
+      double r = sqrt((x - xCenter) * (x - xCenter) + (y - yCenter) * (y - yCenter));
+      double f_r = (r1 - r) / (r1 - r0);
+      double d, mu, mv;
+      if (r <= r0) { d = 10.0; mu = -d * f_r * u0 * (y - yCenter) / r0; mv = d * f_r * u0 * (x - xCenter) / r0; }
+      else if (r <= r1) { d = 1 + 9 * f_r; mu = -d * f_r * u0 * (y - yCenter) / r; mv = d * f_r * u0 * (x - xCenter) / r; }
+      else { d = 1.0; mu = 0.0; mv = 0.0; }
+      U[AT2(p, i, j, ID)] = d;
+      U[AT2(p, i, j, IU)] = mu;
+      U[AT2(p, i, j, IV)] = mv;
+      U[AT2(p, i, j, IW)] = 0.0;
+      U[AT2(p, i, j, IA)] = b0;
+      U[AT2(p, i, j, IB)] = 0.0;
+      U[AT2(p, i, j, IC)] = 0.0;
+      U[AT2(p, i, j, IP)] = p0 / (p->gamma0 - 1.0) + 0.5 * (mu * mu + mv * mv + 0.0 * 0.0) / d + 0.5 * (b0 * b0);
+    }
+}
+
+void orc2d_init_field_loop(const orc_params *p, double radius, double density_in, double amplitude, double vflow, double *U)
+{
+  /* InitFieldLoopFunctor2D_MHD, src/muscl/MHDInitFunctors2D.h:715-945 : A_z everywhere, then the interior cells (face B by
+   * first differences of A_z), then their energy; ghost cells stay zero until the first ghost fill */
+  const int gw = p->gw, isz = p->isize, jsz = p->jsize, nx = p->nx, ny = p->ny, nz = p->nz;
+  double *Az = (double *)calloc((size_t)isz * jsz, sizeof(double));
+  memset(U, 0, sizeof(double) * NV * (size_t)isz * jsz);
+#define AZ(i, j) Az[(size_t)(i) + (size_t)isz * (size_t)(j)]
+  for (int j = 0; j < jsz; ++j)
+    for (int i = 0; i < isz; ++i) {
+      double x = p->xmin + p->dx / 2 + (i + nx * p->px - gw) * p->dx;
+      double y = p->ymin + p->dy / 2 + (j + ny * p->py - gw) * p->dy;
+      double r = sqrt(x * x + y * y);
+      AZ(i, j) = r < radius ? amplitude * (radius - r) : 0.0;
+    }
+  const double cos_theta = 2.0 / sqrt(5.0);
+  const double sin_theta = sqrt(1 - cos_theta * cos_theta);
+  for (int j = gw; j < jsz - gw; ++j)
+    for (int i = gw; i < isz - gw; ++i) {
+      double x = p->xmin + p->dx / 2 + (i + nx * p->px - gw) * p->dx;
+      double y = p->ymin + p->dy / 2 + (j + ny * p->py - gw) * p->dy;
+      double diag = sqrt(1.0 * (nx * nx + ny * ny + nz * nz));
+      double r = sqrt(x * x + y * y);
+      double d = r < radius ? density_in : 1.0;
+      U[AT2(p, i, j, ID)] = d;
+      U[AT2(p, i, j, IU)] = d * vflow * cos_theta;
+      U[AT2(p, i, j, IV)] = d * vflow * sin_theta;
+      U[AT2(p, i, j, IW)] = d * vflow * nz / diag;
+      U[AT2(p, i, j, IA)] = (AZ(i, j + 1) - AZ(i, j)) / p->dy;
+      U[AT2(p, i, j, IB)] = -(AZ(i + 1, j) - AZ(i, j)) / p->dx;
+      U[AT2(p, i, j, IC)] = 0.0;
+    }
+  for (int j = gw; j < jsz - gw; ++j)
+    for (int i = gw; i < isz - gw; ++i) {
+      double a = U[AT2(p, i, j, IA)] + U[AT2(p, i + 1, j, IA)], b = U[AT2(p, i, j, IB)] + U[AT2(p, i, j + 1, IB)];
+      double mu = U[AT2(p, i, j, IU)], mv = U[AT2(p, i, j, IV)];
+      U[AT2(p, i, j, IP)] = 1.0f / (p->gamma0 - 1.0) + 0.5 * (0.25 * (a * a) + 0.25 * (b * b)) + 0.5 * (mu * mu + mv * mv) / U[AT2(p, i, j, ID)];
+    }
+#undef AZ
+  free(Az);
+}
+
+void orc2d_init_kelvin_helmholtz(const orc_params *p, double d_in, double d_out, double pressure, double vflow_in,
+                                 double vflow_out, int mode, double w0, double delta, int sine_robertson, double *U)
+{
+  /* InitKelvinHelmholtzFunctor2D_MHD, src/muscl/MHDInitFunctors2D.h:394-583, the two deterministic perturbations; the
+   * out-of-plane momentum is never written (stays 0) */
+  const int gw = p->gw;
+  const double PI = 3.141592653589793238462643383279502884L; /* PI_F */
+  const double y1 = 0.25, y2 = 0.75;
+  for (int j = 0; j < p->jsize; ++j)
+    for (int i = 0; i < p->isize; ++i) {
+      double x = p->xmin + p->dx / 2 + (i + p->nx * p->px - gw) * p->dx;
+      double y = p->ymin + p->dy / 2 + (j + p->ny * p->py - gw) * p->dy;
+      double d, u, v;
+      if (sine_robertson) {
+        const double ramp = 1.0 / (1.0 + exp(2 * (y - y1) / delta)) + 1.0 / (1.0 + exp(2 * (y2 - y) / delta));
+        d = d_in + ramp * (d_out - d_in);
+        u = vflow_in + ramp * (vflow_out - vflow_in);
+      } else {
+        d = (y >= y1 && y <= y2) ? d_in : d_out;
+        u = (y >= y1 && y <= y2) ? vflow_in : vflow_out;
+      }
+      v = w0 * sin(mode * PI * x);
+      const double bx = 0.5, by = 0.0, bz = 0.0;
+      U[AT2(p, i, j, ID)] = d;
+      U[AT2(p, i, j, IU)] = d * u;
+      U[AT2(p, i, j, IV)] = d * v;
+      U[AT2(p, i, j, IW)] = 0.0;
+      U[AT2(p, i, j, IA)] = bx;
+      U[AT2(p, i, j, IB)] = by;
+      U[AT2(p, i, j, IC)] = bz;
+      U[AT2(p, i, j, IP)] = pressure / (p->gamma0 - 1.0) + 0.5 * d * (u * u + v * v) + 0.5 * (bx * bx + by * by + bz * bz);
+    }
+}
+
 void orc2d_make_boundaries(const orc_params *p, double *U)
 {
   /* SolverBase::make_boundaries_serial, 2-D branch (src/shared/SolverBase.cpp:505-525) with

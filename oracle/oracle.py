@@ -70,6 +70,10 @@ def lib():
         _lib.orc2d_params_finalize.argtypes = [pp]
         _lib.orc2d_init_orszag_tang.argtypes = [pp, dp]
         _lib.orc2d_make_boundaries.argtypes = [pp, dp]
+        _lib.orc2d_init_blast.argtypes = [pp] + [C.c_double] * 7 + [dp]
+        _lib.orc2d_init_rotor.argtypes = [pp] + [C.c_double] * 5 + [dp]
+        _lib.orc2d_init_field_loop.argtypes = [pp] + [C.c_double] * 4 + [dp]
+        _lib.orc2d_init_kelvin_helmholtz.argtypes = [pp] + [C.c_double] * 5 + [C.c_int, C.c_double, C.c_double, C.c_int, dp]
         _lib.orc2d_step.restype = C.c_double
         _lib.orc2d_step.argtypes = [pp, dp, dp, dp, C.c_double, C.c_double]
         _lib.orc_make_boundary.argtypes = [pp, dp, C.c_int]
@@ -306,6 +310,40 @@ class Oracle:
         return sums, m.value
 
 
+def init_problem_2d(p: OrcParams, cfg: Config, U: np.ndarray) -> None:
+    """SolverMHDMuscl<2>::init dispatch (src/muscl/SolverMHDMuscl.h:653-713) with the 2-D functors of MHDInitFunctors2D.h;
+    implode and wave are not restated (ValueError); an unknown name falls back to Orszag-Tang like the reference."""
+    L = lib()
+    problem = cfg.s("hydro", "problem", "unknown")
+    f32 = lambda x: float(np.float32(x))
+    if problem == "blast":
+        xmin, xmax = cfg.f("mesh", "xmin", 0.0), cfg.f("mesh", "xmax", 1.0)
+        ymin, ymax = cfg.f("mesh", "ymin", 0.0), cfg.f("mesh", "ymax", 1.0)
+        L.orc2d_init_blast(C.byref(p), cfg.f("blast", "radius", f32((xmin + xmax) / 2.0 / 10)),
+                           cfg.f("blast", "center_x", f32((xmin + xmax) / 2)), cfg.f("blast", "center_y", f32((ymin + ymax) / 2)),
+                           cfg.f("blast", "density_in", 1.0), cfg.f("blast", "density_out", 1.2),
+                           cfg.f("blast", "pressure_in", 10.0), cfg.f("blast", "pressure_out", 0.1), _dp(U))
+    elif problem == "rotor":
+        L.orc2d_init_rotor(C.byref(p), cfg.f("rotor", "r0", 0.1), cfg.f("rotor", "r1", 0.115), cfg.f("rotor", "u0", 2.0),
+                           cfg.f("rotor", "p0", 1.0), cfg.f("rotor", "b0", 5.0 / np.sqrt(4 * np.pi)), _dp(U))
+    elif problem in ("field_loop", "field loop"):
+        L.orc2d_init_field_loop(C.byref(p), cfg.f("FieldLoop", "radius", 1.0), cfg.f("FieldLoop", "density_in", 1.0),
+                                cfg.f("FieldLoop", "amplitude", 1.0), cfg.f("FieldLoop", "vflow", 1.0), _dp(U))
+    elif problem == "kelvin_helmholtz":
+        if cfg.b("KH", "perturbation_rand", False):
+            raise ValueError("perturbation_rand is not reproducible in the reference (per-thread Kokkos random pool)")
+        rob, sine = cfg.b("KH", "perturbation_sine_robertson", True), cfg.b("KH", "perturbation_sine", False)
+        if rob or sine:
+            L.orc2d_init_kelvin_helmholtz(
+                C.byref(p), cfg.f("KH", "d_in", 1.0), cfg.f("KH", "d_out", 1.0), cfg.f("KH", "pressure", 10.0),
+                cfg.f("KH", "vflow_in", -0.5), cfg.f("KH", "vflow_out", 0.5), cfg.i("KH", "mode", 2),
+                cfg.f("KH", "w0", 0.1), cfg.f("KH", "delta", 0.03), 1 if rob else 0, _dp(U))
+    elif problem in ("implode", "wave"):
+        raise ValueError(f"the 2-D {problem} initial condition is not restated")
+    else:
+        L.orc2d_init_orszag_tang(C.byref(p), _dp(U))
+
+
 class Oracle2D:
     """The 2-D path (MHD_Muscl_2D, implementationVersion 0): oracle only, no CUDA counterpart yet.
     Arrays are (8, jsize, isize)."""
@@ -328,10 +366,7 @@ class Oracle2D:
         self.nstepmax = cfg.i("run", "nstepmax", 1000)
         self.t, self.iteration, self.dt = 0.0, 0, self.t_end
         self.U = np.zeros((8, p.jsize, p.isize))
-        problem = cfg.s("hydro", "problem", "unknown")
-        if problem != "orszag_tang":
-            raise ValueError("the 2-D oracle has the Orszag-Tang initial condition only")
-        lib().orc2d_init_orszag_tang(C.byref(p), _dp(self.U))
+        init_problem_2d(p, cfg, self.U)
         lib().orc2d_make_boundaries(C.byref(p), _dp(self.U))  # constructor sequence, SolverMHDMuscl.h:390-402
         self.U2 = self.U.copy()
         self.Q = np.zeros_like(self.U)

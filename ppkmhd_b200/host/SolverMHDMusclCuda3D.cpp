@@ -416,6 +416,139 @@ void init_orszag_tang_2d(const HydroParams &p, DataArray3dHost &U) {
                               0.25 * sqr(U(i, j, 0, IA) + U(i + 1, j, 0, IA)) + 0.25 * sqr(U(i, j, 0, IB) + U(i, j + 1, 0, IB)));
 }
 
+void init_blast_2d(const HydroParams &p, const BlastParams &b, DataArray3dHost &U) {
+  const CellCoords cc{p};
+  const double radius2 = b.blast_radius * b.blast_radius;
+  for (int j = 0; j < p.jsize; ++j)
+    for (int i = 0; i < p.isize; ++i) {
+      const double x = cc.x(i), y = cc.y(j);
+      const bool in = (x - b.blast_center_x) * (x - b.blast_center_x) + (y - b.blast_center_y) * (y - b.blast_center_y) < radius2;
+      U(i, j, 0, ID) = in ? b.blast_density_in : b.blast_density_out;
+      U(i, j, 0, IU) = 0.0;
+      U(i, j, 0, IV) = 0.0;
+      U(i, j, 0, IW) = 0.0;
+      U(i, j, 0, IA) = 0.5;  // hard-coded uniform field of the reference
+      U(i, j, 0, IB) = 0.5;
+      U(i, j, 0, IC) = 0.5;
+      U(i, j, 0, IP) = (in ? b.blast_pressure_in : b.blast_pressure_out) / (p.settings.gamma0 - 1.0) +
+                       0.5 * (sqr(U(i, j, 0, IA)) + sqr(U(i, j, 0, IB)) + sqr(U(i, j, 0, IC)));
+    }
+}
+
+void init_rotor_2d(const HydroParams &p, const RotorParams &rp, DataArray3dHost &U) {
+  // unlike the 3-D functor the momenta are rho * f_r * u0 * (...), f_r also inside r0
+  const CellCoords cc{p};
+  const double xCenter = (p.xmax + p.xmin) / 2, yCenter = (p.ymax + p.ymin) / 2;
+  for (int j = 0; j < p.jsize; ++j)
+    for (int i = 0; i < p.isize; ++i) {
+      const double x = cc.x(i), y = cc.y(j);
+      const double r = sqrt((x - xCenter) * (x - xCenter) + (y - yCenter) * (y - yCenter));
+      const double f_r = (rp.r1 - r) / (rp.r1 - rp.r0);
+      if (r <= rp.r0) {
+        U(i, j, 0, ID) = 10.0;
+        U(i, j, 0, IU) = -U(i, j, 0, ID) * f_r * rp.u0 * (y - yCenter) / rp.r0;
+        U(i, j, 0, IV) = U(i, j, 0, ID) * f_r * rp.u0 * (x - xCenter) / rp.r0;
+      } else if (r <= rp.r1) {
+        U(i, j, 0, ID) = 1 + 9 * f_r;
+        U(i, j, 0, IU) = -U(i, j, 0, ID) * f_r * rp.u0 * (y - yCenter) / r;
+        U(i, j, 0, IV) = U(i, j, 0, ID) * f_r * rp.u0 * (x - xCenter) / r;
+      } else {
+        U(i, j, 0, ID) = 1.0;
+        U(i, j, 0, IU) = 0.0;
+        U(i, j, 0, IV) = 0.0;
+      }
+      U(i, j, 0, IW) = 0.0;
+      U(i, j, 0, IA) = rp.b0;
+      U(i, j, 0, IB) = 0.0;
+      U(i, j, 0, IC) = 0.0;
+      U(i, j, 0, IP) = rp.p0 / (p.settings.gamma0 - 1.0) +
+                       0.5 * (U(i, j, 0, IU) * U(i, j, 0, IU) + U(i, j, 0, IV) * U(i, j, 0, IV) + U(i, j, 0, IW) * U(i, j, 0, IW)) /
+                         U(i, j, 0, ID) +
+                       0.5 * (U(i, j, 0, IA) * U(i, j, 0, IA));
+    }
+}
+
+void init_field_loop_2d(const HydroParams &p, const FieldLoopParams &fl, DataArray3dHost &U) {
+  // A_z on every cell, then face B of the interior cells by first differences, then their energy (ghosts stay zero)
+  const CellCoords cc{p};
+  const int gw = p.ghostWidth;
+  std::vector<double> az((size_t)p.isize * p.jsize, 0.0);
+  auto Az = [&](int i, int j) -> double & { return az[(size_t)i + (size_t)p.isize * j]; };
+  for (int j = 0; j < p.jsize; ++j)
+    for (int i = 0; i < p.isize; ++i) {
+      const double x = cc.x(i), y = cc.y(j), r = sqrt(x * x + y * y);
+      Az(i, j) = r < fl.radius ? fl.amplitude * (fl.radius - r) : 0.0;
+    }
+  const double cos_theta = 2.0 / sqrt(5.0), sin_theta = sqrt(1 - cos_theta * cos_theta);
+  for (int j = gw; j < p.jsize - gw; ++j)
+    for (int i = gw; i < p.isize - gw; ++i) {
+      const double x = cc.x(i), y = cc.y(j);
+      const double diag = sqrt(1.0 * (p.nx * p.nx + p.ny * p.ny + p.nz * p.nz));
+      const double r = sqrt(x * x + y * y);
+      U(i, j, 0, ID) = r < fl.radius ? fl.density_in : 1.0;
+      U(i, j, 0, IU) = U(i, j, 0, ID) * fl.vflow * cos_theta;
+      U(i, j, 0, IV) = U(i, j, 0, ID) * fl.vflow * sin_theta;
+      U(i, j, 0, IW) = U(i, j, 0, ID) * fl.vflow * p.nz / diag;
+      U(i, j, 0, IA) = (Az(i, j + 1) - Az(i, j)) / p.dy;
+      U(i, j, 0, IB) = -(Az(i + 1, j) - Az(i, j)) / p.dx;
+      U(i, j, 0, IC) = 0.0;
+    }
+  for (int j = gw; j < p.jsize - gw; ++j)
+    for (int i = gw; i < p.isize - gw; ++i)
+      U(i, j, 0, IP) = 1.0f / (p.settings.gamma0 - 1.0) +
+                       0.5 * (0.25 * sqr(U(i, j, 0, IA) + U(i + 1, j, 0, IA)) + 0.25 * sqr(U(i, j, 0, IB) + U(i, j + 1, 0, IB))) +
+                       0.5 * (U(i, j, 0, IU) * U(i, j, 0, IU) + U(i, j, 0, IV) * U(i, j, 0, IV)) / U(i, j, 0, ID);
+}
+
+void init_kelvin_helmholtz_2d(const HydroParams &p, const KHParams &kh, DataArray3dHost &U) {
+  if (kh.p_rand) {
+    fprintf(stderr, "kelvin_helmholtz: perturbation_rand draws from Kokkos' per-thread random pool in the reference and is not "
+                    "reproducible; use perturbation_sine or perturbation_sine_robertson\n");
+    std::abort();
+  }
+  const CellCoords cc{p};
+  const double pi = 3.141592653589793238462643383279502884L, gamma0 = p.settings.gamma0;
+  const double y1 = 0.25, y2 = 0.75;
+  for (int j = 0; j < p.jsize; ++j)
+    for (int i = 0; i < p.isize; ++i) {
+      const double x = cc.x(i), y = cc.y(j);
+      double d, u;
+      if (kh.p_sine_rob) {
+        const double ramp = 1.0 / (1.0 + exp(2 * (y - y1) / kh.delta)) + 1.0 / (1.0 + exp(2 * (y2 - y) / kh.delta));
+        d = kh.d_in + ramp * (kh.d_out - kh.d_in);
+        u = kh.vflow_in + ramp * (kh.vflow_out - kh.vflow_in);
+      } else if (kh.p_sine) {
+        d = (y >= y1 && y <= y2) ? kh.d_in : kh.d_out;
+        u = (y >= y1 && y <= y2) ? kh.vflow_in : kh.vflow_out;
+      } else {
+        continue;
+      }
+      const double v = kh.w0 * sin(kh.mode * pi * x);
+      const double bx = 0.5, by = 0.0, bz = 0.0;
+      U(i, j, 0, ID) = d;
+      U(i, j, 0, IU) = d * u;
+      U(i, j, 0, IV) = d * v;
+      U(i, j, 0, IA) = bx;
+      U(i, j, 0, IB) = by;
+      U(i, j, 0, IC) = bz;
+      U(i, j, 0, IP) = kh.pressure / (gamma0 - 1.0) + 0.5 * d * (u * u + v * v) + 0.5 * (bx * bx + by * by + bz * bz);
+    }
+}
+
+std::string init_problem_2d(const HydroParams &params, ConfigMap &configMap, const std::string &problem, DataArray3dHost &U) {
+  if (problem == "orszag_tang") { init_orszag_tang_2d(params, U); return problem; }
+  if (problem == "blast") { init_blast_2d(params, BlastParams(configMap), U); return problem; }
+  if (problem == "rotor") { init_rotor_2d(params, RotorParams(configMap), U); return problem; }
+  if (problem == "field_loop" || problem == "field loop") { init_field_loop_2d(params, FieldLoopParams(configMap), U); return problem; }
+  if (problem == "kelvin_helmholtz") { init_kelvin_helmholtz_2d(params, KHParams(configMap), U); return problem; }
+  // implode and wave exist in the reference's 2-D dispatch but are not built here; like its final else
+  // (SolverMHDMuscl.h:701-709) anything else falls back to Orszag-Tang with a message
+  std::cout << "Problem : " << problem << " is not recognized / implemented." << std::endl;
+  std::cout << "Use default - Orszag-Tang vortex" << std::endl;
+  init_orszag_tang_2d(params, U);
+  return "orszag_tang";
+}
+
 std::string init_problem(const HydroParams &params, ConfigMap &configMap, const std::string &problem, DataArray3dHost &U) {
   if (problem == "blast") {
     init_blast(params, BlastParams(configMap), U);
@@ -564,13 +697,7 @@ SolverMHDMusclCuda2D::SolverMHDMusclCuda2D(HydroParams &params_, ConfigMap &conf
   ppk_mhd3d_params cp = params.to_c_params();
   PPK_CALL(ppk_mhd2d_create(&cp, &m_handle));
   Uhost = DataArray3dHost(params.isize, params.jsize, 1, params.nbvar);
-  if (m_problem_name != "orszag_tang") {
-    // SolverMHDMuscl<2>::init falls back to Orszag-Tang for an unknown name; the other 2-D problems are not built here
-    std::cout << "Problem : " << m_problem_name << " is not recognized / implemented." << std::endl;
-    std::cout << "Use default - Orszag-Tang vortex" << std::endl;
-    m_problem_name = "orszag_tang";
-  }
-  init_orszag_tang_2d(params, Uhost);
+  m_problem_name = init_problem_2d(params, configMap, m_problem_name, Uhost);
   PPK_CALL(ppk_mhd2d_upload(m_handle, Uhost.data()));
   PPK_CALL(ppk_mhd2d_set_time(m_handle, m_t, m_tEnd, 0));
   make_boundaries();

@@ -55,6 +55,12 @@ void init_field_loop(const HydroParams &params, const FieldLoopParams &fl, DataA
 std::string init_problem(const HydroParams &params, ConfigMap &configMap, const std::string &problem, DataArray3dHost &U);
 // 2-D path (MHD_Muscl_2D): U is (isize, jsize, 1, 8). InitOrszagTangFunctor2D, src/muscl/MHDInitFunctors2D.h:241-385
 void init_orszag_tang_2d(const HydroParams &params, DataArray3dHost &U);
+void init_blast_2d(const HydroParams &params, const BlastParams &b, DataArray3dHost &U);               // MHDInitFunctors2D.h:144-236
+void init_rotor_2d(const HydroParams &params, const RotorParams &rp, DataArray3dHost &U);              // MHDInitFunctors2D.h:588-668
+void init_field_loop_2d(const HydroParams &params, const FieldLoopParams &fl, DataArray3dHost &U);     // MHDInitFunctors2D.h:715-945
+void init_kelvin_helmholtz_2d(const HydroParams &params, const KHParams &kh, DataArray3dHost &U);      // MHDInitFunctors2D.h:394-583
+// SolverMHDMuscl<2>::init dispatch; implode and wave are not built in 2-D (message + Orszag-Tang, like an unknown name)
+std::string init_problem_2d(const HydroParams &params, ConfigMap &configMap, const std::string &problem, DataArray3dHost &U);
 
 class SolverMHDMusclCuda3D : public SolverBase {
 public:

@@ -66,9 +66,8 @@ int ppk_init_condition_2d_from_ini(const char *ini_text, double *u_host) {
   if (!ini_text || !u_host) return PPK_ERR_INVALID_ARGUMENT;
   ConfigMap cfg(ini_text, (int)strlen(ini_text));
   HydroParams p = params_for(cfg, 0);
-  if (cfg.getString("hydro", "problem", "unknown") != "orszag_tang") return PPK_ERR_UNSUPPORTED;
   DataArray3dHost U(p.isize, p.jsize, 1, p.nbvar);
-  init_orszag_tang_2d(p, U);
+  init_problem_2d(p, cfg, cfg.getString("hydro", "problem", "unknown"), U);
   memcpy(u_host, U.data(), U.size() * sizeof(double));
   return 0;
 }

@@ -18,7 +18,8 @@ sys.path.insert(0, ROOT)
 from oracle import oracle as O  # noqa: E402
 
 
-def make_ini2d(n=(16, 12), nstepmax=5, bc=3, riemann="hlld", cfl=0.8, slope_type=2, smallr="1e-8", version=0, tend=10.0):
+def make_ini2d(n=(16, 12), nstepmax=5, bc=3, riemann="hlld", cfl=0.8, slope_type=2, smallr="1e-8", version=0, tend=10.0,
+               problem="orszag_tang", extra="", bounds=(0.0, 1.0, 0.0, 1.0), gamma0="1.666"):
     bcs = bc if isinstance(bc, (list, tuple)) else [bc] * 4
     bc_txt = "\n".join(f"boundary_type_{nm}={v}" for nm, v in zip(("xmin", "xmax", "ymin", "ymax"), bcs))
     return f"""[run]
@@ -30,18 +31,18 @@ nlog=1
 [mesh]
 nx={n[0]}
 ny={n[1]}
-xmin=0.0
-xmax=1.0
-ymin=0.0
-ymax=1.0
+xmin={bounds[0]}
+xmax={bounds[1]}
+ymin={bounds[2]}
+ymax={bounds[3]}
 {bc_txt}
 [hydro]
-gamma0=1.666
+gamma0={gamma0}
 cfl={cfl}
 niter_riemann=10
 iorder=2
 slope_type={slope_type}
-problem=orszag_tang
+problem={problem}
 riemann={riemann}
 smallr={smallr}
 smallc={smallr}
@@ -50,7 +51,7 @@ outputPrefix=run
 outputVtkAscii=false
 [other]
 implementationVersion={version}
-"""
+{extra}"""
 
 
 CASES = {
@@ -62,6 +63,19 @@ CASES = {
     "ot2d_hll_16x12": dict(n=(16, 12), nstepmax=5, riemann="hll"),
     "ot2d_llf_12x12": dict(n=(12, 12), nstepmax=5, riemann="llf"),
     "ot2d_minmod_16x16": dict(n=(16, 16), nstepmax=5, slope_type=1, cfl=0.5),
+    # the other 2-D problems with a shipped .ini (test_mhd_blast_2D, test_mhd_rotor, mhd_fieldloop2d, ..._kelvin_helmholtz_2D_mhd)
+    "blast2d_16x16": dict(n=(16, 16), nstepmax=6, problem="blast",
+                          extra="[blast]\nradius=0.25\ndensity_in=1.0\ndensity_out=1.2\npressure_in=10.0\npressure_out=0.1\n"),
+    "blast2d_neumann_12x16": dict(n=(12, 16), nstepmax=6, problem="blast", bc=2,
+                                  extra="[blast]\nradius=0.25\ndensity_in=1.0\ndensity_out=1.2\npressure_in=10.0\npressure_out=0.1\n"),
+    # settings/test_mhd_rotor.ini at 32^2 (with gamma0 = 1.666, u0 = 2 and periodic faces the reference itself turns NaN)
+    "rotor2d_32x32": dict(n=(32, 32), nstepmax=8, problem="rotor", bc=2, cfl=0.4, gamma0="1.4",
+                          extra="[rotor]\nr0=0.1\nr1=0.115\nu0=1.0\np0=1.5\n"),
+    "fieldloop2d_24x12": dict(n=(24, 12), nstepmax=6, problem="field_loop", cfl=0.4, bounds=(-1.0, 1.0, -0.5, 0.5),
+                              extra="[FieldLoop]\nradius=0.3\namplitude=0.001\nvflow=3\ndensity_in=1\n"),
+    "kh2d_robertson_16x16": dict(n=(16, 16), nstepmax=5, problem="kelvin_helmholtz", extra="[KH]\nd_in=2.0\n"),
+    "kh2d_sine_16x12": dict(n=(16, 12), nstepmax=5, problem="kelvin_helmholtz", bc=[3, 3, 2, 2],
+                            extra="[KH]\nperturbation_sine=true\nperturbation_sine_robertson=false\nd_in=2.0\nw0=0.05\nmode=4\n"),
 }
 
 

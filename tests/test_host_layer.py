@@ -102,7 +102,8 @@ def test_bench_reference_arm_prints_one_json_line():
 
 
 def test_initial_condition_2d_bitwise(oracle_mod):
-    """Host-layer Orszag-Tang 2-D initial condition == the reference's step-0 .vti == the 2-D oracle, ghosts included."""
+    """Host-layer 2-D initial conditions (Orszag-Tang, blast, rotor, field loop, Kelvin-Helmholtz) == the reference's step-0
+    .vti == the 2-D oracle, ghosts included."""
     g2 = os.path.join(ROOT, "tests", "golden2d")
     for f in sorted(os.listdir(g2)):
         if not f.endswith(".npz"):
@@ -113,5 +114,5 @@ def test_initial_condition_2d_bitwise(oracle_mod):
         assert np.array_equal(U[:, 3:-3, 3:-3], g["init"]), f
         orc = oracle_mod.Oracle2D(ini)
         Uo = np.zeros_like(U)
-        oracle_mod.lib().orc2d_init_orszag_tang(oracle_mod.C.byref(orc.p), oracle_mod._dp(Uo))
+        oracle_mod.init_problem_2d(orc.p, orc.cfg, Uo)
         assert np.array_equal(U, Uo), f
