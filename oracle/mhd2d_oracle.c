@@ -201,6 +201,30 @@ void orc2d_init_kelvin_helmholtz(const orc_params *p, double d_in, double d_out,
     }
 }
 
+void orc2d_init_implode(const orc_params *p, const double outer[8], const double inner[8], int shape, double *U)
+{
+  /* InitImplodeFunctor2D_MHD, src/muscl/MHDInitFunctors2D.h:36-139 ; outer/inner = rho, p, u, v, w, Bx, By, Bz of
+   * ImplodeParams (w and Bz are not used in 2-D); velocities go into the momentum slots, as in the reference */
+  const int gw = p->gw;
+  for (int j = 0; j < p->jsize; ++j)
+    for (int i = 0; i < p->isize; ++i) {
+      double x = p->xmin + p->dx / 2 + (i + p->nx * p->px - gw) * p->dx;
+      double y = p->ymin + p->dy / 2 + (j + p->ny * p->py - gw) * p->dy;
+      int tmp;
+      if (shape == 1) tmp = x + y > 0.5 && x + y < 2.5;
+      else tmp = x + y > (p->xmin + p->xmax) / 2. + p->ymin;
+      const double *s = tmp ? outer : inner;
+      U[AT2(p, i, j, ID)] = s[0];
+      U[AT2(p, i, j, IP)] = s[1] / (p->gamma0 - 1.0) + 0.5 * s[0] * (s[2] * s[2] + s[3] * s[3]) + 0.5 * (s[5] * s[5] + s[6] * s[6]);
+      U[AT2(p, i, j, IU)] = s[2];
+      U[AT2(p, i, j, IV)] = s[3];
+      U[AT2(p, i, j, IW)] = 0.0;
+      U[AT2(p, i, j, IA)] = s[5];
+      U[AT2(p, i, j, IB)] = s[6];
+      U[AT2(p, i, j, IC)] = 0.0;
+    }
+}
+
 void orc2d_make_boundaries(const orc_params *p, double *U)
 {
   /* SolverBase::make_boundaries_serial, 2-D branch (src/shared/SolverBase.cpp:505-525) with

@@ -71,6 +71,7 @@ def lib():
         _lib.orc2d_init_orszag_tang.argtypes = [pp, dp]
         _lib.orc2d_make_boundaries.argtypes = [pp, dp]
         _lib.orc2d_init_blast.argtypes = [pp] + [C.c_double] * 7 + [dp]
+        _lib.orc2d_init_implode.argtypes = [pp, dp, dp, C.c_int, dp]
         _lib.orc2d_init_rotor.argtypes = [pp] + [C.c_double] * 5 + [dp]
         _lib.orc2d_init_field_loop.argtypes = [pp] + [C.c_double] * 4 + [dp]
         _lib.orc2d_init_kelvin_helmholtz.argtypes = [pp] + [C.c_double] * 5 + [C.c_int, C.c_double, C.c_double, C.c_int, dp]
@@ -312,7 +313,7 @@ class Oracle:
 
 def init_problem_2d(p: OrcParams, cfg: Config, U: np.ndarray) -> None:
     """SolverMHDMuscl<2>::init dispatch (src/muscl/SolverMHDMuscl.h:653-713) with the 2-D functors of MHDInitFunctors2D.h;
-    implode and wave are not restated (ValueError); an unknown name falls back to Orszag-Tang like the reference."""
+    the reference's 2-D wave functor is empty (ValueError); an unknown name falls back to Orszag-Tang like the reference."""
     L = lib()
     problem = cfg.s("hydro", "problem", "unknown")
     f32 = lambda x: float(np.float32(x))
@@ -338,8 +339,13 @@ def init_problem_2d(p: OrcParams, cfg: Config, U: np.ndarray) -> None:
                 C.byref(p), cfg.f("KH", "d_in", 1.0), cfg.f("KH", "d_out", 1.0), cfg.f("KH", "pressure", 10.0),
                 cfg.f("KH", "vflow_in", -0.5), cfg.f("KH", "vflow_out", 0.5), cfg.i("KH", "mode", 2),
                 cfg.f("KH", "w0", 0.1), cfg.f("KH", "delta", 0.03), 1 if rob else 0, _dp(U))
-    elif problem in ("implode", "wave"):
-        raise ValueError(f"the 2-D {problem} initial condition is not restated")
+    elif problem == "implode":
+        names = ("density", "pressure", "vx", "vy", "vz", "Bx", "By", "Bz")
+        outer = np.array([cfg.f("implode", n + "_outer", d) for n, d in zip(names, (1.0, 1.0, 0, 0, 0, 0, 0, 0))])
+        inner = np.array([cfg.f("implode", n + "_inner", d) for n, d in zip(names, (0.125, 0.14, 0, 0, 0, 0, 0, 0))])
+        L.orc2d_init_implode(C.byref(p), _dp(outer), _dp(inner), cfg.i("implode", "shape_region", 0), _dp(U))
+    elif problem == "wave":
+        raise ValueError("InitWaveFunctor2D_MHD is an empty functor in the reference (MHDInitFunctors2D.h:950-980): no 2-D wave")
     else:
         L.orc2d_init_orszag_tang(C.byref(p), _dp(U))
 

@@ -535,14 +535,38 @@ void init_kelvin_helmholtz_2d(const HydroParams &p, const KHParams &kh, DataArra
     }
 }
 
+void init_implode_2d(const HydroParams &p, const ImplodeParams &ip, DataArray3dHost &U) {
+  const CellCoords cc{p};
+  const double gamma0 = p.settings.gamma0;
+  for (int j = 0; j < p.jsize; ++j)
+    for (int i = 0; i < p.isize; ++i) {
+      const double x = cc.x(i), y = cc.y(j);
+      bool outer;
+      if (ip.shape == 1) outer = x + y > 0.5 && x + y < 2.5;
+      else outer = x + y > (p.xmin + p.xmax) / 2. + p.ymin;
+      const double rho = outer ? ip.rho_out : ip.rho_in, pr = outer ? ip.p_out : ip.p_in;
+      const double u = outer ? ip.u_out : ip.u_in, v = outer ? ip.v_out : ip.v_in;
+      const double bx = outer ? ip.Bx_out : ip.Bx_in, by = outer ? ip.By_out : ip.By_in;
+      U(i, j, 0, ID) = rho;
+      U(i, j, 0, IP) = pr / (gamma0 - 1.0) + 0.5 * rho * (u * u + v * v) + 0.5 * (bx * bx + by * by);
+      U(i, j, 0, IU) = u;  // velocities in the momentum slots, as in the reference
+      U(i, j, 0, IV) = v;
+      U(i, j, 0, IW) = 0.0;
+      U(i, j, 0, IA) = bx;
+      U(i, j, 0, IB) = by;
+      U(i, j, 0, IC) = 0.0;
+    }
+}
+
 std::string init_problem_2d(const HydroParams &params, ConfigMap &configMap, const std::string &problem, DataArray3dHost &U) {
   if (problem == "orszag_tang") { init_orszag_tang_2d(params, U); return problem; }
   if (problem == "blast") { init_blast_2d(params, BlastParams(configMap), U); return problem; }
   if (problem == "rotor") { init_rotor_2d(params, RotorParams(configMap), U); return problem; }
   if (problem == "field_loop" || problem == "field loop") { init_field_loop_2d(params, FieldLoopParams(configMap), U); return problem; }
   if (problem == "kelvin_helmholtz") { init_kelvin_helmholtz_2d(params, KHParams(configMap), U); return problem; }
-  // implode and wave exist in the reference's 2-D dispatch but are not built here; like its final else
-  // (SolverMHDMuscl.h:701-709) anything else falls back to Orszag-Tang with a message
+  if (problem == "implode") { init_implode_2d(params, ImplodeParams(configMap), U); return problem; }
+  // "wave" is in the reference's 2-D dispatch, but InitWaveFunctor2D_MHD is an empty functor (MHDInitFunctors2D.h:950-980:
+  // an all-zero state); like the reference's final else (SolverMHDMuscl.h:701-709) it falls back to Orszag-Tang with a message
   std::cout << "Problem : " << problem << " is not recognized / implemented." << std::endl;
   std::cout << "Use default - Orszag-Tang vortex" << std::endl;
   init_orszag_tang_2d(params, U);

@@ -59,7 +59,8 @@ void init_blast_2d(const HydroParams &params, const BlastParams &b, DataArray3dH
 void init_rotor_2d(const HydroParams &params, const RotorParams &rp, DataArray3dHost &U);              // MHDInitFunctors2D.h:588-668
 void init_field_loop_2d(const HydroParams &params, const FieldLoopParams &fl, DataArray3dHost &U);     // MHDInitFunctors2D.h:715-945
 void init_kelvin_helmholtz_2d(const HydroParams &params, const KHParams &kh, DataArray3dHost &U);      // MHDInitFunctors2D.h:394-583
-// SolverMHDMuscl<2>::init dispatch; implode and wave are not built in 2-D (message + Orszag-Tang, like an unknown name)
+void init_implode_2d(const HydroParams &params, const ImplodeParams &ip, DataArray3dHost &U);           // MHDInitFunctors2D.h:36-139
+// SolverMHDMuscl<2>::init dispatch; the reference's 2-D wave functor is empty: message + Orszag-Tang, like an unknown name
 std::string init_problem_2d(const HydroParams &params, ConfigMap &configMap, const std::string &problem, DataArray3dHost &U);
 
 class SolverMHDMusclCuda3D : public SolverBase {

@@ -73,6 +73,7 @@ CASES = {
                           extra="[rotor]\nr0=0.1\nr1=0.115\nu0=1.0\np0=1.5\n"),
     "fieldloop2d_24x12": dict(n=(24, 12), nstepmax=6, problem="field_loop", cfl=0.4, bounds=(-1.0, 1.0, -0.5, 0.5),
                               extra="[FieldLoop]\nradius=0.3\namplitude=0.001\nvflow=3\ndensity_in=1\n"),
+    "implode2d_16x16": dict(n=(16, 16), nstepmax=6, problem="implode", bc=1, extra="[implode]\nBx_outer=0.3\nBy_inner=0.2\nvx_inner=0.1\n"),
     "kh2d_robertson_16x16": dict(n=(16, 16), nstepmax=5, problem="kelvin_helmholtz", extra="[KH]\nd_in=2.0\n"),
     "kh2d_sine_16x12": dict(n=(16, 12), nstepmax=5, problem="kelvin_helmholtz", bc=[3, 3, 2, 2],
                             extra="[KH]\nperturbation_sine=true\nperturbation_sine_robertson=false\nd_in=2.0\nw0=0.05\nmode=4\n"),
