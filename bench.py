@@ -286,7 +286,8 @@ def run_ours(args):
     ini = make_ini(n, world, 10 ** 9)
     p, t_end, _ = ppk.params_from_ini(ini, rank_z=rank, device=local, exact=exact)
     solver = ppk.Mhd3d(p)
-    solver.set_pipeline(args.pipeline)
+    if args.pipeline != "auto":
+        solver.set_pipeline(args.pipeline)
     # a dedicated (non-default) torch stream: the C ABI launches on it, torch.cuda.Event records on it
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -394,7 +395,8 @@ def run_ours(args):
     e2e_solvers, e2e_streams = [solver], [stream]
     for _ in range(depth - 1):
         s2 = ppk.Mhd3d(p)
-        s2.set_pipeline(args.pipeline)
+        if args.pipeline != "auto":
+            s2.set_pipeline(args.pipeline)
         st2 = torch.cuda.Stream()
         s2.set_stream(st2.cuda_stream)
         s2.set_time(0.0, t_end, 0)
@@ -487,7 +489,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=256, help="cells per axis per GPU")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
-    ap.add_argument("--pipeline", default="unfused", choices=["fused", "fused_split", "unfused", "streamed"])
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "tiled", "fused", "fused_split", "unfused", "streamed"],
+                    help="auto = the handle's default (tiled on one slab, unfused on decomposed runs)")
     ap.add_argument("--ref-n", type=int, default=128, help="grid of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=9)
     ap.add_argument("--e2e-depth", type=int, default=3, help="solver handles (batches) in flight in the e2e leg at N=1")

@@ -136,7 +136,7 @@ int ppk_mhd3d_halo_plan(const ppk_mhd3d_params *params, int capacity, ppk_halo_m
  * handle's own non-blocking stream. */
 int ppk_mhd3d_set_stream(ppk_mhd3d *handle, void *cuda_stream);
 /* Kernel schedule of one step (results are identical, bit for bit in exact mode):
- *   PPK_PIPELINE_UNFUSED (default, the fastest measured on B200): ghost fill | primitives + CFL | edge E +
+ *   PPK_PIPELINE_UNFUSED (round 1's default; the schedule of decomposed runs): ghost fill | primitives + CFL | edge E +
  *       face-B slopes | Hancock trace | one TMA-staged kernel per flux direction and EMF component | update;
  *       stores Fluxes_x|y|z and Emf like the reference's v0 (what ppk_mhd3d_debug_array exposes);
  *   PPK_PIPELINE_FUSED: after the trace, ONE z-marching consumer kernel = HLLD fluxes x,y,z + edge EMFs z,y,x +
@@ -145,8 +145,12 @@ int ppk_mhd3d_set_stream(ppk_mhd3d *handle, void *cuda_stream);
  *   PPK_PIPELINE_FUSED_SPLIT: that consumer as two kernels (fluxes + hydro update, EMFs + CT update);
  *   PPK_PIPELINE_STREAMED: after the trace, one z-marching kernel whose threads exchange one-sided states (warp
  *       shuffles / shared memory) solves the three HLLD fluxes of every cell and applies the hydro update (no flux
- *       array), then the TMA-staged EMF kernels and the CT update of the field. */
-enum ppk_pipeline { PPK_PIPELINE_UNFUSED = 0, PPK_PIPELINE_FUSED = 1, PPK_PIPELINE_FUSED_SPLIT = 2, PPK_PIPELINE_STREAMED = 3 };
+ *       array), then the TMA-staged EMF kernels and the CT update of the field.
+ *   PPK_PIPELINE_TILED (default where available: even nx >= 32, mz = 1): ghost fill | CFL reduction (reads U only) |
+ *       ONE fused producer kernel = primitives + edge electric field + face-field slopes + hydro slopes + Hancock trace
+ *       on TMA-staged U tiles marching in z (Q and E never reach HBM) | ONE launch with the six flux / EMF tasks ordered
+ *       (y-slab, plane, task, tile) so that the basis is read from HBM once and from the L2 five times | update. */
+enum ppk_pipeline { PPK_PIPELINE_UNFUSED = 0, PPK_PIPELINE_FUSED = 1, PPK_PIPELINE_FUSED_SPLIT = 2, PPK_PIPELINE_STREAMED = 3, PPK_PIPELINE_TILED = 4 };
 int ppk_mhd3d_set_pipeline(ppk_mhd3d *handle, int pipeline);
 /* Per-kernel CUDA-event timing (replaces the coarse timers of SolverBase.h:35-42 for profiling).
  * While enabled every kernel launch is bracketed by events on the launch stream. */

@@ -300,7 +300,7 @@ class Mhd3d:
     def set_stream(self, stream_ptr):
         _check(self.L.ppk_mhd3d_set_stream(self.h, stream_ptr))
 
-    PIPELINES = {"unfused": 0, "fused": 1, "fused_split": 2, "streamed": 3}
+    PIPELINES = {"unfused": 0, "fused": 1, "fused_split": 2, "streamed": 3, "tiled": 4}
 
     def set_pipeline(self, name: str):
         _check(self.L.ppk_mhd3d_set_pipeline(self.h, self.PIPELINES[name]))

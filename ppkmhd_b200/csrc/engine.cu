@@ -87,7 +87,8 @@ int load_nccl() {
 
 const char *const kKernelNames[KK_COUNT] = {"boundary", "prim_dt", "finalize_dt", "elec_dbf", "trace",
                                             "flux_x", "flux_y", "flux_z", "emf_z", "emf_y", "emf_x",
-                                            "update", "diagnostics", "halo_exchange", "consume", "hydro", "update_ct"};
+                                            "update", "diagnostics", "halo_exchange", "consume", "hydro", "update_ct",
+                                            "dt_only", "producer", "riemann_all"};
 
 }  // namespace
 
@@ -103,6 +104,7 @@ struct ppk_mhd3d {
   StepState *st = nullptr;
   double *diag = nullptr;
   void *tma = nullptr;  // tensor maps for the TMA-staged flux / EMF kernels
+  void *prod = nullptr; // tensor maps of U / U2 for the fused producer (tiled pipeline)
   long long bytes = 0;
   long launches = 0;
   long host_iteration = 0;  // parity selects U / U2 like SolverMHDMuscl::godunov_unsplit (SolverMHDMuscl.h:793-805)
@@ -261,10 +263,51 @@ int boundaries_and_primitives(ppk_mhd3d *h, double *U, bool with_prim, bool defe
   return 0;
 }
 
+// The tiled pipeline (round 2): ghost fill | CFL reduction (reads U only) | dt | fused producer U -> basis + face-field
+// slopes (TMA-staged, z-marching; Q and the edge electric field stay on chip) | the six flux / EMF tasks as one
+// L2-ordered launch | update. Same arithmetic, same results as the unfused pipeline, bit for bit in exact mode.
+int enqueue_step_tiled(ppk_mhd3d *h) {
+  const GridParams &g = h->g;
+  cudaStream_t s = h->stream;
+  double *Uin = h->cur(), *Uout = h->nxt();
+  if (h->exch_lo || h->exch_hi) return fail(PPK_ERR_STATE, "the tiled pipeline is single-slab for now");
+  if (!h->F[0] || !h->EMF) {
+    if (int rc = ppk_mhd3d_set_pipeline(h, PPK_PIPELINE_TILED)) return rc;
+  }
+  if (int rc = boundaries_and_primitives(h, Uin, false)) return rc;
+  { Scope sc(h, KK_DT_ONLY, s); h->kt->dt_only(g, Uin, h->st, g.gw, g.nz + g.gw, s); }
+  { Scope sc(h, KK_FINALIZE_DT, s); h->kt->finalize_dt(g, h->st, s); }
+  {
+    Scope sc(h, KK_PRODUCER, s);
+    if (h->kt->producer(g, h->st, h->prod, Uin, h->BASIS, h->DBF, 2, g.ksize - 2, s) != 0)
+      return fail(PPK_ERR_STATE, "fused producer unavailable for this handle");
+  }
+  {
+    Scope sc(h, KK_RIEMANN_ALL, s);
+    if (h->kt->riemann_all(g, h->BASIS, h->DBF, h->F[0], h->F[1], h->F[2], h->EMF, h->tma, s) != 0) {
+      // PPK_RALL=0: the six tasks as six launches (A/B of the L2-ordered launch)
+      h->kt->flux(g, 0, h->BASIS, h->F[0], h->tma, s);
+      h->kt->flux(g, 1, h->BASIS, h->F[1], h->tma, s);
+      h->kt->flux(g, 2, h->BASIS, h->F[2], h->tma, s);
+      h->kt->emf(g, 2, h->BASIS, h->DBF, h->EMF, h->tma, s);
+      h->kt->emf(g, 1, h->BASIS, h->DBF, h->EMF, h->tma, s);
+      h->kt->emf(g, 0, h->BASIS, h->DBF, h->EMF, h->tma, s);
+      h->launches += 5;
+    }
+  }
+  { Scope sc(h, KK_UPDATE, s); h->kt->update(g, h->st, Uin, Uout, h->F[0], h->F[1], h->F[2], h->EMF, 0, g.ksize, s); }
+  h->kt->advance_time(h->st, s);
+  h->launches += 1;
+  h->host_iteration += 1;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int enqueue_step(ppk_mhd3d *h) {
   const GridParams &g = h->g;
   cudaStream_t s = h->stream;
   double *Uin = h->cur(), *Uout = h->nxt();
+  if (h->pipeline == PPK_PIPELINE_TILED) return enqueue_step_tiled(h);
   const bool multi = h->comm && h->nranks > 1 && h->defer_dt;
   if (int rc = boundaries_and_primitives(h, Uin, true, multi)) return rc;
   if (multi) {
@@ -418,6 +461,13 @@ int ppk_mhd3d_create(const ppk_mhd3d_params *p, ppk_mhd3d **out) {
     return rc;
   }
   h->tma = h->kt->tma_create(g, h->BASIS, h->DBF);
+  h->prod = h->kt->prod_create(g, h->U[0], h->U[1]);
+  // default schedule: the tiled pipeline where its TMA boxes exist (even isize, nx >= 32) and the slab has no z exchange
+  if (h->tma && h->prod && p->mz == 1) h->pipeline = PPK_PIPELINE_TILED;
+  if (const char *e = getenv("PPK_PIPELINE")) {
+    const int want = atoi(e);
+    if (want != PPK_PIPELINE_TILED || (h->tma && h->prod && p->mz == 1)) h->pipeline = want;
+  }
   CUDA_TRY(cudaMalloc((void **)&h->st, sizeof(StepState)));
   StepState st0{};
   st0.t = 0.0; st0.t_end = 1e300; st0.dt = 0.0; st0.inv_dt_bits = 0ull; st0.iteration = 0;
@@ -436,6 +486,7 @@ int ppk_mhd3d_destroy(ppk_mhd3d *h) {
     if (p) cudaFree(p);
   if (h->st) cudaFree(h->st);
   if (h->tma && h->kt) h->kt->tma_destroy(h->tma);
+  if (h->prod && h->kt) h->kt->prod_destroy(h->prod);
   for (auto &p : h->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
   for (auto e : h->pool) cudaEventDestroy(e);
   if (h->ev_xy) cudaEventDestroy(h->ev_xy);
@@ -805,9 +856,11 @@ int ppk_mhd3d_set_stream(ppk_mhd3d *h, void *cuda_stream) {
 
 int ppk_mhd3d_set_pipeline(ppk_mhd3d *h, int pipeline) {
   if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
-  if (pipeline < PPK_PIPELINE_UNFUSED || pipeline > PPK_PIPELINE_STREAMED) return fail(PPK_ERR_INVALID_ARGUMENT, "unknown pipeline");
+  if (pipeline < PPK_PIPELINE_UNFUSED || pipeline > PPK_PIPELINE_TILED) return fail(PPK_ERR_INVALID_ARGUMENT, "unknown pipeline");
+  if (pipeline == PPK_PIPELINE_TILED && (!h->tma || !h->prod || h->params.mz != 1))
+    return fail(PPK_ERR_UNSUPPORTED, "the tiled pipeline needs an even nx >= 32 (16-byte TMA rows) and a single slab (mz = 1)");
   DeviceGuard guard(h->device);
-  if (pipeline == PPK_PIPELINE_UNFUSED && !h->F[0]) {  // flux / EMF arrays exist only for the unfused pipeline
+  if ((pipeline == PPK_PIPELINE_UNFUSED || pipeline == PPK_PIPELINE_TILED) && !h->F[0]) {  // flux / EMF arrays exist only for the unfused pipeline
     int rc = 0;
     const long long n = h->g.ncell;
     if ((rc = alloc_doubles(h, &h->F[0], NFLUX * n)) || (rc = alloc_doubles(h, &h->F[1], NFLUX * n)) ||
@@ -865,6 +918,8 @@ int ppk_mhd3d_debug_array(ppk_mhd3d *h, const char *name, double *host_out, int 
   else if (s == "Emf") { src = h->EMF; nc = NEMF; }
   else return fail(PPK_ERR_INVALID_ARGUMENT, "unknown array name " + s);
   if (!src) return fail(PPK_ERR_STATE, s + " exists only in the unfused pipeline (ppk_mhd3d_set_pipeline)");
+  if (h->pipeline == PPK_PIPELINE_TILED && (s == "Q" || s == "ElecField"))
+    return fail(PPK_ERR_STATE, s + " never reaches device memory in the tiled pipeline (ppk_mhd3d_set_pipeline)");
   // x periodic: the launchers skip the column i = nx+gw of the x-fluxes and of the z- / y-EMFs (the update reads the
   // bit-identical column i = gw); complete the arrays for the caller
   if (s == "Fluxes_x") h->kt->wrap_x_column(h->g, h->F[0], NFLUX, h->stream);

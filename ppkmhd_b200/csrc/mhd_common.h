@@ -52,7 +52,7 @@ struct StepState {
 // kernel kinds, for the per-kernel timers
 enum KernelKind {
   KK_BOUNDARY = 0, KK_PRIM_DT, KK_FINALIZE_DT, KK_ELEC_DBF, KK_TRACE,
-  KK_FLUX_X, KK_FLUX_Y, KK_FLUX_Z, KK_EMF_Z, KK_EMF_Y, KK_EMF_X, KK_UPDATE, KK_DIAG, KK_HALO, KK_CONSUME, KK_HYDRO, KK_UPDATE_CT, KK_COUNT
+  KK_FLUX_X, KK_FLUX_Y, KK_FLUX_Z, KK_EMF_Z, KK_EMF_Y, KK_EMF_X, KK_UPDATE, KK_DIAG, KK_HALO, KK_CONSUME, KK_HYDRO, KK_UPDATE_CT, KK_DT_ONLY, KK_PRODUCER, KK_RIEMANN_ALL, KK_COUNT
 };
 
 // Launchers exported by each arithmetic build (mhd_kernels.cu compiled twice).
@@ -92,6 +92,16 @@ struct KernelTable {
   void (*flux_emf2d)(const GridParams &g, const double *S, double *FX, double *FY, double *EMF, cudaStream_t s);
   void (*update2d)(const GridParams &g, const StepState *st, const double *Uin, double *Uout, const double *FX,
                    const double *FY, const double *EMF, cudaStream_t s);
+  // tiled pipeline (round 2): CFL reduction alone over the planes [k0, k1); fused producer U -> basis + face-field
+  // slopes of the planes [k0, k1) (context: tensor maps of the two conservative arrays; returns -1 if unusable);
+  // the six flux / EMF tasks as one L2-ordered launch (returns -1 if unusable)
+  void (*dt_only)(const GridParams &g, const double *U, StepState *st, int k0, int k1, cudaStream_t s);
+  void *(*prod_create)(const GridParams &g, const double *U0, const double *U1);
+  void (*prod_destroy)(void *ctx);
+  int (*producer)(const GridParams &g, const StepState *st, const void *ctx, const double *U, double *BASIS, double *DBF,
+                  int k0, int k1, cudaStream_t s);
+  int (*riemann_all)(const GridParams &g, const double *BASIS, const double *DBF, double *F0, double *F1, double *F2,
+                     double *EMF, const void *tma, cudaStream_t s);
 };
 
 const KernelTable *kernel_table_exact();

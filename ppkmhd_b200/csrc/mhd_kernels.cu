@@ -17,6 +17,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #ifndef PPK_EXACT
 #  error "compile with -DPPK_EXACT=0 or 1"
 #endif
@@ -726,6 +728,7 @@ DEV double warp_max(double v) {
 // fused with ComputeDtFunctor3D_MHD (MHDRunFunctors3D.h:16-83, find_speed_info<3> mhd_utils.h:319-366):
 // Q is written on [0,size-1)^3 and the CFL max is reduced over interior cells with warp shuffles,
 // one shared-memory stage and one 64-bit atomicMax per block (positive doubles order like their bits).
+template <bool WRITEQ>
 __global__ void __launch_bounds__(256) k_prim_dt(const GridParams g, const double *__restrict__ U, double *__restrict__ Q,
                                                  StepState *st, int k0) {
   const int k = k0 + blockIdx.y;
@@ -758,8 +761,10 @@ __global__ void __launch_bounds__(256) k_prim_dt(const GridParams g, const doubl
     const double eint = (ue - emag) * ir - eken;
 #endif
     const double p = vmax((g.gamma0 - 1.0) * r * eint, r * g.smallp);
-    Q[c + ID * N] = r; Q[c + IP * N] = p; Q[c + IU * N] = u; Q[c + IV * N] = v; Q[c + IW * N] = w;
-    Q[c + IA * N] = A; Q[c + IB * N] = B; Q[c + IC * N] = C;
+    if (WRITEQ) {
+      Q[c + ID * N] = r; Q[c + IP * N] = p; Q[c + IU * N] = u; Q[c + IV * N] = v; Q[c + IW * N] = w;
+      Q[c + IA * N] = A; Q[c + IB * N] = B; Q[c + IC * N] = C;
+    }
     const int gw = g.gw;
     if ((int)i >= gw && (int)i < g.isize - gw && (int)j >= gw && (int)j < g.jsize - gw && k >= gw && k < g.ksize - gw) {
 #if PPK_EXACT
@@ -1235,33 +1240,23 @@ DEV Corner edge_state_smem(const GridParams &g, const double *__restrict__ sm, i
   return c;
 }
 
-template <int E, bool SLAB>
-__global__ void __launch_bounds__(EmfCfg<E>::THREADS, EmfCfg<E>::MINB)
-  k_emf_tma(const GridParams g, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapD,
-            double *__restrict__ EMF, const int yslab, const unsigned ymagic) {
-  using Cfg = EmfCfg<E>;
+// One tile of edges of direction E: stage the 19 component boxes, wait, solve, store. `bar` is a CTA-shared mbarrier.
+template <int E, class Cfg = EmfCfg<E>>
+DEV void emf_tile_body(const GridParams &g, const CUtensorMap *mapB, const CUtensorMap *mapD, double *__restrict__ EMF,
+                       double *sm, unsigned long long *bar, const int i0, const int j0, const int k0) {
   constexpr int D1 = (E + 1) % 3, D2 = (E + 2) % 3;
-  extern __shared__ __align__(128) double sm[];
-  __shared__ unsigned long long bar;
   const int tid = threadIdx.x;
   const int tx = tid % Cfg::TX, ty = (tid / Cfg::TX) % Cfg::TY, tz = tid / (Cfg::TX * Cfg::TY);
-  // grid (x-tiles, y-tiles, z-tiles) when one y-slab covers the plane (!SLAB); otherwise x = x-tiles,
-  // y = (z-tile, y-tile inside a slab of `yslab` tiles), z = slab -- see slab_rows()
-  // (blockIdx.y / yslab by multiply-high: exact for 16-bit operands, keeps the prologue off the slow integer division)
-  const unsigned ydiv = SLAB ? __umulhi(blockIdx.y, ymagic) : 0u;
-  const int by = SLAB ? blockIdx.z * yslab + (int)(blockIdx.y - ydiv * yslab) : blockIdx.y;
-  const int bz = SLAB ? (int)ydiv : blockIdx.z;
-  const int i0 = g.gw + blockIdx.x * Cfg::TX, j0 = g.gw + by * Cfg::TY, k0 = g.gw + bz * Cfg::TZ;
-  if (SLAB && j0 >= g.gw + g.ny + (E == 1 ? 0 : 1)) return;  // the last slab may be short
-  if (tid == 0) mbar_init(&bar, 1);
+  if (tid == 0) mbar_init(bar, 1);
   __syncthreads();
+  if (tid >= Cfg::THREADS) return;  // (a CTA wider than the tile: k_riemann_all's x-edge task)
   if (tid == 0) {
-    mbar_expect_tx(&bar, Cfg::NSLOT * Cfg::BOX * 8);
+    mbar_expect_tx(bar, Cfg::NSLOT * Cfg::BOX * 8);
 #pragma unroll
     for (int s = 0; s < Cfg::NSLOT; ++s)
-      tma_load_box(sm + s * Cfg::SLOT, s < 17 ? &mapB : &mapD, i0 - Cfg::HX, j0 - Cfg::HY, k0 - Cfg::HZ, emf_slot_comp<E>(s), &bar);
+      tma_load_box(sm + s * Cfg::SLOT, s < 17 ? mapB : mapD, i0 - Cfg::HX, j0 - Cfg::HY, k0 - Cfg::HZ, emf_slot_comp<E>(s), bar);
   }
-  mbar_wait(&bar, 0);
+  mbar_wait(bar, 0);
   const int i = i0 + tx, j = j0 + ty, k = k0 + tz;
   // edges the CT update reads: index <= n+gw along d1 and d2, interior along the edge direction
   const int nj = g.ny + (E == 1 ? 0 : 1), nk = g.nz + (E == 2 ? 0 : 1);
@@ -1273,6 +1268,24 @@ __global__ void __launch_bounds__(EmfCfg<E>::THREADS, EmfCfg<E>::MINB)
   const Corner LT = edge_state_smem<E, Cfg>(g, sm, o - st[D2], false, true);
   const Corner LB = edge_state_smem<E, Cfg>(g, sm, o, false, false);
   ST(EMF[cidx(g, i, j, k) + (2 - E) * g.ncell], emf_from_corners(g, RT, RB, LT, LB));
+}
+
+template <int E, bool SLAB>
+__global__ void __launch_bounds__(EmfCfg<E>::THREADS, EmfCfg<E>::MINB)
+  k_emf_tma(const GridParams g, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapD,
+            double *__restrict__ EMF, const int yslab, const unsigned ymagic) {
+  using Cfg = EmfCfg<E>;
+  extern __shared__ __align__(128) double sm[];
+  __shared__ unsigned long long bar;
+  // grid (x-tiles, y-tiles, z-tiles) when one y-slab covers the plane (!SLAB); otherwise x = x-tiles,
+  // y = (z-tile, y-tile inside a slab of `yslab` tiles), z = slab -- see slab_rows()
+  // (blockIdx.y / yslab by multiply-high: exact for 16-bit operands, keeps the prologue off the slow integer division)
+  const unsigned ydiv = SLAB ? __umulhi(blockIdx.y, ymagic) : 0u;
+  const int by = SLAB ? blockIdx.z * yslab + (int)(blockIdx.y - ydiv * yslab) : blockIdx.y;
+  const int bz = SLAB ? (int)ydiv : blockIdx.z;
+  const int i0 = g.gw + blockIdx.x * Cfg::TX, j0 = g.gw + by * Cfg::TY, k0 = g.gw + bz * Cfg::TZ;
+  if (SLAB && j0 >= g.gw + g.ny + (E == 1 ? 0 : 1)) return;  // the last slab may be short
+  emf_tile_body<E>(g, &mapB, &mapD, EMF, sm, &bar, i0, j0, k0);
 }
 
 // component staged in slot s of the flux kernel: 0-6 q (r,p,un,t1,t2,b1,b2), 7-13 their slopes along D,
@@ -1288,32 +1301,22 @@ DEV constexpr int flux_slot_comp(int s) {
   return BFACE + D;
 }
 
-template <int D, bool SLAB, int RS>
-__global__ void __launch_bounds__(FluxCfg<D>::THREADS, FluxCfg<D>::MINB)
-  k_flux_tma(const GridParams g, const __grid_constant__ CUtensorMap mapB, double *__restrict__ F, const int yslab,
-             const unsigned ymagic) {
+// One tile of faces of direction D: stage the 15 component boxes, wait, solve, store.
+template <int D, int RS>
+DEV void flux_tile_body(const GridParams &g, const CUtensorMap *mapB, double *__restrict__ F, double *sm,
+                        unsigned long long *bar, const int i0, const int j0, const int k0) {
   using Cfg = FluxCfg<D>;
-  extern __shared__ __align__(128) double sm[];
-  __shared__ unsigned long long bar;
   const int tid = threadIdx.x;
   const int tx = tid % Cfg::TX, ty = (tid / Cfg::TX) % Cfg::TY, tz = tid / (Cfg::TX * Cfg::TY);
-  // grid (x-tiles, y-tiles, z-tiles) when one y-slab covers the plane (!SLAB); otherwise x = x-tiles,
-  // y = (z-tile, y-tile inside a slab of `yslab` tiles), z = slab -- see slab_rows()
-  // (blockIdx.y / yslab by multiply-high: exact for 16-bit operands, keeps the prologue off the slow integer division)
-  const unsigned ydiv = SLAB ? __umulhi(blockIdx.y, ymagic) : 0u;
-  const int by = SLAB ? blockIdx.z * yslab + (int)(blockIdx.y - ydiv * yslab) : blockIdx.y;
-  const int bz = SLAB ? (int)ydiv : blockIdx.z;
-  const int i0 = g.gw + blockIdx.x * Cfg::TX, j0 = g.gw + by * Cfg::TY, k0 = g.gw + bz * Cfg::TZ;
-  if (SLAB && j0 >= g.gw + g.ny + (D == 1 ? 1 : 0)) return;  // the last slab may be short
-  if (tid == 0) mbar_init(&bar, 1);
+  if (tid == 0) mbar_init(bar, 1);
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(&bar, Cfg::NSLOT * Cfg::BOX * 8);
+    mbar_expect_tx(bar, Cfg::NSLOT * Cfg::BOX * 8);
 #pragma unroll
     for (int s = 0; s < Cfg::NSLOT; ++s)
-      tma_load_box(sm + s * Cfg::SLOT, &mapB, i0 - Cfg::HX, j0 - Cfg::HY, k0 - Cfg::HZ, flux_slot_comp<D>(s), &bar);
+      tma_load_box(sm + s * Cfg::SLOT, mapB, i0 - Cfg::HX, j0 - Cfg::HY, k0 - Cfg::HZ, flux_slot_comp<D>(s), bar);
   }
-  mbar_wait(&bar, 0);
+  mbar_wait(bar, 0);
   const int i = i0 + tx, j = j0 + ty, k = k0 + tz;
   const int nj = g.ny + (D == 1 ? 1 : 0), nk = g.nz + (D == 2 ? 1 : 0);
   if (j >= g.gw + nj || k >= g.gw + nk) return;
@@ -1342,6 +1345,79 @@ __global__ void __launch_bounds__(FluxCfg<D>::THREADS, FluxCfg<D>::MINB)
   const long long N = g.ncell;
   double *Fo = F + cidx(g, i, j, k);
   ST(Fo[0 * N], fd); ST(Fo[1 * N], fp); ST(Fo[2 * N], fu); ST(Fo[3 * N], fv); ST(Fo[4 * N], fw);
+}
+
+template <int D, bool SLAB, int RS>
+__global__ void __launch_bounds__(FluxCfg<D>::THREADS, FluxCfg<D>::MINB)
+  k_flux_tma(const GridParams g, const __grid_constant__ CUtensorMap mapB, double *__restrict__ F, const int yslab,
+             const unsigned ymagic) {
+  using Cfg = FluxCfg<D>;
+  extern __shared__ __align__(128) double sm[];
+  __shared__ unsigned long long bar;
+  // grid (x-tiles, y-tiles, z-tiles) when one y-slab covers the plane (!SLAB); otherwise x = x-tiles,
+  // y = (z-tile, y-tile inside a slab of `yslab` tiles), z = slab -- see slab_rows()
+  // (blockIdx.y / yslab by multiply-high: exact for 16-bit operands, keeps the prologue off the slow integer division)
+  const unsigned ydiv = SLAB ? __umulhi(blockIdx.y, ymagic) : 0u;
+  const int by = SLAB ? blockIdx.z * yslab + (int)(blockIdx.y - ydiv * yslab) : blockIdx.y;
+  const int bz = SLAB ? (int)ydiv : blockIdx.z;
+  const int i0 = g.gw + blockIdx.x * Cfg::TX, j0 = g.gw + by * Cfg::TY, k0 = g.gw + bz * Cfg::TZ;
+  if (SLAB && j0 >= g.gw + g.ny + (D == 1 ? 1 : 0)) return;  // the last slab may be short
+  flux_tile_body<D, RS>(g, &mapB, F, sm, &bar, i0, j0, k0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// All six Riemann tasks of the step in ONE launch, ordered for the L2: the grid is one-dimensional and CTAs are
+// dispatched in the order (y-slab, z-plane, task, tile), so the 38 basis / slope numbers of a plane are fetched from
+// HBM by the first task that touches them and come out of the 126 MB L2 for the five others (and for the z-halo of
+// the next plane). Launched one kernel per task, the same boxes came from HBM 3.3 times (every launch sweeps an array
+// far larger than the L2). CTAs that are resident together mostly run the same task (a task-plane is about one wave),
+// which keeps the instruction cache warm. Every task uses 32 x 4 x 1 tiles: the bodies are those of k_flux_tma /
+// k_emf_tma.
+// ---------------------------------------------------------------------------------------------
+struct RiemannPlan {
+  int ntx, nrows, rows;  // x tiles; rows of faces / edges (ny+1); rows per y-slab (a multiple of 12)
+  unsigned per_task4, per_task3, per_plane, per_slab;
+};
+struct RiemannMaps {
+  CUtensorMap fluxB[3], emfB[3], emfD[3];
+};
+// x-edges inside k_riemann_all: 32 x 3 tiles (their boxes span two planes and one extra row: 34 x 4 x 2 cells x 19
+// components = 41 KB like the y-edge boxes), so that every task fits five CTAs per SM
+struct EmfXCfg3 : TileCfg<3, 1, 1, 1, 1, 19, 5> {};
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
+constexpr int RALL_SMEM = cmax(cmax(EmfXCfg3::SMEM_BYTES, EmfCfg<1>::SMEM_BYTES), cmax(EmfCfg<2>::SMEM_BYTES, FluxCfg<2>::SMEM_BYTES));
+static_assert(EmfCfg<1>::THREADS == 128 && EmfCfg<2>::THREADS == 128 && FluxCfg<0>::THREADS == 128 && FluxCfg<1>::THREADS == 128 &&
+                FluxCfg<2>::THREADS == 128 && EmfCfg<1>::TY == 4 && EmfCfg<2>::TY == 4 && FluxCfg<0>::TY == 4 && FluxCfg<1>::TY == 4 &&
+                FluxCfg<2>::TY == 4 && EmfXCfg3::THREADS == 96,
+              "k_riemann_all assumes 32x4x1 tiles (32x3x1 for the x-edges)");
+static_assert(5 * (RALL_SMEM + 1024) <= 227 * 1024, "five CTAs of k_riemann_all per SM");
+
+template <int RS>
+__global__ void __launch_bounds__(128, 5)
+  k_riemann_all(const GridParams g, const RiemannPlan pl, const __grid_constant__ RiemannMaps maps, double *__restrict__ F0,
+                double *__restrict__ F1, double *__restrict__ F2, double *__restrict__ EMF) {
+  extern __shared__ __align__(128) double sm[];
+  __shared__ unsigned long long bar;
+  unsigned r = blockIdx.x;
+  const unsigned slab = r / pl.per_slab; r -= slab * pl.per_slab;
+  const unsigned plane = r / pl.per_plane; r -= plane * pl.per_plane;
+  unsigned task, th;  // th = tile height
+  if (r < 5u * pl.per_task4) { task = r / pl.per_task4; r -= task * pl.per_task4; th = 4; }
+  else { task = 5; r -= 5u * pl.per_task4; th = 3; }
+  const unsigned ty = r / (unsigned)pl.ntx, bx = r - ty * (unsigned)pl.ntx;
+  const int jrow = (int)(slab * pl.rows + ty * th);  // first row of the tile
+  if (jrow >= pl.nrows || jrow >= (int)(slab + 1) * pl.rows) return;
+  const int i0 = g.gw + (int)bx * 32, j0 = g.gw + jrow, k0 = g.gw + (int)plane;
+  const bool top = (int)plane == g.nz;  // only the z-faces and the x- / y-edges exist on the plane above the last cells
+  const bool last_row = jrow >= g.ny;   // only y-faces and z- / x-edges exist on the row above the last cells
+  switch (task) {
+    case 0: if (!top && !last_row) flux_tile_body<0, RS>(g, &maps.fluxB[0], F0, sm, &bar, i0, j0, k0); break;
+    case 1: if (!top) flux_tile_body<1, RS>(g, &maps.fluxB[1], F1, sm, &bar, i0, j0, k0); break;
+    case 2: if (!top) emf_tile_body<2>(g, &maps.emfB[2], &maps.emfD[2], EMF, sm, &bar, i0, j0, k0); break;
+    case 3: if (!last_row) flux_tile_body<2, RS>(g, &maps.fluxB[2], F2, sm, &bar, i0, j0, k0); break;
+    case 4: if (!last_row) emf_tile_body<1>(g, &maps.emfB[1], &maps.emfD[1], EMF, sm, &bar, i0, j0, k0); break;
+    default: emf_tile_body<0, EmfXCfg3>(g, &maps.emfB[0], &maps.emfD[0], EMF, sm, &bar, i0, j0, k0); break;
+  }
 }
 
 // Kokkos::deep_copy(data_out, data_in) (SolverMHDMuscl.cpp:477) + UpdateFunctor3D_MHD
@@ -1884,7 +1960,17 @@ static void l_prim_dt(const GridParams &g, const double *U, double *Q, StepState
   if (k1 <= k0) return;
   const int bs = 256;
   dim3 grid(cdiv((long long)g.isize * g.jsize, bs), k1 - k0);
-  k_prim_dt<<<grid, bs, 0, s>>>(g, U, Q, st, k0);
+  k_prim_dt<true><<<grid, bs, 0, s>>>(g, U, Q, st, k0);
+}
+// the CFL reduction alone (planes k in [k0, k1); only interior cells contribute): the tiled pipeline rebuilds the
+// primitives on chip and needs dt before its producer kernel starts
+static void l_dt_only(const GridParams &g, const double *U, StepState *st, int k0, int k1, cudaStream_t s) {
+  if (k0 < g.gw) k0 = g.gw;
+  if (k1 > g.ksize - g.gw) k1 = g.ksize - g.gw;
+  if (k1 <= k0) return;
+  const int bs = 256;
+  dim3 grid(cdiv((long long)g.isize * g.jsize, bs), k1 - k0);
+  k_prim_dt<false><<<grid, bs, 0, s>>>(g, U, nullptr, st, k0);
 }
 // The plane-sweeping kernels (grid x = cells of a k-plane, y = k) reuse the planes k-1, k, k+1 of their inputs from L2 --
 // as long as one k-plane of ALL their streams fits there. At 512^3 a plane of the trace kernel's 46 streams is 99 MB and
@@ -1924,6 +2010,7 @@ static void l_trace(const GridParams &g, const StepState *st, const double *U, c
 // ---- TMA tensor maps (host) ---------------------------------------------------------------------
 struct TmaCtx {
   CUtensorMap emfB[3], emfD[3], fluxB[3];
+  RiemannMaps rall;  // the same nine maps, as the single kernel parameter of k_riemann_all
 };
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1972,7 +2059,14 @@ static void *l_tma_create(const GridParams &g, const double *BASIS, const double
        cudaFuncSetAttribute(k_flux_tma<1, true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<1>::SMEM_BYTES) == cudaSuccess &&
        cudaFuncSetAttribute(k_flux_tma<2, true, RIEMANN_HLLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<2>::SMEM_BYTES) == cudaSuccess &&
        cudaFuncSetAttribute(k_flux_tma<2, true, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FluxCfg<2>::SMEM_BYTES) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(k_riemann_all<RIEMANN_HLLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, RALL_SMEM) == cudaSuccess &&
+       cudaFuncSetAttribute(k_riemann_all<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RALL_SMEM) == cudaSuccess;
   if (!ok) { delete c; return nullptr; }
+  for (int d = 0; d < 3; ++d) { c->rall.fluxB[d] = c->fluxB[d]; c->rall.emfB[d] = c->emfB[d]; c->rall.emfD[d] = c->emfD[d]; }
+  if (!encode_cfg<EmfXCfg3>(enc, &c->rall.emfB[0], g, BASIS, NBASIS) || !encode_cfg<EmfXCfg3>(enc, &c->rall.emfD[0], g, DBF, NDBF)) {
+    delete c;
+    return nullptr;
+  }
   return c;
 }
 static void l_tma_destroy(void *ctx) { delete (TmaCtx *)ctx; }
@@ -2065,6 +2159,50 @@ static void l_emf(const GridParams &g, int e, const double *BASIS, const double 
   else if (e == 1) launch_emf<1>(g, BASIS, DBF, EMF, (const TmaCtx *)tma, s);
   else launch_emf<2>(g, BASIS, DBF, EMF, (const TmaCtx *)tma, s);
 }
+// The six flux / EMF tasks in one L2-ordered launch (k_riemann_all); returns -1 when the TMA context is missing
+// (the caller then launches the tasks one by one). Columns beyond the last full 32-wide tile go through the plain
+// kernels, task by task, exactly like launch_flux / launch_emf.
+static int l_riemann_all(const GridParams &g, const double *BASIS, const double *DBF, double *F0, double *F1, double *F2,
+                         double *EMF, const void *tma_, cudaStream_t s) {
+  const TmaCtx *tma = (const TmaCtx *)tma_;
+  if (!tma) return -1;
+  static const int off = getenv("PPK_RALL") ? atoi(getenv("PPK_RALL")) == 0 : 0;
+  if (off) return -1;
+  const bool wrap = g.wrap_x && g.nx % 32 == 0;
+  int ntx = g.nx / 32;
+  if (!wrap && (g.nx + 1 - ntx * 32) < 8 && ntx > 1) --ntx;  // keep the left-over rows of the plain kernels coalesced
+  const int done = ntx * 32;
+  RiemannPlan pl;
+  pl.ntx = ntx;
+  pl.nrows = g.ny + 1;
+  // y-slabs: two planes (k-1, k) of the 38 numbers a slab of rows needs stay in the L2 while the six tasks run
+  static const int slab_mb = getenv("PPK_RALL_SLAB_MB") ? atoi(getenv("PPK_RALL_SLAB_MB")) : 40;
+  long long rows = ((long long)slab_mb << 20) / (2LL * 38 * g.isize * 8);
+  rows = rows / 12 * 12;
+  if (rows < 12) rows = 12;
+  if (rows >= pl.nrows - 12) rows = (pl.nrows + 11) / 12 * 12;  // no sliver slab
+  pl.rows = (int)rows;
+  const unsigned nslab = cdiv(pl.nrows, rows);
+  pl.per_task4 = (unsigned)ntx * (unsigned)(rows / 4);
+  pl.per_task3 = (unsigned)ntx * (unsigned)(rows / 3);
+  pl.per_plane = 5u * pl.per_task4 + pl.per_task3;
+  pl.per_slab = (unsigned)(g.nz + 1) * pl.per_plane;
+  const unsigned long long total = (unsigned long long)nslab * pl.per_slab;
+  if (total > 0x7FFFFFFFull || ntx < 1) return -1;
+  if (g.riemann == RIEMANN_HLLD) k_riemann_all<RIEMANN_HLLD><<<(unsigned)total, 128, RALL_SMEM, s>>>(g, pl, tma->rall, F0, F1, F2, EMF);
+  else k_riemann_all<-1><<<(unsigned)total, 128, RALL_SMEM, s>>>(g, pl, tma->rall, F0, F1, F2, EMF);
+  if (!wrap) {
+    const int bs = 128;
+    const int nif[3] = {g.nx + 1, g.nx, g.nx}, nie[3] = {g.nx, g.nx + 1, g.nx + 1};
+    if (done < nif[0]) k_flux<0, 5><<<dim3(cdiv((long long)(nif[0] - done) * g.ny, bs), g.nz), bs, 0, s>>>(g, BASIS, F0, done, nif[0] - done);
+    if (done < nif[1]) k_flux<1, 5><<<dim3(cdiv((long long)(nif[1] - done) * (g.ny + 1), bs), g.nz), bs, 0, s>>>(g, BASIS, F1, done, nif[1] - done);
+    if (done < nif[2]) k_flux<2, 5><<<dim3(cdiv((long long)(nif[2] - done) * g.ny, bs), g.nz + 1), bs, 0, s>>>(g, BASIS, F2, done, nif[2] - done);
+    if (done < nie[2]) k_emf<2, 5><<<dim3(cdiv((long long)(nie[2] - done) * (g.ny + 1), bs), g.nz), bs, 0, s>>>(g, BASIS, DBF, EMF, done, nie[2] - done);
+    if (done < nie[1]) k_emf<1, 5><<<dim3(cdiv((long long)(nie[1] - done) * g.ny, bs), g.nz + 1), bs, 0, s>>>(g, BASIS, DBF, EMF, done, nie[1] - done);
+    if (done < nie[0]) k_emf<0, 5><<<dim3(cdiv((long long)(nie[0] - done) * (g.ny + 1), bs), g.nz + 1), bs, 0, s>>>(g, BASIS, DBF, EMF, done, nie[0] - done);
+  }
+  return 0;
+}
 static void l_update(const GridParams &g, const StepState *st, const double *Uin, double *Uout, const double *Fx,
                      const double *Fy, const double *Fz, const double *EMF, int k0, int k1, cudaStream_t s) {
   if (k1 <= k0) return;
@@ -2136,6 +2274,7 @@ static void l_fastmath_selftest(int n, const double *x, double *rcp, double *sq,
   k_fastmath_selftest<<<(n + 255) / 256, 256, 0, s>>>(n, x, rcp, sq, rsq);
 }
 
+#include "mhd_prod.inc"
 #include "mhd2d_kernels.inc"
 
 static const KernelTable table = {
@@ -2146,6 +2285,7 @@ static const KernelTable table = {
 #endif
   l_boundary, l_prim_dt, l_finalize_dt, l_advance_time, l_elec_dbf, l_trace, l_flux, l_emf, l_update, l_diagnostics, l_fastmath_selftest, l_consume, l_tma_create, l_tma_destroy, l_hydro, l_update_ct, l_wrap_x_column,
   l2_boundary, l2_prim_dt, l2_trace, l2_flux_emf, l2_update,
+  l_dt_only, l_prod_create, l_prod_destroy, l_producer, l_riemann_all,
 };
 
 }  // namespace PPK_NS

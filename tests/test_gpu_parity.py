@@ -23,10 +23,12 @@ OT = "[OrszagTang]\nkt=1\n"
 BLAST = "[blast]\nradius=0.25\ndensity_in=1.0\ndensity_out=1.2\npressure_in=10.0\npressure_out=0.1\n"
 
 
-def make_solver(ini, exact=True, pipeline="unfused"):
+def make_solver(ini, exact=True, pipeline=None):
+    """pipeline=None keeps the handle's default: "tiled" where its TMA boxes exist (even nx >= 32), else "unfused"."""
     p, t_end, nstep = ppk.params_from_ini(ini, exact=exact)
     s = ppk.Mhd3d(p)
-    s.set_pipeline(pipeline)
+    if pipeline is not None:
+        s.set_pipeline(pipeline)
     s.upload(ppk.init_condition_from_ini(ini))
     s.set_time(0.0, t_end, 0)
     return s, nstep
@@ -88,13 +90,20 @@ def test_exact_mode_vs_oracle_with_intermediates(problem, n, extra, bounds, cfl,
     s, _ = make_solver(ini, exact=True, pipeline="unfused")   # the pipeline that stores Fluxes_* and Emf
     f, _ = make_solver(ini, exact=True, pipeline="fused")
     m, _ = make_solver(ini, exact=True, pipeline="streamed")
+    tl, _ = make_solver(ini, exact=True, pipeline="tiled")   # fused producer + the six Riemann tasks in one launch
+    tf, _ = make_solver(ini, exact=False, pipeline="tiled")  # the same in fast arithmetic (what bench.py measures)
     for step in range(4):
         orc.step()
         s.step()
         f.step()
         m.step()
+        tl.step()
+        tf.step()
         assert np.array_equal(f.interior(), orc.interior()), f"fused pipeline differs at step {step + 1}"
         assert np.array_equal(m.interior(), orc.interior()), f"streamed pipeline differs at step {step + 1}"
+        assert np.array_equal(tl.interior(), orc.interior()), f"tiled pipeline differs at step {step + 1}"
+        assert tl.get_time() == s.get_time()
+        close_per_cell(tf.interior(), orc.interior(), 1e-12 if step == 0 else 1e-11)
         t, dt, it = s.get_time()
         assert dt == orc.dt and t == orc.t, f"dt/t differ at step {step}: {dt} vs {orc.dt}"
         if step == 0:
@@ -103,6 +112,17 @@ def test_exact_mode_vs_oracle_with_intermediates(problem, n, extra, bounds, cfl,
             assert np.array_equal(Q[:, :-1, :-1, :-1], orc.Q[:, :-1, :-1, :-1]), "primitive variables"
             E = s.debug_array("ElecField")
             assert np.array_equal(E[:, 1:-1, 1:-1, 1:-1], orc.scratch_array("ElecField", 3)[:, 1:-1, 1:-1, 1:-1])
+            # limited face-field slopes: dA/dy, dA/dz, dB/dx, dB/dz, dC/dx, dC/dy (ComputeMagSlopesFunctor3D)
+            dbf = s.debug_array("dbf")
+            dA, dB, dC = (orc.scratch_array(nm, 3) for nm in ("DeltaA", "DeltaB", "DeltaC"))
+            for comp, want in enumerate((dA[1], dA[2], dB[0], dB[2], dC[0], dC[1])):
+                assert np.array_equal(dbf[comp, 1:-1, 1:-1, 1:-1], want[1:-1, 1:-1, 1:-1]), f"face-field slope {comp}"
+            # the fused producer writes the same basis and slopes as the three kernels it replaces
+            inner = (slice(None), slice(2, -2), slice(2, -2), slice(2, -2))
+            assert np.array_equal(tl.debug_array("basis")[inner], s.debug_array("basis")[inner]), "basis of the fused producer"
+            assert np.array_equal(tl.debug_array("dbf")[inner], dbf[inner]), "face-field slopes of the fused producer"
+            for name in ("Fluxes_x", "Fluxes_y", "Fluxes_z", "Emf"):
+                assert np.array_equal(tl.debug_array(name), s.debug_array(name)), name + " of the one-launch Riemann kernel"
             emf = s.debug_array("Emf")
             eo = orc.scratch_array("Emf", 3)
             nz, ny, nx = n[2], n[1], n[0]
@@ -123,6 +143,8 @@ def test_exact_mode_vs_oracle_with_intermediates(problem, n, extra, bounds, cfl,
     s.close()
     f.close()
     m.close()
+    tl.close()
+    tf.close()
 
 
 def test_hundred_steps_conserved_sums_and_divb(oracle_mod):
