@@ -8,7 +8,9 @@
 A "step" is one full time step of the hot path (ghost fill / NCCL halo exchange, primitives + CFL
 reduction, edge E + face-B slopes, Hancock trace, HLLD fluxes x/y/z, edge EMFs z/y/x, conservative + CT
 update) over the rank's slab.  Workload at every N: Orszag-Tang 3-D with kt=1 (a genuinely 3-D flow),
-n^3 cells PER GPU (default 256^3 = BASELINE configs[1]; weak scaling: the domain grows along z with N).
+n^3 cells PER GPU (default 512^3 = BASELINE's target size and configs[4]; weak scaling: the domain grows along z with N;
+256^3 = configs[1] is measured beside it at N=1 as `extra.n256`).  `--workload blast|field_loop` and `--strong`
+(n^3 cells in TOTAL, split into z-slabs) cover configs[2] and configs[3].
 `value` counts interior cell-updates of all ranks per second with the state resident in HBM;
 `e2e` is the same metric through the C ABI with HOST buffers (pinned H2D of U before and D2H of U after
 every step inside the timed region).  Prints ONE JSON line on rank 0.
@@ -44,8 +46,20 @@ ALGO_BYTES_PER_CELL = 128.0  # read 8 fp64 + write 8 fp64 per inter
 OT = "[OrszagTang]\nkt=1\n"
 
 
-def make_ini(n, mz, nstepmax, noutput=0):
-    """Orszag-Tang, kt=1, periodic, cubic cells, domain [0,1]x[0,1]x[0,mz]."""
+PROBLEMS = {
+    # problem -> (ini [hydro] problem name, extra sections, domain extent per cell count, cfl)
+    "orszag_tang": ("orszag_tang", OT, 0.8),
+    "blast": ("blast", "[blast]\nradius=0.1\ndensity_in=1.0\ndensity_out=1.2\npressure_in=10.0\npressure_out=0.1\n", 0.8),
+    "field_loop": ("field_loop", "[FieldLoop]\nradius=0.3\namplitude=0.001\nvflow=3\ndensity_in=1\n", 0.4),
+}
+
+
+def make_ini(n, mz, nstepmax, noutput=0, problem="orszag_tang", nz=None):
+    """periodic box of cubic cells; n x n x nz cells per rank, mz z-slabs (nz = n: weak scaling,
+    nz = n/mz: a fixed n^3 problem split over the ranks). Orszag-Tang runs with kt=1 (a genuinely 3-D flow)."""
+    nz = n if nz is None else nz
+    name, extra, cfl = PROBLEMS[problem]
+    zmax = float(nz * mz) / float(n)
     bc = "\n".join(f"boundary_type_{f}=3" for f in ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax"))
     return f"""[run]
 solver_name=MHD_Muscl_3D
@@ -56,21 +70,21 @@ nlog=1000000
 [mesh]
 nx={n}
 ny={n}
-nz={n}
+nz={nz}
 xmin=0.0
 xmax=1.0
 ymin=0.0
 ymax=1.0
 zmin=0.0
-zmax={float(mz)}
+zmax={zmax}
 {bc}
 [hydro]
 gamma0=1.666
-cfl=0.8
+cfl={cfl}
 niter_riemann=10
 iorder=2
 slope_type=2
-problem=orszag_tang
+problem={name}
 riemann=hlld
 smallr=1e-8
 smallc=1e-8
@@ -83,7 +97,17 @@ outputPrefix=bench
 outputVtkAscii=false
 [other]
 implementationVersion=0
-{OT}"""
+{extra}"""
+
+
+def workload_config(args, world):
+    """The `config` object of the JSON line: identical in both arms (the reference arm times a bounded sample of it)."""
+    n = args.n
+    nz = n // world if args.strong else n
+    title = {"orszag_tang": "Orszag-Tang 3D kt=1", "blast": "MHD blast 3D", "field_loop": "MHD field-loop advection 3D"}[args.workload]
+    return {"workload": f"{title}, {n}x{n}x{nz} cells per GPU (global {n}x{n}x{nz * world}), z-slabs mz={world}, HLLD + CT, periodic, "
+                        f"cfl {PROBLEMS[args.workload][2]}, gamma 1.666, implementationVersion=0 semantics",
+            "problem": args.workload, "n": n, "nz_per_gpu": nz, "scaling": "strong" if args.strong else "weak"}
 
 
 def peaks():
@@ -186,10 +210,10 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the UNMODIFIED reference (oracle/_ref/ppkMHD) on the host cores
 # ---------------------------------------------------------------------------------------------
-def _run_ref_once(n, nsteps, threads):
+def _run_ref_once(n, nsteps, threads, problem="orszag_tang"):
     from oracle import oracle as O
 
-    ini = make_ini(n, 1, nsteps)
+    ini = make_ini(n, 1, nsteps, problem=problem)
     if O.have_reference():
         with tempfile.TemporaryDirectory() as tmp:
             open(os.path.join(tmp, "run.ini"), "w").write(ini)
@@ -204,10 +228,10 @@ def _run_ref_once(n, nsteps, threads):
     return time.time() - t0, "port"
 
 
-def cpu_reference_throughput(n, steps, warmup, threads):
+def cpu_reference_throughput(n, steps, warmup, threads, problem="orszag_tang"):
     """interior Mcell-updates/s of the reference's own loop: (T(W+K) - T(W)) isolates K steps."""
-    t_w, kind = _run_ref_once(n, max(warmup, 1), threads)
-    t_wk, kind = _run_ref_once(n, max(warmup, 1) + steps, threads)
+    t_w, kind = _run_ref_once(n, max(warmup, 1), threads, problem)
+    t_wk, kind = _run_ref_once(n, max(warmup, 1) + steps, threads, problem)
     dt = max(t_wk - t_w, 1e-9)
     return n ** 3 * steps / dt * 1e-6, kind, dt / steps
 
@@ -240,20 +264,22 @@ def ref_cuda_throughput(n, device):
 
 
 def run_reference_arm(args):
+    """The UNMODIFIED reference (Kokkos-OpenMP, implementationVersion 0) on all host cores, on a bounded sample of our arm's
+    workload: same problem, same ini keys, --ref-n^3 cells (v0 of the reference needs 207 doubles per cell: 512^3 is
+    230 GB of host memory, 256^3 is 30 GB), the SAME number of timed and warm-up steps as our arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     n = args.ref_n
-    steps = max(1, min(args.steps, 10))
-    warm = max(1, min(args.warmup, 2))
-    v, kind, spp = cpu_reference_throughput(n, steps, warm, threads)
-    sample = f"Orszag-Tang 3D kt=1 {n}^3, {steps} timed steps after {warm} warm-up steps (total-time difference of two runs), implementationVersion=0"
+    steps, warm = args.steps, max(args.warmup, 1)
+    v, kind, spp = cpu_reference_throughput(n, steps, warm, threads, args.workload)
+    sample = (f"{args.workload} {n}^3 sample of the workload, {steps} timed steps after {warm} warm-up steps (total-time difference of "
+              f"two runs of oracle/_ref/ppkMHD), {threads} OpenMP threads, implementationVersion=0")
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-        "ms_per_step": spp * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": f"Orszag-Tang 3D kt=1 (bounded CPU sample {n}^3; GPU arm runs {args.n}^3 per GPU)",
-                                        "hlld": True, "implementationVersion": 0},
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": spp * 1e3, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, max(args.gpus, 1)),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -282,12 +308,16 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, K, W = args.n, args.steps, max(args.warmup, 3)
     exact = args.mode == "exact"
+    if args.strong and n % world != 0:
+        raise SystemExit("--strong needs n divisible by the number of GPUs")
+    nz = n // world if args.strong else n
 
-    ini = make_ini(n, world, 10 ** 9)
+    ini = make_ini(n, world, 10 ** 9, problem=args.workload, nz=nz)
     p, t_end, _ = ppk.params_from_ini(ini, rank_z=rank, device=local, exact=exact)
     solver = ppk.Mhd3d(p)
     if args.pipeline != "auto":
         solver.set_pipeline(args.pipeline)
+    pipeline = solver.pipeline()
     # a dedicated (non-default) torch stream: the C ABI launches on it, torch.cuda.Event records on it
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
@@ -319,27 +349,51 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks(x):
+        if world == 1:
+            return [x]
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = x
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.cpu()]
+
+    def timed_run(nsteps):
+        """nsteps steps bracketed by barrier + synchronize, CUDA events on the launch stream, max over ranks; clocks sampled
+        on rank 0 during the region"""
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        solver.run(nsteps)
+        b.record(stream)
+        barrier()
+        return max_over_ranks(a.elapsed_time(b)), (sampler.stop() if rank == 0 else None)
+
+    cells = float(n) * n * nz * world  # interior cells of all ranks
+
     # ---- resident leg ------------------------------------------------------------------------
     solver.run(W)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = solver.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    solver.run(K)
-    e1.record(stream)
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms, clocks = timed_run(K)
     launches = solver.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
-    cells = float(n) ** 3 * world
     value = cells * K / (ms * 1e-3) * 1e-6
+    # the same loop for at least two seconds: the clocks of a sustained run (the K-step region is a burst)
+    sustained = None
+    if ms < 2000.0 and not args.no_sustained:
+        Ks = int(2000.0 / (ms / K)) + 1
+        ms_s, clocks_s = timed_run(Ks)
+        sustained = {"steps": Ks, "ms_per_step": ms_s / Ks, "value": cells * Ks / (ms_s * 1e-3) * 1e-6, "unit": UNIT,
+                     "seconds": ms_s * 1e-3, "clocks": clocks_s}
     t_sim, dt_sim, it = solver.get_time()
     sums, divb = solver.diagnostics()
     if not np.all(np.isfinite(sums)):
         raise SystemExit("non-finite state after the timed steps")
+    divb_ranks = all_ranks(divb)
+    # constrained transport keeps div B at round-off on every slab, decomposed or not (north-star criterion)
+    if max(divb_ranks) > 1e-12 * max(1.0, float(n) / 256.0):
+        raise SystemExit(f"max|div B| per rank {divb_ranks} exceeds 1e-12: the run is not a valid measurement")
 
     # ---- per-kernel timing (CUDA events around every launch, on the launch stream) ------------
     solver.profile(True)
@@ -354,129 +408,139 @@ def run_ours(args):
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"] / max(per_kernel[k]["launches_per_step"], 1))
     dom_ms = per_kernel[dom]["ms_per_step"] / per_kernel[dom]["launches_per_step"]
     pk, pk_kind = peaks()
-    algo_bytes = ALGO_BYTES_PER_CELL * float(n) ** 3  # per launch: one launch sweeps the rank's n^3 cells
+    cells_rank = float(n) * n * nz
+    algo_bytes = ALGO_BYTES_PER_CELL * cells_rank  # per launch: one launch sweeps the rank's cells
     achieved = algo_bytes / (dom_ms * 1e-3) / 1e9
-    # DRAM bytes of the dominant kernel from the committed ncu --set full capture (same n), per launch
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "kernel_dram_traffic.json")
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        if tj.get("n") == n:
-            traffic = tj.get("dram_bytes_per_launch", {}).get(dom)
-    # second roofline of this path: the FP64 pipe. Instructions per cell-update from the SASS of the
-    # kernels timed here (profiles/sass_counts.json), pipe peak measured on this pool's B200 by
-    # profiles/microbench/fp64_pipe.cu (17.0 T thread-instructions/s = 34 TFLOP/s)
-    fp64 = None
-    spath = os.path.join(ROOT, "profiles", "sass_counts.json")
-    if os.path.exists(spath):
-        per_cell = json.load(open(spath))["per_cell_update"]
-        rate = per_cell["fp64_pipe"] * cells / world * K / (ms * 1e-3)
-        fp64 = {"fp64_pipe_inst_per_cell_update": per_cell["fp64_pipe"], "all_inst_per_cell_update": per_cell["instructions"],
-                "achieved_Tinst_s": rate / 1e12, "peak_Tinst_s": 17.0, "frac": rate / 17.0e12,
-                "peak_source": "profiles/microbench/fp64_pipe.cu measured on B200 (DFMA, 16 warps/SM, ILP 4)"}
-    step_gbs = ALGO_BYTES_PER_CELL * cells / world * K / (ms * 1e-3) / 1e9
+    # measured per-kernel counters of this pipeline (profiles/r2/counters.json: ncu on one step, per launch): DRAM bytes
+    # (dram__bytes_read.sum + dram__bytes_write.sum) and executed instructions (smsp__inst_executed.sum,
+    # smsp__inst_executed_pipe_fp64.sum), both scaled to the cell count of this run
+    traffic, fp64 = None, None
+    cpath = os.path.join(ROOT, "profiles", "r2", "counters.json")
+    if os.path.exists(cpath):
+        cj = json.load(open(cpath)).get(pipeline)
+        if cj:
+            scale = cells_rank / float(cj["cells"])
+            if dom in cj["kernels"]:
+                traffic = cj["kernels"][dom]["dram_bytes"] * scale if cj["cells"] == cells_rank else None
+            inst = sum(k["inst_executed"] for k in cj["kernels"].values()) * 32.0 / cj["cells"]
+            f64 = sum(k["inst_fp64"] for k in cj["kernels"].values()) * 32.0 / cj["cells"]
+            rate = f64 * cells_rank * K / (ms * 1e-3)
+            fp64 = {"fp64_pipe_inst_per_cell_update": f64, "all_inst_per_cell_update": inst, "achieved_Tinst_s": rate / 1e12,
+                    "peak_Tinst_s": 17.0, "frac": rate / 17.0e12, "issue_frac": inst * cells_rank * K / (ms * 1e-3) / 36.0e12,
+                    "dram_bytes_per_cell_update": sum(k["dram_bytes"] for k in cj["kernels"].values()) / cj["cells"],
+                    "source": f"ncu counters of one {cj['n']}^3 step (profiles/r2/counters.json): smsp__inst_executed_pipe_fp64.sum, "
+                              "smsp__inst_executed.sum (warp instructions x 32), dram__bytes_read+write; FP64 peak 17.0 T "
+                              "thread-inst/s measured by profiles/microbench/fp64_pipe.cu, issue peak 148 SMs x 4 x 32 x 1.9 GHz"}
+    step_gbs = ALGO_BYTES_PER_CELL * cells_rank * K / (ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind + " copy bandwidth (burst)",
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": dom_ms,
                 "whole_step": {"achieved": step_gbs, "frac": step_gbs / pk["hbm_gbs"]},
                 "fp64_pipe": fp64,
-                "note": "128 algorithmic B per cell-update (read U^n, write U^n+1). The step needs ~3.0k FP64-pipe "
-                        "instructions per cell-update, so the FP64 pipe bounds it at ~5.7 Gcell/s = 11% of the HBM roofline; "
-                        "see DESIGN.md"}
+                "note": "128 algorithmic B per cell-update (read U^n, write U^n+1). The step executes ~2.9k FP64-pipe and ~6k "
+                        "instructions per cell-update: FP64 pipe and instruction issue bound it near 5 Gcell/s = 10% of the "
+                        "HBM roofline; see DESIGN.md"}
 
     # ---- e2e leg: host buffers through the C ABI, H2D + step + D2H every step ------------------
-    # Every step is one batch: upload a full host state (pinned), advance it one step, download the full result.
-    # N=1: `depth` solver handles are in flight, each on its own stream, so that the download of batch i overlaps the
-    # upload of batch i+1 and the step of the batch between them (PCIe is full duplex; the copies bound the leg).
-    # N>1: one handle (one NCCL communicator per rank), the three phases run back to back.
+    # Every step is one batch: a full host state (pinned) goes to the device, advances one step, and the full result comes
+    # back. ONE handle at every N: ppk_mhd3d_stage_upload / _stage_swap / _step / _stage_download rotate three device arrays
+    # so that the upload of batch i+1 (copy stream 1) overlaps the step of batch i and the download of batch i-1 (copy
+    # stream 2); PCIe is full duplex and bounds the leg.
     Ke = max(2, min(K, args.e2e_steps))
     nbytes = int(np.prod(p.shape)) * 8
-    depth = args.e2e_depth if world == 1 else 1
-    e2e_solvers, e2e_streams = [solver], [stream]
-    for _ in range(depth - 1):
-        s2 = ppk.Mhd3d(p)
-        if args.pipeline != "auto":
-            s2.set_pipeline(args.pipeline)
-        st2 = torch.cuda.Stream()
-        s2.set_stream(st2.cuda_stream)
-        s2.set_time(0.0, t_end, 0)
-        e2e_solvers.append(s2)
-        e2e_streams.append(st2)
-    host_in = [host] + [torch.empty(p.shape, dtype=torch.float64).pin_memory() for _ in range(depth - 1)]
-    host_out = [torch.empty(p.shape, dtype=torch.float64).pin_memory() for _ in range(depth)]
-    for hb in host_in[1:]:
-        hb.copy_(host)
+    host_in = [host, torch.empty(p.shape, dtype=torch.float64).pin_memory()]
+    host_in[1].copy_(host)
+    host_out = [torch.empty(p.shape, dtype=torch.float64).pin_memory() for _ in range(2)]
 
     def e2e_pass(nsteps):
-        for it in range(nsteps):
-            sv = e2e_solvers[it % depth]
-            sv.synchronize()  # batch it-depth is back on the host: its buffers are free again
-            sv.upload(host_in[it % depth].data_ptr())
-            sv.step()
-            sv.download_async(host_out[it % depth].data_ptr())
-        for sv in e2e_solvers:
-            sv.synchronize()
+        solver.stage_upload(host_in[0].data_ptr())
+        for b in range(nsteps):
+            solver.stage_swap()
+            solver.step()
+            solver.stage_download(host_out[b % 2].data_ptr())
+            if b + 1 < nsteps:
+                solver.stage_upload(host_in[(b + 1) % 2].data_ptr())
+        solver.synchronize()
 
-    e2e_pass(depth)  # warm the extra handles (first-touch allocations, flux arrays)
+    e2e_pass(2)  # warm-up: the staging array, the copy streams
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    join = torch.cuda.Stream()
-    f0.record(join)
-    for st_ in e2e_streams:
-        st_.wait_stream(join)  # nothing of the timed region starts before f0
+    f0.record(stream)
     w0 = time.perf_counter()
-    e2e_pass(Ke)
-    for st_ in e2e_streams:
-        join.wait_stream(st_)
-    f1.record(join)
+    e2e_pass(Ke)  # ends with ppk_mhd3d_synchronize: every stream of the handle is idle when f1 is recorded
+    f1.record(stream)
     barrier()
     w1 = time.perf_counter()
     ems = max_over_ranks(f0.elapsed_time(f1))
-    assert np.all(np.isfinite(host_out[0].numpy()[:, 3:-3, 3:-3, 3:-3].sum()))
+    assert np.all(np.isfinite(host_out[(Ke - 1) % 2].numpy()[:, 3:-3, 3:-3, 3:-3].sum()))
     e2e = {"value": cells * Ke / (ems * 1e-3) * 1e-6, "unit": UNIT, "h2d_bytes_per_step": nbytes * world,
            "d2h_bytes_per_step": nbytes * world, "steps": Ke, "ms_per_step": ems / Ke, "wall_ms_per_step": (w1 - w0) * 1e3 / Ke,
-           "handles_in_flight": depth,
-           "what": "per step: ppk_mhd3d_upload(pinned host U) + ppk_mhd3d_step + ppk_mhd3d_download_async(pinned host U); "
-                   f"{depth} independent batches in flight on {depth} streams, a batch's buffers are reused after "
-                   "ppk_mhd3d_synchronize"}
-    for s2 in e2e_solvers[1:]:
-        s2.close()
-    torch.cuda.set_stream(stream)
+           "pcie_GBs_per_gpu_each_way": nbytes / (ems / Ke * 1e-3) / 1e9,
+           "what": "per step: ppk_mhd3d_stage_upload(pinned host U) + _stage_swap + ppk_mhd3d_step + ppk_mhd3d_stage_download("
+                   "pinned host U) on one handle per GPU; three device arrays rotate, uploads, steps and downloads of "
+                   "consecutive batches overlap on three streams"}
+    del host_in, host_out
 
     # ---- CPU baseline beside it (rank 0, N=1 only; bounded sample) -----------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        v, kind, spp = cpu_reference_throughput(args.ref_n, 6, 2, threads)
+        v, kind, spp = cpu_reference_throughput(args.cpu_n, 6, 2, threads, args.workload)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
-               "sample": f"Orszag-Tang 3D kt=1 {args.ref_n}^3, 6 timed steps after 2 warm-up (difference of two runs of oracle/_ref/ppkMHD, "
-                         f"Kokkos-OpenMP, implementationVersion=0); {spp * 1e3:.0f} ms/step"}
+               "sample": f"{args.workload} {args.cpu_n}^3 sample, 6 timed steps after 2 warm-up (difference of two runs of "
+                         f"oracle/_ref/ppkMHD, Kokkos-OpenMP, implementationVersion=0); {spp * 1e3:.0f} ms/step"}
+
+    sim = {"t": t_sim, "dt": dt_sim, "iteration": it, "max_divB": max(divb_ranks), "max_divB_per_rank": divb_ranks,
+           "device_GB": solver.device_bytes() / 1e9}
+    solver.close()
+    del solver
+
+    # ---- BASELINE configs[1] (256^3 on one GPU) beside the headline size, N=1 only --------------
+    extra = {}
+    if rank == 0 and world == 1 and n != 256 and args.workload == "orszag_tang" and not args.no_extra:
+        ini2 = make_ini(256, 1, 10 ** 9)
+        p2, t_end2, _ = ppk.params_from_ini(ini2, device=local, exact=exact)
+        s2 = ppk.Mhd3d(p2)
+        if args.pipeline != "auto":
+            s2.set_pipeline(args.pipeline)
+        s2.set_stream(stream.cuda_stream)
+        s2.upload(ppk.init_condition_from_ini(ini2))
+        s2.set_time(0.0, t_end2, 0)
+        s2.run(max(W, 5))
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        K2 = max(K, 40)
+        a.record(stream)
+        s2.run(K2)
+        b.record(stream)
+        torch.cuda.synchronize()
+        ms2 = a.elapsed_time(b)
+        extra["n256"] = {"value": 256.0 ** 3 * K2 / (ms2 * 1e-3) * 1e-6, "unit": UNIT, "ms_per_step": ms2 / K2, "steps": K2,
+                         "config": "Orszag-Tang 3D kt=1 256^3 on one GPU (BASELINE configs[1]), resident"}
+        s2.close()
 
     ref_cuda = None
-    if rank == 0 and world == 1 and not args.no_ref_cuda:
-        solver.synchronize()
-        ref_cuda = ref_cuda_throughput(n, local)
+    if rank == 0 and world == 1 and not args.no_ref_cuda and args.workload == "orszag_tang":
+        torch.cuda.synchronize()
+        ref_cuda = ref_cuda_throughput(256, local)  # v0 of the reference needs 207 doubles per cell: 256^3 is what fits
 
     if rank == 0:
+        cfg = workload_config(args, world)
+        cfg.update({"pipeline": pipeline,
+                    "arithmetic": "fast (FMA contraction, within 1e-12 of the reference)" if not exact else "exact (--fmad=false, bit-identical)",
+                    "l2": f"inputs larger than L2 (every array >= {8 * cells_rank / 1e9:.1f} GB vs 126 MB L2)",
+                    "cells_with_ghosts_per_gpu": int(np.prod(p.shape[1:])),
+                    "reference_style_value_with_ghosts": value * float(np.prod(p.shape[1:])) / cells_rank})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": f"Orszag-Tang 3D kt=1, {n}^3 cells per GPU (global {n}x{n}x{n * world}), z-slabs mz={world}, "
-                                   f"HLLD + CT, periodic, cfl 0.8, gamma 1.666, implementationVersion=0 semantics",
-                       "pipeline": args.pipeline,
-                       "arithmetic": "fast (FMA contraction, within 1e-12 of the reference)" if not exact else "exact (--fmad=false, bit-identical)",
-                       "l2": "inputs larger than L2 (every array >= 1.1 GB vs 126 MB L2)",
-                       "cells_with_ghosts_per_gpu": int(np.prod(p.shape[1:])),
-                       "reference_style_value_with_ghosts": value * float(np.prod(p.shape[1:])) / float(n) ** 3},
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfg,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "reference_cuda_baseline": ref_cuda,
+            "sustained": sustained, "extra": extra, "reference_cuda_baseline": ref_cuda,
             "per_kernel_ms": {k: round(v["ms_per_step"], 4) for k, v in per_kernel.items()},
-            "profiled_step_ms": step_ms_prof,
-            "sim": {"t": t_sim, "dt": dt_sim, "iteration": it, "max_divB": divb, "device_GB": solver.device_bytes() / 1e9},
+            "profiled_step_ms": step_ms_prof, "sim": sim,
         }
         emit(line)
-    solver.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -487,13 +551,17 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=256, help="cells per axis per GPU")
+    ap.add_argument("--n", type=int, default=512, help="cells per axis per GPU (with --strong: of the whole problem)")
+    ap.add_argument("--workload", default="orszag_tang", choices=sorted(PROBLEMS))
+    ap.add_argument("--strong", action="store_true", help="a fixed n^3 problem split into z-slabs (BASELINE configs[3]) instead of n^3 per GPU")
+    ap.add_argument("--cpu-n", type=int, default=128, help="grid of the bounded CPU sample printed beside our arm (cpu_baseline)")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the 256^3 (configs[1]) measurement beside the headline size")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--pipeline", default="auto", choices=["auto", "tiled", "fused", "fused_split", "unfused", "streamed"],
                     help="auto = the handle's default (tiled on one slab, unfused on decomposed runs)")
-    ap.add_argument("--ref-n", type=int, default=128, help="grid of the bounded CPU sample")
+    ap.add_argument("--ref-n", type=int, default=256, help="grid of the reference arm's bounded sample (--impl reference)")
     ap.add_argument("--e2e-steps", type=int, default=9)
-    ap.add_argument("--e2e-depth", type=int, default=3, help="solver handles (batches) in flight in the e2e leg at N=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference's Kokkos-CUDA build on the same GPU")
     args = ap.parse_args()

@@ -52,7 +52,10 @@ typedef struct ppk_mhd3d_params {
   int boundary_type[6];/* xmin,xmax,ymin,ymax,zmin,zmax of the GLOBAL domain (enum ppk_bc) */
   double gamma0, cfl, slope_type, smallr, smallc, smallp; /* smallp = smallc*smallc/gamma0 (HydroParams.cpp:441) */
   int riemann_solver;  /* enum ppk_riemann: hlld, hll or llf for the face fluxes (the edge EMFs always use 2-D HLLD) */
-  int implementation_version; /* only 0 (the deterministic variant, SolverMHDMuscl.cpp:494-517) */
+  int implementation_version; /* 0 (the deterministic variant, SolverMHDMuscl.cpp:494-517) or 1 (the reference's atomic-scatter
+                                 variant of the same arithmetic: runs v0's deterministic kernels, so results equal v0's, which
+                                 the reference's own v1 matches to ~1e-15). 3-D rejects 2 (PPK_ERR_UNSUPPORTED); the 2-D entry
+                                 points accept 0, 1 and 2 and always run the v0 formulation (v2 agrees to ~1e-15, not bitwise) */
   int mx, my, mz;      /* Cartesian decomposition ([mpi] mx,my,mz); this build supports z-slabs: mx = my = 1 */
   int rank_x, rank_y, rank_z; /* position of this slab (replaces myMpiPos, HydroParams.cpp:269-277) */
   int device;          /* CUDA device ordinal to run on */
@@ -77,6 +80,20 @@ int ppk_mhd3d_download(ppk_mhd3d *handle, double *u_host);
  * ppk_mhd3d_synchronize(handle) makes `u_host` valid. Plays the role of the asynchronous deep_copy(exec_space, ...)
  * overloads of Kokkos the reference never uses (its IO_VTK.cpp:253 copy is blocking). */
 int ppk_mhd3d_download_async(ppk_mhd3d *handle, double *u_host);
+
+/* Split-phase host transfers: batches pipelined on ONE handle (bench.py's end-to-end leg at sizes where several handles do not
+ * fit in HBM). A third conservative array rotates with U and U2:
+ *   ppk_mhd3d_stage_upload  : asynchronous H2D of a full state (pinned `u_host`) into the staging array, on its own copy stream;
+ *                             overlaps a running step and a running stage_download of another array;
+ *   ppk_mhd3d_stage_swap    : the staged array becomes the current array (the previous current array becomes the staging
+ *                             array); the compute stream waits for the copy, nothing else does;
+ *   ppk_mhd3d_stage_download: asynchronous D2H of the current array on a second copy stream, ordered after the work already
+ *                             enqueued on the compute stream; whatever overwrites that array later waits for the copy.
+ * ppk_mhd3d_synchronize waits for all of it. Same role as ppk_mhd3d_upload / ppk_mhd3d_download_async (the reference's only
+ * counterpart is the blocking Kokkos::deep_copy of src/utils/io/IO_VTK.cpp:253). */
+int ppk_mhd3d_stage_upload(ppk_mhd3d *handle, const double *u_host);
+int ppk_mhd3d_stage_swap(ppk_mhd3d *handle);
+int ppk_mhd3d_stage_download(ppk_mhd3d *handle, double *u_host);
 
 /* Time bookkeeping of SolverBase (m_t, m_tEnd, m_iteration; SolverBase.cpp:119-124, 206-220). */
 int ppk_mhd3d_set_time(ppk_mhd3d *handle, double t, double t_end, long iteration);
@@ -152,6 +169,7 @@ int ppk_mhd3d_set_stream(ppk_mhd3d *handle, void *cuda_stream);
  *       (y-slab, plane, task, tile) so that the basis is read from HBM once and from the L2 five times | update. */
 enum ppk_pipeline { PPK_PIPELINE_UNFUSED = 0, PPK_PIPELINE_FUSED = 1, PPK_PIPELINE_FUSED_SPLIT = 2, PPK_PIPELINE_STREAMED = 3, PPK_PIPELINE_TILED = 4 };
 int ppk_mhd3d_set_pipeline(ppk_mhd3d *handle, int pipeline);
+int ppk_mhd3d_get_pipeline(ppk_mhd3d *handle); /* the schedule in use (enum ppk_pipeline), -1 for a null handle */
 /* Per-kernel CUDA-event timing (replaces the coarse timers of SolverBase.h:35-42 for profiling).
  * While enabled every kernel launch is bracketed by events on the launch stream. */
 int ppk_mhd3d_profile(ppk_mhd3d *handle, int enable);

@@ -25,10 +25,8 @@ ID, IP, IU, IV, IW, IA, IB, IC = range(8)
 
 
 def build(force: bool = False) -> str:
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(
-        os.path.join(HERE, "mhd3d_oracle.c")
-    ):
-        subprocess.check_call(["make", "-C", HERE, "-s"], stdout=subprocess.DEVNULL)
+    # always ask make: the Makefile tracks mhd3d_oracle.c, mhd2d_oracle.c and mhd3d_oracle.h (a no-op when up to date)
+    subprocess.check_call(["make", "-C", HERE, "-s"] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
     return LIB_PATH
 
 

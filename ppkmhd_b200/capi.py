@@ -57,7 +57,7 @@ class HaloMsg(C.Structure):
 
 _lib = None
 
-# every symbol include/*.h declares (tests/test_abi.py checks the library exports them all)
+# every symbol include/*.h declares (tests/test_host_layer.py checks the library exports them all)
 EXPORTS = [
     "ppk_mhd3d_create", "ppk_mhd3d_destroy", "ppk_mhd3d_upload", "ppk_mhd3d_download", "ppk_mhd3d_download_async", "ppk_mhd3d_set_time",
     "ppk_mhd3d_get_time", "ppk_mhd3d_make_boundaries", "ppk_mhd3d_compute_dt", "ppk_mhd3d_step", "ppk_mhd3d_run",
@@ -65,6 +65,7 @@ EXPORTS = [
     "ppk_mhd3d_set_stream", "ppk_mhd3d_profile", "ppk_mhd3d_kernel_times", "ppk_mhd3d_launch_count",
     "ppk_mhd3d_debug_array", "ppk_mhd3d_device_bytes", "ppk_last_error_string", "ppk_version_string",
     "ppk_mhd3d_halo_plan", "ppk_selftest_fastmath", "ppk_mhd3d_set_pipeline",
+    "ppk_mhd3d_get_pipeline", "ppk_mhd3d_stage_upload", "ppk_mhd3d_stage_swap", "ppk_mhd3d_stage_download",
     "ppk_params_from_ini", "ppk_init_condition_from_ini", "ppk_run_ini", "ppk_init_condition_2d_from_ini",
     "ppk_mhd2d_create", "ppk_mhd2d_destroy", "ppk_mhd2d_upload", "ppk_mhd2d_download", "ppk_mhd2d_set_time", "ppk_mhd2d_get_time",
     "ppk_mhd2d_make_boundaries", "ppk_mhd2d_compute_dt", "ppk_mhd2d_step", "ppk_mhd2d_run", "ppk_mhd2d_synchronize", "ppk_mhd2d_launch_count",
@@ -86,6 +87,9 @@ def load_library():
     L.ppk_mhd3d_upload.argtypes = [vp, vp]
     L.ppk_mhd3d_download.argtypes = [vp, vp]
     L.ppk_mhd3d_download_async.argtypes = [vp, vp]
+    L.ppk_mhd3d_stage_upload.argtypes = [vp, vp]
+    L.ppk_mhd3d_stage_swap.argtypes = [vp]
+    L.ppk_mhd3d_stage_download.argtypes = [vp, vp]
     L.ppk_mhd3d_set_time.argtypes = [vp, C.c_double, C.c_double, C.c_long]
     L.ppk_mhd3d_get_time.argtypes = [vp, dp, dp, C.POINTER(C.c_long)]
     L.ppk_mhd3d_make_boundaries.argtypes = [vp]
@@ -99,6 +103,7 @@ def load_library():
     L.ppk_mhd3d_set_stream.argtypes = [vp, vp]
     L.ppk_mhd3d_profile.argtypes = [vp, C.c_int]
     L.ppk_mhd3d_set_pipeline.argtypes = [vp, C.c_int]
+    L.ppk_mhd3d_get_pipeline.argtypes = [vp]
     L.ppk_mhd3d_kernel_times.argtypes = [vp, C.c_int, C.POINTER(C.c_char_p), dp, C.POINTER(C.c_long), C.c_int]
     L.ppk_mhd3d_launch_count.argtypes = [vp]
     L.ppk_mhd3d_launch_count.restype = C.c_long
@@ -259,6 +264,17 @@ class Mhd3d:
         """Enqueue the device-to-host copy into the PINNED buffer at address `out_ptr`; valid after synchronize()."""
         _check(self.L.ppk_mhd3d_download_async(self.h, int(out_ptr)))
 
+    def stage_upload(self, in_ptr):
+        """ppk_mhd3d_stage_upload: asynchronous H2D of a full state from the PINNED buffer at `in_ptr` into the staging array."""
+        _check(self.L.ppk_mhd3d_stage_upload(self.h, int(in_ptr)))
+
+    def stage_swap(self):
+        _check(self.L.ppk_mhd3d_stage_swap(self.h))
+
+    def stage_download(self, out_ptr):
+        """ppk_mhd3d_stage_download: asynchronous D2H of the current array on the second copy stream; valid after synchronize()."""
+        _check(self.L.ppk_mhd3d_stage_download(self.h, int(out_ptr)))
+
     def interior(self):
         return self.download()[:, 3:-3, 3:-3, 3:-3]
 
@@ -304,6 +320,10 @@ class Mhd3d:
 
     def set_pipeline(self, name: str):
         _check(self.L.ppk_mhd3d_set_pipeline(self.h, self.PIPELINES[name]))
+
+    def pipeline(self) -> str:
+        code = self.L.ppk_mhd3d_get_pipeline(self.h)
+        return {v: k for k, v in self.PIPELINES.items()}.get(code, str(code))
 
     def profile(self, enable=True):
         _check(self.L.ppk_mhd3d_profile(self.h, 1 if enable else 0))

@@ -105,6 +105,12 @@ struct ppk_mhd3d {
   double *diag = nullptr;
   void *tma = nullptr;  // tensor maps for the TMA-staged flux / EMF kernels
   void *prod = nullptr; // tensor maps of U / U2 for the fused producer (tiled pipeline)
+  // split-phase host transfers (ppk_mhd3d_stage_*): a third conservative array and two copy streams
+  double *Ustage = nullptr;
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+  cudaEvent_t ev_h2d = nullptr, ev_main = nullptr;
+  struct Pending { double *buf; cudaEvent_t done; };
+  std::vector<Pending> d2h_pending;  // arrays a staged download is still reading
   long long bytes = 0;
   long launches = 0;
   long host_iteration = 0;  // parity selects U / U2 like SolverMHDMuscl::godunov_unsplit (SolverMHDMuscl.h:793-805)
@@ -213,6 +219,21 @@ int halo_exchange_z(ppk_mhd3d *h, double *U, cudaStream_t s) {
   return 0;
 }
 
+// an array that a staged download (ppk_mhd3d_stage_download) is still reading must not be overwritten on stream s
+int wait_staged_reads(ppk_mhd3d *h, const double *buf, cudaStream_t s) {
+  for (auto &pd : h->d2h_pending)
+    if (pd.buf == buf) CUDA_TRY(cudaStreamWaitEvent(s, pd.done, 0));
+  return 0;
+}
+
+// Q and the edge electric field only exist for the schedules that store them (the tiled pipeline keeps both on chip)
+int ensure_prim_arrays(ppk_mhd3d *h) {
+  const long long n = h->g.ncell;
+  if (!h->Q) { if (int rc = alloc_doubles(h, &h->Q, NBVAR * n)) return rc; }
+  if (!h->E) { if (int rc = alloc_doubles(h, &h->E, NELEC * n)) return rc; }
+  return 0;
+}
+
 // make_boundaries on array U, optionally overlapped with the part of prim+CFL that needs no z ghost.
 // `defer_dt`: the caller finishes the time step size itself (enqueue_step overlaps the all-reduce with E + dB).
 int boundaries_and_primitives(ppk_mhd3d *h, double *U, bool with_prim, bool defer_dt = false) {
@@ -221,6 +242,7 @@ int boundaries_and_primitives(ppk_mhd3d *h, double *U, bool with_prim, bool defe
   const bool exch = h->exch_lo || h->exch_hi;
   const bool posted = exch && h->halo_posted == U;  // the z exchange of this array started at the end of the last step
   if (exch && !h->comm) return fail(PPK_ERR_STATE, "mz > 1 but ppk_mhd3d_comm_init was not called");
+  if (with_prim) { if (int rc = ensure_prim_arrays(h)) return rc; }
   if (posted) {
     // the edge planes already carry their x / y ghosts (they are being sent), the z ghost planes are being received
     { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, U, 0, 2 * g.gw, g.nz, s); }
@@ -271,6 +293,7 @@ int enqueue_step_tiled(ppk_mhd3d *h) {
   cudaStream_t s = h->stream;
   double *Uin = h->cur(), *Uout = h->nxt();
   if (h->exch_lo || h->exch_hi) return fail(PPK_ERR_STATE, "the tiled pipeline is single-slab for now");
+  if (int rc = wait_staged_reads(h, Uout, s)) return rc;
   if (!h->F[0] || !h->EMF) {
     if (int rc = ppk_mhd3d_set_pipeline(h, PPK_PIPELINE_TILED)) return rc;
   }
@@ -308,6 +331,7 @@ int enqueue_step(ppk_mhd3d *h) {
   cudaStream_t s = h->stream;
   double *Uin = h->cur(), *Uout = h->nxt();
   if (h->pipeline == PPK_PIPELINE_TILED) return enqueue_step_tiled(h);
+  if (int rc = wait_staged_reads(h, Uout, s)) return rc;
   const bool multi = h->comm && h->nranks > 1 && h->defer_dt;
   if (int rc = boundaries_and_primitives(h, Uin, true, multi)) return rc;
   if (multi) {
@@ -374,6 +398,9 @@ int enqueue_step(ppk_mhd3d *h) {
   return 0;
 }
 
+int create_impl(const ppk_mhd3d_params *p, ppk_mhd3d *h);
+int create2d_impl(const ppk_mhd3d_params *p, ppk_mhd2d *h);
+
 // a posted z exchange writes ghost planes of the current array: finish it before the host reads or replaces that array
 int settle_halo(ppk_mhd3d *h) {
   if (h->halo_posted) CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
@@ -408,6 +435,19 @@ int ppk_mhd3d_create(const ppk_mhd3d_params *p, ppk_mhd3d **out) {
   if (p->device < 0 || p->device >= ndev) return fail(PPK_ERR_INVALID_ARGUMENT, "device ordinal out of range");
 
   ppk_mhd3d *h = new ppk_mhd3d();
+  if (int rc = create_impl(p, h)) {  // any failure (stream / event creation, an out-of-memory cudaMalloc at 512^3, ...)
+    const std::string msg = g_last_error;
+    ppk_mhd3d_destroy(h);              // releases whatever was already allocated
+    g_last_error = msg;
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+} // extern "C"
+namespace {
+int create_impl(const ppk_mhd3d_params *p, ppk_mhd3d *h) {
   h->params = *p;
   h->device = p->device;
   h->kt = p->exact_arithmetic ? kernel_table_exact() : kernel_table_fast();
@@ -454,12 +494,9 @@ int ppk_mhd3d_create(const ppk_mhd3d_params *p, ppk_mhd3d **out) {
   int rc = 0;
   const long long n = g.ncell;
   if ((rc = alloc_doubles(h, &h->U[0], NBVAR * n)) || (rc = alloc_doubles(h, &h->U[1], NBVAR * n)) ||
-      (rc = alloc_doubles(h, &h->Q, NBVAR * n)) || (rc = alloc_doubles(h, &h->E, NELEC * n)) ||
       (rc = alloc_doubles(h, &h->DBF, NDBF * n)) || (rc = alloc_doubles(h, &h->BASIS, NBASIS * n)) ||
-      (rc = alloc_doubles(h, &h->diag, 16))) {
-    ppk_mhd3d_destroy(h);
+      (rc = alloc_doubles(h, &h->diag, 16)))
     return rc;
-  }
   h->tma = h->kt->tma_create(g, h->BASIS, h->DBF);
   h->prod = h->kt->prod_create(g, h->U[0], h->U[1]);
   // default schedule: the tiled pipeline where its TMA boxes exist (even isize, nx >= 32) and the slab has no z exchange
@@ -473,17 +510,23 @@ int ppk_mhd3d_create(const ppk_mhd3d_params *p, ppk_mhd3d **out) {
   st0.t = 0.0; st0.t_end = 1e300; st0.dt = 0.0; st0.inv_dt_bits = 0ull; st0.iteration = 0;
   CUDA_TRY(cudaMemcpyAsync(h->st, &st0, sizeof(st0), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  *out = h;
   return 0;
 }
+}  // namespace
+extern "C" {
 
 int ppk_mhd3d_destroy(ppk_mhd3d *h) {
   if (!h) return 0;
   DeviceGuard guard(h->device);
   cudaDeviceSynchronize();
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
-  for (double *p : {h->U[0], h->U[1], h->Q, h->E, h->DBF, h->BASIS, h->F[0], h->F[1], h->F[2], h->EMF, h->diag})
+  for (double *p : {h->U[0], h->U[1], h->Ustage, h->Q, h->E, h->DBF, h->BASIS, h->F[0], h->F[1], h->F[2], h->EMF, h->diag})
     if (p) cudaFree(p);
+  for (auto &pd : h->d2h_pending) cudaEventDestroy(pd.done);
+  if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
+  if (h->ev_main) cudaEventDestroy(h->ev_main);
+  if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+  if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
   if (h->st) cudaFree(h->st);
   if (h->tma && h->kt) h->kt->tma_destroy(h->tma);
   if (h->prod && h->kt) h->kt->prod_destroy(h->prod);
@@ -503,6 +546,7 @@ int ppk_mhd3d_upload(ppk_mhd3d *h, const double *u_host) {
   DeviceGuard guard(h->device);
   if (int rc = settle_halo(h)) return rc;
   h->halo_posted = nullptr;  // the array is replaced: its ghosts are exchanged again at the next step
+  if (int rc = wait_staged_reads(h, h->cur(), h->stream)) return rc;
   CUDA_TRY(cudaMemcpyAsync(h->cur(), u_host, (size_t)NBVAR * h->g.ncell * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   return 0;
 }
@@ -561,7 +605,11 @@ int ppk_mhd3d_make_boundaries(ppk_mhd3d *h) {
 int ppk_mhd3d_compute_dt(ppk_mhd3d *h, double *dt) {
   if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
   DeviceGuard guard(h->device);
-  if (int rc = boundaries_and_primitives(h, h->cur(), true)) return rc;
+  if (h->pipeline == PPK_PIPELINE_TILED) {  // the tiled pipeline never stores Q: CFL reduction straight from U
+    if (int rc = boundaries_and_primitives(h, h->cur(), false)) return rc;
+    { Scope sc(h, KK_DT_ONLY, h->stream); h->kt->dt_only(h->g, h->cur(), h->st, h->g.gw, h->g.nz + h->g.gw, h->stream); }
+    { Scope sc(h, KK_FINALIZE_DT, h->stream); h->kt->finalize_dt(h->g, h->st, h->stream); }
+  } else if (int rc = boundaries_and_primitives(h, h->cur(), true)) return rc;
   CUDA_TRY(cudaGetLastError());
   return ppk_mhd3d_get_time(h, nullptr, dt, nullptr);
 }
@@ -585,8 +633,69 @@ int ppk_mhd3d_synchronize(ppk_mhd3d *h) {
   DeviceGuard guard(h->device);
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->comm_stream));
+  if (h->h2d_stream) CUDA_TRY(cudaStreamSynchronize(h->h2d_stream));
+  if (h->d2h_stream) CUDA_TRY(cudaStreamSynchronize(h->d2h_stream));
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+// ---- split-phase host transfers: batches pipelined on ONE handle ---------------------------------------------
+// Three conservative arrays rotate: the one a step reads (current), the one it writes, and a staging array that the
+// next batch is uploaded into while the step runs and the previous result is still being downloaded.
+static int stage_init(ppk_mhd3d *h) {
+  if (h->Ustage) return 0;
+  if (int rc = alloc_doubles(h, &h->Ustage, NBVAR * h->g.ncell)) return rc;
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_h2d, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));  // (the zero fill of the new array)
+  return 0;
+}
+
+int ppk_mhd3d_stage_upload(ppk_mhd3d *h, const double *u_host) {
+  if (!h || !u_host) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
+  DeviceGuard guard(h->device);
+  if (int rc = stage_init(h)) return rc;
+  // the staging array may still be the source of a staged download: the copy waits for it (and for nothing else)
+  for (auto &pd : h->d2h_pending)
+    if (pd.buf == h->Ustage) CUDA_TRY(cudaStreamWaitEvent(h->h2d_stream, pd.done, 0));
+  CUDA_TRY(cudaMemcpyAsync(h->Ustage, u_host, (size_t)NBVAR * h->g.ncell * sizeof(double), cudaMemcpyHostToDevice, h->h2d_stream));
+  CUDA_TRY(cudaEventRecord(h->ev_h2d, h->h2d_stream));
+  return 0;
+}
+
+int ppk_mhd3d_stage_swap(ppk_mhd3d *h) {
+  if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
+  if (!h->Ustage) return fail(PPK_ERR_STATE, "ppk_mhd3d_stage_swap before ppk_mhd3d_stage_upload");
+  DeviceGuard guard(h->device);
+  if (int rc = settle_halo(h)) return rc;
+  h->halo_posted = nullptr;
+  CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_h2d, 0));  // the step reads the staged array after its copy
+  std::swap(h->U[h->host_iteration & 1], h->Ustage);
+  return 0;
+}
+
+int ppk_mhd3d_stage_download(ppk_mhd3d *h, double *u_host) {
+  if (!h || !u_host) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
+  DeviceGuard guard(h->device);
+  if (int rc = stage_init(h)) return rc;
+  if (int rc = settle_halo(h)) return rc;
+  double *src = h->cur();
+  CUDA_TRY(cudaEventRecord(h->ev_main, h->stream));
+  CUDA_TRY(cudaStreamWaitEvent(h->d2h_stream, h->ev_main, 0));
+  CUDA_TRY(cudaMemcpyAsync(u_host, src, (size_t)NBVAR * h->g.ncell * sizeof(double), cudaMemcpyDeviceToHost, h->d2h_stream));
+  ppk_mhd3d::Pending *slot = nullptr;
+  for (auto &pd : h->d2h_pending)
+    if (pd.buf == src) slot = &pd;
+  if (!slot) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->d2h_pending.push_back({src, e});
+    slot = &h->d2h_pending.back();
+  }
+  CUDA_TRY(cudaEventRecord(slot->done, h->d2h_stream));
+  return 0;  // (whoever overwrites `src` later waits for slot->done: wait_staged_reads)
 }
 
 int ppk_mhd3d_diagnostics(ppk_mhd3d *h, double sums[8], double *max_divb) {
@@ -636,6 +745,19 @@ int ppk_mhd2d_create(const ppk_mhd3d_params *p, ppk_mhd2d **out) {
     return fail(PPK_ERR_NO_DEVICE, "no CUDA device: ppkmhd_b200 has no CPU fallback");
   if (p->device < 0 || p->device >= ndev) return fail(PPK_ERR_INVALID_ARGUMENT, "device ordinal out of range");
   ppk_mhd2d *h = new ppk_mhd2d();
+  if (int rc = create2d_impl(p, h)) {
+    const std::string msg = g_last_error;
+    ppk_mhd2d_destroy(h);
+    g_last_error = msg;
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+} // extern "C"
+namespace {
+int create2d_impl(const ppk_mhd3d_params *p, ppk_mhd2d *h) {
   h->device = p->device;
   h->kt = p->exact_arithmetic ? kernel_table_exact() : kernel_table_fast();
   GridParams &g = h->g;
@@ -669,9 +791,10 @@ int ppk_mhd2d_create(const ppk_mhd3d_params *p, ppk_mhd2d **out) {
   st0.t_end = 1e300;
   CUDA_TRY(cudaMemcpyAsync(h->st, &st0, sizeof(st0), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  *out = h;
   return 0;
 }
+}  // namespace
+extern "C" {
 
 int ppk_mhd2d_destroy(ppk_mhd2d *h) {
   if (!h) return 0;
@@ -874,6 +997,8 @@ int ppk_mhd3d_set_pipeline(ppk_mhd3d *h, int pipeline) {
   return 0;
 }
 
+int ppk_mhd3d_get_pipeline(ppk_mhd3d *h) { return h ? h->pipeline : -1; }
+
 int ppk_mhd3d_profile(ppk_mhd3d *h, int enable) {
   if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
   DeviceGuard guard(h->device);
@@ -917,7 +1042,7 @@ int ppk_mhd3d_debug_array(ppk_mhd3d *h, const char *name, double *host_out, int 
   else if (s == "Fluxes_z") { src = h->F[2]; nc = NFLUX; }
   else if (s == "Emf") { src = h->EMF; nc = NEMF; }
   else return fail(PPK_ERR_INVALID_ARGUMENT, "unknown array name " + s);
-  if (!src) return fail(PPK_ERR_STATE, s + " exists only in the unfused pipeline (ppk_mhd3d_set_pipeline)");
+  if (!src) return fail(PPK_ERR_STATE, s + " has not been produced by the pipeline of this handle (ppk_mhd3d_set_pipeline)");
   if (h->pipeline == PPK_PIPELINE_TILED && (s == "Q" || s == "ElecField"))
     return fail(PPK_ERR_STATE, s + " never reaches device memory in the tiled pipeline (ppk_mhd3d_set_pipeline)");
   // x periodic: the launchers skip the column i = nx+gw of the x-fluxes and of the z- / y-EMFs (the update reads the

@@ -58,6 +58,7 @@ DEV double vmin(double a, double b) { return a < b ? a : b; }
 #endif
 
 // TVD limited slope, MHDBaseFunctor3D.h:280-288 (hydro) and :605-665 (face B)
+#if PPK_EXACT
 DEV double limited_slope(double st, double q, double qplus, double qminus) {
   const double dlft = st * (q - qminus);
   const double drgt = st * (qplus - q);
@@ -68,6 +69,24 @@ DEV double limited_slope(double st, double q, double qplus, double qminus) {
   if ((dlft * drgt) <= 0.0) dlim = 0.0;
   return dsgn * vmin(dlim, fabs(dcen));
 }
+#else
+// The same value with 16 instructions instead of 21 (27 slopes per cell are a third of the producer's instructions):
+// min(|st a|, |st b|) = st min(|a|, |b|) (st > 0, rounding is monotonic); when a and b have the same sign, qplus - qminus
+// has it too, so the sign of the result is the sign of a and "a b <= 0" is a test on the two sign bits (a zero
+// difference makes the minimum zero by itself). Only the sign of a zero result can differ from the expression above.
+DEV double limited_slope(double st, double q, double qplus, double qminus) {
+  const double a = q - qminus, b = qplus - q, cen = qplus - qminus;
+  const double fa = fabs(a), fb = fabs(b);
+  const double m = st * (fa < fb ? fa : fb);
+  const double hc = 0.5 * fabs(cen);
+  const double r = m < hc ? m : hc;
+  const int ha = __double2hiint(a), hb = __double2hiint(b);
+  const bool opposite = (ha ^ hb) < 0;
+  const int hi = opposite ? 0 : (__double2hiint(r) | (ha & 0x80000000));
+  const int lo = opposite ? 0 : __double2loint(r);
+  return __hiloint2double(hi, lo);
+}
+#endif
 
 // find_speed_fast<dir>, mhd_utils.h:89-117; `n` is the field component normal to the direction
 DEV void fast_speed_common(double gamma0, double d, double p, double a, double b, double c, double &c2, double &d2) {
@@ -2243,12 +2262,16 @@ static void l_hydro(const GridParams &g, const StepState *st, const double *BASI
   int zchunk = (g.nz + nchunk - 1) / nchunk;
   if (zc_env > 0) zchunk = zc_env;
   dim3 grid(cdiv(g.nx, 32), cdiv(g.ny, SHY), cdiv(g.nz, zchunk));
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(k_hydro<168>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HydroSmem));
-    cudaFuncSetAttribute(k_hydro<112>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HydroSmem));
-    cudaFuncSetAttribute(k_hydro<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HydroSmem));
-    attr_done = true;
+  // the dynamic shared-memory limit is a per-device attribute of the function: set it once on every device used
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    if (cudaFuncSetAttribute(k_hydro<168>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HydroSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hydro<112>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HydroSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hydro<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HydroSmem)) != cudaSuccess)
+      return;  // the launch below would fail anyway; the sticky error reaches the caller through cudaGetLastError
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   if (minb == 1) k_hydro<168><<<grid, SH_THREADS, sizeof(HydroSmem), s>>>(g, st, BASIS, Uin, Uout, zchunk);
   else if (minb == 3) k_hydro<96><<<grid, SH_THREADS, sizeof(HydroSmem), s>>>(g, st, BASIS, Uin, Uout, zchunk);

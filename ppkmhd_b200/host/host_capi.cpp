@@ -5,6 +5,9 @@
 #include <fstream>
 #include <iostream>
 #include <thread>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <ctime>
 
 #include "../../include/ppkmhd_b200_host.h"
 #include "SolverMHDMusclCuda3D.h"
@@ -24,18 +27,26 @@ HydroParams params_for(ConfigMap &cfg, int rank_z) {
 // NCCL bootstrap without MPI: rank 0 publishes the 128-byte unique id in a file next to the output,
 // the other processes poll for it (the reference gets its communicator from MPI_Cart_create instead).
 int exchange_unique_id(const std::string &path, int rank, unsigned char id[128]) {
-  if (rank == 0) {
+  if (rank == 0 && id) {
     if (int rc = ppk_nccl_get_unique_id(id)) return rc;
     const std::string tmp = path + ".tmp";
     std::ofstream(tmp, std::ios::binary).write((const char *)id, 128);
     std::rename(tmp.c_str(), path.c_str());
     return 0;
   }
+  // a file left behind by a crashed run must not be mistaken for this run's id: the name carries the launcher's pid
+  // (see ppk_run_ini) and the file has to be younger than this process
+  static const time_t loaded = time(nullptr);  // (first call; ppk_run_ini touches it before it creates the solver)
+  if (rank < 0) return 0;
   for (int tries = 0; tries < 6000; ++tries) {
-    std::ifstream in(path, std::ios::binary);
-    if (in && in.read((char *)id, 128) && in.gcount() == 128) return 0;
+    struct stat sb;
+    if (stat(path.c_str(), &sb) == 0 && sb.st_mtime >= loaded - 120) {
+      std::ifstream in(path, std::ios::binary);
+      if (in && in.read((char *)id, 128) && in.gcount() == 128) return 0;
+    }
     std::this_thread::sleep_for(std::chrono::milliseconds(10));
   }
+  fprintf(stderr, "rank %d: no NCCL unique id appeared at %s within 60 s\n", rank, path.c_str());
   return PPK_ERR_NCCL;
 }
 }  // namespace
@@ -79,6 +90,7 @@ int ppk_run_ini(const char *ini_path, int rank, int nranks) {
     fprintf(stderr, "cannot read parameter file %s\n", ini_path);
     return PPK_ERR_INVALID_ARGUMENT;
   }
+  exchange_unique_id("", -1, nullptr);  // records the start time of this run (see the staleness check there)
   HydroParams params;
   if (rank >= 0) {
     params.forcedRank = rank;
@@ -91,12 +103,22 @@ int ppk_run_ini(const char *ini_path, int rank, int nranks) {
   if (params.nProcs > 1) {
     unsigned char id[128];
     const char *port = getenv("MASTER_PORT");
-    const std::string path = configMap.getString("output", "outputDir", "./") + "/.ppk_nccl_id_" + (port ? port : "0");
+    // one file per launch: the ranks of a launch share MASTER_PORT (torchrun) and their parent process (the launcher)
+    const char *nonce = getenv("PPK_RUN_NONCE");
+    const std::string path = configMap.getString("output", "outputDir", "./") + "/.ppk_nccl_id_" + (port ? port : "0") + "_" +
+                             (nonce ? std::string(nonce) : std::to_string((long)getppid()));
+    SolverMHDMusclCuda3D *solver3d = dynamic_cast<SolverMHDMusclCuda3D *>(solver);
+    if (!solver3d) {
+      fprintf(stderr, "[mpi] mx*my*mz > 1 is only supported by MHD_Muscl_3D (z-slabs); %s is single-GPU\n", solver_name.c_str());
+      delete solver;
+      return PPK_ERR_UNSUPPORTED;
+    }
+    if (params.myRank == 0) std::remove(path.c_str());  // (rank 0 writes it through a rename: never half-visible)
     if (int rc = exchange_unique_id(path, params.myRank, id)) {
       fprintf(stderr, "NCCL unique-id exchange failed: %s\n", ppk_last_error_string());
       return rc;
     }
-    static_cast<SolverMHDMusclCuda3D *>(solver)->comm_init(id);
+    solver3d->comm_init(id);
     if (params.myRank == 0) std::remove(path.c_str());
   }
 
