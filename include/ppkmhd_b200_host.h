@@ -30,6 +30,13 @@ int ppk_init_condition_from_ini(const char *ini_text, int rank_z, double *u_host
  * u_host (8*isize*jsize doubles). */
 int ppk_init_condition_2d_from_ini(const char *ini_text, double *u_host);
 
+/* SolverBase::save_data (src/shared/SolverBase.cpp:286-310 -> IO_ReadWrite::save_data, src/utils/io/IO_ReadWrite.cpp:60-130)
+ * for the state `u_host` (8*isize*jsize*ksize doubles of slab `rank_z`, ghosts included) as output number `i_step`:
+ * a single .vti (IO_VTK.cpp:211-408) for an undecomposed run; with [mpi] mz > 1 the piece `_time%07d_mpi%05d.vti` of this
+ * slab (IO_VTK.cpp:630-853) and, from slab 0, the `.pvti` header naming every piece (IO_VTK.cpp:860-1008). Host only:
+ * needs no GPU (the solvers call the same writer after ppk_mhd3d_download). */
+int ppk_save_data_from_ini(const char *ini_text, int rank_z, const double *u_host, int i_step);
+
 /* The whole program of src/main.cpp: read the ini file, create the solver through SolverFactory, run the
  * time loop, write VTK output, print the monitoring table. rank < 0: take RANK / WORLD_SIZE from the env. */
 int ppk_run_ini(const char *ini_path, int rank, int nranks);

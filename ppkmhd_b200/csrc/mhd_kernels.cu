@@ -1439,6 +1439,8 @@ __global__ void __launch_bounds__(128, 5)
   }
 }
 
+#include "mhd_rpers.inc"
+
 // Kokkos::deep_copy(data_out, data_in) (SolverMHDMuscl.cpp:477) + UpdateFunctor3D_MHD
 // (MHDRunFunctors3D.h:2430-2544) + UpdateEmfFunctor3D (:2549-2628) in one pass over the array:
 // ghost cells are copied, interior cells receive the 6 face fluxes (fixed order) and the CT update.
@@ -2030,6 +2032,8 @@ static void l_trace(const GridParams &g, const StepState *st, const double *U, c
 struct TmaCtx {
   CUtensorMap emfB[3], emfD[3], fluxB[3];
   RiemannMaps rall;  // the same nine maps, as the single kernel parameter of k_riemann_all
+  unsigned *counter = nullptr;  // work-item counter of k_riemann_pers (device memory, zeroed before every launch)
+  int sms = 148;
 };
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -2047,6 +2051,7 @@ template <class Cfg> static bool encode_cfg(EncodeTiledFn enc, CUtensorMap *m, c
 }
 // returns nullptr when TMA staging cannot be used (odd isize => global strides not 16-byte multiples, or
 // PPK_TMA=0): the plain kernels then do all the work
+static void l_tma_destroy(void *ctx);
 static void *l_tma_create(const GridParams &g, const double *BASIS, const double *DBF) {
   if (getenv("PPK_TMA") && atoi(getenv("PPK_TMA")) == 0) return nullptr;
   if ((g.isize & 1) || g.nx < 32) return nullptr;
@@ -2086,9 +2091,21 @@ static void *l_tma_create(const GridParams &g, const double *BASIS, const double
     delete c;
     return nullptr;
   }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaFuncSetAttribute(k_riemann_pers<RIEMANN_HLLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, RALL_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(k_riemann_pers<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RALL_SMEM) != cudaSuccess ||
+      cudaMalloc(&c->counter, sizeof(unsigned)) != cudaSuccess) {
+    l_tma_destroy(c);
+    return nullptr;
+  }
   return c;
 }
-static void l_tma_destroy(void *ctx) { delete (TmaCtx *)ctx; }
+static void l_tma_destroy(void *ctx) {
+  TmaCtx *c = (TmaCtx *)ctx;
+  if (c && c->counter) cudaFree(c->counter);
+  delete c;
+}
 
 template <int D>
 static void launch_flux(const GridParams &g, const double *BASIS, double *F, const TmaCtx *tma, cudaStream_t s) {
@@ -2208,7 +2225,15 @@ static int l_riemann_all(const GridParams &g, const double *BASIS, const double 
   pl.per_slab = (unsigned)(g.nz + 1) * pl.per_plane;
   const unsigned long long total = (unsigned long long)nslab * pl.per_slab;
   if (total > 0x7FFFFFFFull || ntx < 1) return -1;
-  if (g.riemann == RIEMANN_HLLD) k_riemann_all<RIEMANN_HLLD><<<(unsigned)total, 128, RALL_SMEM, s>>>(g, pl, tma->rall, F0, F1, F2, EMF);
+  // persistent CTAs (mhd_rpers.inc) unless PPK_RALL_PERS=0 selects the single-shot form
+  static const int pers = getenv("PPK_RALL_PERS") ? atoi(getenv("PPK_RALL_PERS")) : 1;
+  static const int pers_ctas = getenv("PPK_RALL_CTAS") ? atoi(getenv("PPK_RALL_CTAS")) : 5;
+  if (pers && total > (unsigned long long)tma->sms * pers_ctas) {
+    const unsigned G = (unsigned)(tma->sms * pers_ctas);
+    cudaMemsetAsync(tma->counter, 0, sizeof(unsigned), s);
+    if (g.riemann == RIEMANN_HLLD) k_riemann_pers<RIEMANN_HLLD><<<G, 128, RALL_SMEM, s>>>(g, pl, tma->rall, F0, F1, F2, EMF, (unsigned)total, tma->counter);
+    else k_riemann_pers<-1><<<G, 128, RALL_SMEM, s>>>(g, pl, tma->rall, F0, F1, F2, EMF, (unsigned)total, tma->counter);
+  } else if (g.riemann == RIEMANN_HLLD) k_riemann_all<RIEMANN_HLLD><<<(unsigned)total, 128, RALL_SMEM, s>>>(g, pl, tma->rall, F0, F1, F2, EMF);
   else k_riemann_all<-1><<<(unsigned)total, 128, RALL_SMEM, s>>>(g, pl, tma->rall, F0, F1, F2, EMF);
   if (!wrap) {
     const int bs = 128;

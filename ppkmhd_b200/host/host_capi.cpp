@@ -73,6 +73,19 @@ int ppk_init_condition_from_ini(const char *ini_text, int rank_z, double *u_host
   return 0;
 }
 
+int ppk_save_data_from_ini(const char *ini_text, int rank_z, const double *u_host, int i_step) {
+  if (!ini_text || !u_host) return PPK_ERR_INVALID_ARGUMENT;
+  ConfigMap cfg(ini_text, (int)strlen(ini_text));
+  HydroParams p = params_for(cfg, rank_z);
+  DataArray3dHost U(p.isize, p.jsize, p.dimType == TWO_D ? 1 : p.ksize, p.nbvar);
+  memcpy(U.data(), u_host, U.size() * sizeof(double));
+  std::map<int, std::string> names = {{ID, "rho"}, {IP, "energy"}, {IU, "rho_vx"}, {IV, "rho_vy"}, {IW, "rho_vz"},
+                                      {IA, "bx"},  {IB, "by"},     {IC, "bz"}};  // SolverBase.cpp:49-56
+  io::IO_ReadWrite writer(p, cfg, names);
+  writer.save_data(U, i_step, 0.0, "");
+  return 0;
+}
+
 int ppk_init_condition_2d_from_ini(const char *ini_text, double *u_host) {
   if (!ini_text || !u_host) return PPK_ERR_INVALID_ARGUMENT;
   ConfigMap cfg(ini_text, (int)strlen(ini_text));

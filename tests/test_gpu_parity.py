@@ -169,6 +169,79 @@ def test_hundred_steps_conserved_sums_and_divb(oracle_mod):
         s.close()
 
 
+def test_benchmarked_workload_128_vs_oracle(oracle_mod):
+    """The workload bench.py times (Orszag-Tang kt=1: a genuinely 3-D flow, every flux and EMF component exercised) at
+    128^3 against the oracle: the exact build bit for bit after 1 and 3 steps on the default (tiled) and the unfused
+    pipeline, the fast build (the one that is benchmarked) within 1e-12 per cell after one step."""
+    O = oracle_mod
+    ini = O.make_ini("orszag_tang", (128, 128, 128), nstepmax=3, extra=OT, tend=10.0)
+    orc = O.Oracle(ini)
+    orc.step()
+    ref1 = orc.interior().copy()
+    orc.step()
+    orc.step()
+    ref3 = orc.interior()
+    for pipeline in (None, "unfused"):
+        s, _ = make_solver(ini, exact=True, pipeline=pipeline)
+        s.step()
+        assert np.array_equal(s.interior(), ref1), f"exact build, pipeline {pipeline}: step 1 differs from the oracle"
+        s.run(2)
+        assert s.get_time()[0] == orc.t
+        assert np.array_equal(s.interior(), ref3), f"exact build, pipeline {pipeline}: step 3 differs from the oracle"
+        s.close()
+        f, _ = make_solver(ini, exact=False, pipeline=pipeline)
+        f.step()
+        close_per_cell(f.interior(), ref1, 1e-12)
+        f.run(2)
+        close_per_cell(f.interior(), ref3, 1e-11)
+        f.close()
+
+
+def test_benchmarked_workload_256_fast_vs_exact():
+    """BASELINE configs[1] exactly as bench.py runs it (Orszag-Tang kt=1, 256^3, fast build, default pipeline) against the
+    exact build, which is pinned to the reference bit for bit at every size the oracle can reach: 1e-12 per cell after
+    one step (north-star criterion)."""
+    from oracle import oracle as O  # ini text helper only
+
+    ini = O.make_ini("orszag_tang", (256, 256, 256), nstepmax=1, extra=OT, tend=10.0)
+    e, _ = make_solver(ini, exact=True)
+    e.step()
+    want = e.interior()
+    te, dte, _ = e.get_time()
+    e.close()
+    for pipeline in (None, "unfused"):
+        f, _ = make_solver(ini, exact=False, pipeline=pipeline)
+        f.step()
+        tf, dtf, _ = f.get_time()
+        assert abs(dtf - dte) <= 1e-14 * dte
+        close_per_cell(f.interior(), want, 1e-12)
+        f.close()
+
+
+def test_hundred_steps_128_conserved_sums_and_divb(oracle_mod):
+    """North-star 100-step criterion at the size SURVEY 8(d) names (128^3, kt=1): total mass, momentum, energy and
+    magnetic flux within 1e-10 relative of the reference arithmetic (the pinned oracle), max|div B| <= 1e-12; the exact
+    build reproduces the oracle's state bit for bit after the 100 steps."""
+    O = oracle_mod
+    ini = O.make_ini("orszag_tang", (128, 128, 128), nstepmax=100, extra=OT, tend=10.0)
+    orc = O.Oracle(ini).run()
+    so, divb_o = orc.diagnostics()
+    scale = np.abs(orc.interior()).reshape(8, -1).sum(axis=1)
+    for exact in (True, False):
+        s, nstep = make_solver(ini, exact=exact)
+        s.run(nstep)
+        t, _, it = s.get_time()
+        assert it == 100
+        sums, divb = s.diagnostics()
+        assert np.all(np.abs(sums - so) <= 1e-10 * np.maximum(np.abs(so), 1e-2 * scale)), (sums, so)
+        assert divb <= max(1e-12, 4 * divb_o), (divb, divb_o)
+        if exact:
+            assert t == orc.t and np.array_equal(s.interior(), orc.interior())
+        else:
+            assert abs(t - orc.t) <= 1e-12
+        s.close()
+
+
 def test_dropin_executable_matches_reference_vti_bytes(oracle_mod):
     """ppkMHD_b200 <ini> (SolverFactory -> 'MHD_Muscl_3D' -> C ABI) writes the same .vti payload as the
     reference; when the reference binary travelled to this box, compare the files byte for byte."""

@@ -116,3 +116,57 @@ def test_initial_condition_2d_bitwise(oracle_mod):
         Uo = np.zeros_like(U)
         oracle_mod.init_problem_2d(orc.p, orc.cfg, Uo)
         assert np.array_equal(U, Uo), f
+
+
+def test_pvti_pieces_reassemble_to_the_single_vti(tmp_path):
+    """Output contract of a decomposed run (src/utils/io/IO_VTK.cpp:630-853 pieces, :860-1008 .pvti header): three z-slabs
+    written through the host layer's save_data must (a) carry the header text the reference writes, line for line, (b) name
+    their pieces with the extents of the MPI coordinates, and (c) reassemble, piece by piece, to exactly the payload of the
+    single .vti an undecomposed run writes for the same global state. Host code only: no GPU."""
+    import re
+
+    import ppkmhd_b200 as ppk
+    from oracle import oracle as O
+
+    nx, ny, nzl, mz, gw = 10, 6, 4, 3, 3
+    rng = np.random.default_rng(11)
+    glob = rng.standard_normal((8, nzl * mz + 2 * gw, ny + 2 * gw, nx + 2 * gw))
+    ini_1 = O.make_ini("orszag_tang", (nx, ny, nzl * mz), bounds=(0.0, 1.0, 0.0, 0.5, -1.0, 2.0)).replace("outputPrefix=run", f"outputDir={tmp_path}\noutputPrefix=one")
+    ini_n = O.make_ini("orszag_tang", (nx, ny, nzl), mz=mz, bounds=(0.0, 1.0, 0.0, 0.5, -1.0, 2.0)).replace("outputPrefix=run", f"outputDir={tmp_path}\noutputPrefix=slab")
+    ppk.save_data_from_ini(ini_1, glob, 7)
+    for r in range(mz):
+        ppk.save_data_from_ini(ini_n, glob[:, r * nzl:r * nzl + nzl + 2 * gw], 7, rank_z=r)
+    whole = O.read_vti(str(tmp_path / "one_0000007.vti"))
+    assert np.array_equal(whole, glob[:, gw:-gw, gw:-gw, gw:-gw])
+
+    # (a) header, line by line (write_pvti_header, IO_VTK.cpp:905-1003); dx = 1/10, dy = 0.5/6, dz = 3/12 as operator<< prints them
+    p, _, _ = ppk.params_from_ini(ini_n)
+    fmt = lambda x: np.format_float_positional(x, precision=6, unique=True, fractional=False, trim="-")
+    names = ["rho", "energy", "rho_vx", "rho_vy", "rho_vz", "bx", "by", "bz"]
+    want = ['<?xml version="1.0"?>',
+            '<VTKFile type="PImageData" version="1.0" byte_order="LittleEndian" header_type="UInt64">',
+            f'  <PImageData WholeExtent="0 {nx} 0 {ny} 0 {mz * nzl}" GhostLevel="0" Origin="0 0 -1" Spacing="{fmt(p.dx)} {fmt(p.dy)} {fmt(p.dz)}">',
+            '    <PCellData Scalars="Scalars_">'] + [f'      <PDataArray type="Float64" Name="{n}"/>' for n in names] + ['    </PCellData>']
+    want += [f' <Piece Extent="0 {nx} 0 {ny} {r * nzl} {r * nzl + nzl} " Source="slab_time0000007_mpi{r:05d}.vti"/>' for r in range(mz)]
+    want += ['</PImageData>', '</VTKFile>']
+    got = open(tmp_path / "slab_time0000007.pvti").read().splitlines()
+    assert got == want, "\n".join(got)
+
+    # (b) + (c): follow the .pvti to its pieces and rebuild the global payload
+    rebuilt = np.full_like(whole, np.nan)
+    for ln in got:
+        m = re.match(r' <Piece Extent="(\d+) (\d+) (\d+) (\d+) (\d+) (\d+) " Source="([^"]+)"/>', ln)
+        if not m:
+            continue
+        x0, x1, y0, y1, z0, z1 = (int(m.group(i)) for i in range(1, 7))
+        blob = open(tmp_path / m.group(7), "rb").read()
+        head = blob[:blob.index(b"<AppendedData")].decode()
+        assert '<VTKFile type="ImageData" version="1.0" byte_order="LittleEndian" header_type="UInt64">' in head
+        assert f'WholeExtent="{x0} {x1} {y0} {y1} {z0} {z1}"' in head and f'<Piece Extent="{x0} {x1} {y0} {y1} {z0} {z1}">' in head
+        pos = blob.index(b"_", blob.index(b"<AppendedData")) + 1
+        for v in range(8):
+            nbytes = int(np.frombuffer(blob, dtype="<u8", count=1, offset=pos)[0])
+            assert nbytes == (x1 - x0) * (y1 - y0) * (z1 - z0) * 8
+            rebuilt[v, z0:z1, y0:y1, x0:x1] = np.frombuffer(blob, dtype="<f8", count=nbytes // 8, offset=pos + 8).reshape(z1 - z0, y1 - y0, x1 - x0)
+            pos += 8 + nbytes
+    assert np.array_equal(rebuilt, whole)
