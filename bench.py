@@ -417,7 +417,9 @@ def run_ours(args):
     traffic, fp64 = None, None
     cpath = os.path.join(ROOT, "profiles", "r2", "counters.json")
     if os.path.exists(cpath):
-        cj = json.load(open(cpath)).get(pipeline)
+        allj = json.load(open(cpath))
+        # the capture of this pipeline at this size, else at another size (per-cell figures are size-independent to ~1 %)
+        cj = allj.get(f"{pipeline}_{n}") or next((v for k, v in sorted(allj.items()) if v.get("pipeline") == pipeline), None)
         if cj:
             scale = cells_rank / float(cj["cells"])
             if dom in cj["kernels"]:
@@ -441,16 +443,23 @@ def run_ours(args):
                         "instructions per cell-update: FP64 pipe and instruction issue bound it near 5 Gcell/s = 10% of the "
                         "HBM roofline; see DESIGN.md"}
 
+    nbytes = int(np.prod(p.shape)) * 8
     # ---- e2e leg: host buffers through the C ABI, H2D + step + D2H every step ------------------
     # Every step is one batch: a full host state (pinned) goes to the device, advances one step, and the full result comes
-    # back. ONE handle at every N: ppk_mhd3d_stage_upload / _stage_swap / _step / _stage_download rotate three device arrays
+    # back. ONE handle at every N: ppk_mhd3d_stage_upload / _stage_swap / _step / _stage_download rotate four device arrays
     # so that the upload of batch i+1 (copy stream 1) overlaps the step of batch i and the download of batch i-1 (copy
     # stream 2); PCIe is full duplex and bounds the leg.
     Ke = max(2, min(K, args.e2e_steps))
-    nbytes = int(np.prod(p.shape)) * 8
-    host_in = [host, torch.empty(p.shape, dtype=torch.float64).pin_memory()]
-    host_in[1].copy_(host)
-    host_out = [torch.empty(p.shape, dtype=torch.float64).pin_memory() for _ in range(2)]
+    # pinned host buffers: every batch uploads the same initial state (one input buffer); results alternate between two
+    # output buffers when the host has room for them (8.9 GB each at 512^3, per rank), else share one
+    try:
+        import psutil
+        host_free = psutil.virtual_memory().available
+    except Exception:
+        host_free = 0
+    n_out = 2 if host_free > 4 * nbytes * max(world, 1) else 1
+    host_in = [host, host]
+    host_out = [torch.empty(p.shape, dtype=torch.float64).pin_memory() for _ in range(n_out)] * (2 // n_out)
 
     def e2e_pass(nsteps):
         solver.stage_upload(host_in[0].data_ptr())
@@ -477,7 +486,7 @@ def run_ours(args):
            "d2h_bytes_per_step": nbytes * world, "steps": Ke, "ms_per_step": ems / Ke, "wall_ms_per_step": (w1 - w0) * 1e3 / Ke,
            "pcie_GBs_per_gpu_each_way": nbytes / (ems / Ke * 1e-3) / 1e9,
            "what": "per step: ppk_mhd3d_stage_upload(pinned host U) + _stage_swap + ppk_mhd3d_step + ppk_mhd3d_stage_download("
-                   "pinned host U) on one handle per GPU; three device arrays rotate, uploads, steps and downloads of "
+                   "pinned host U) on one handle per GPU; four device arrays rotate, uploads, steps and downloads of "
                    "consecutive batches overlap on three streams"}
     del host_in, host_out
 
@@ -558,8 +567,8 @@ def main():
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the 256^3 (configs[1]) measurement beside the headline size")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
-    ap.add_argument("--pipeline", default="auto", choices=["auto", "tiled", "fused", "fused_split", "unfused", "streamed"],
-                    help="auto = the handle's default (tiled on one slab, unfused on decomposed runs)")
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "ordered", "tiled", "fused", "fused_split", "unfused", "streamed"],
+                    help="auto = the handle's default (unfused below 384^2-cell planes, ordered above)")
     ap.add_argument("--ref-n", type=int, default=256, help="grid of the reference arm's bounded sample (--impl reference)")
     ap.add_argument("--e2e-steps", type=int, default=9)
     ap.add_argument("--no-cpu-baseline", action="store_true")

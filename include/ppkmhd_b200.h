@@ -82,7 +82,8 @@ int ppk_mhd3d_download(ppk_mhd3d *handle, double *u_host);
 int ppk_mhd3d_download_async(ppk_mhd3d *handle, double *u_host);
 
 /* Split-phase host transfers: batches pipelined on ONE handle (bench.py's end-to-end leg at sizes where several handles do not
- * fit in HBM). A third conservative array rotates with U and U2:
+ * fit in HBM). A third conservative array rotates with U and U2 (and a fourth one, allocated the first time an upload
+ * finds the third still being downloaded):
  *   ppk_mhd3d_stage_upload  : asynchronous H2D of a full state (pinned `u_host`) into the staging array, on its own copy stream;
  *                             overlaps a running step and a running stage_download of another array;
  *   ppk_mhd3d_stage_swap    : the staged array becomes the current array (the previous current array becomes the staging
@@ -152,8 +153,9 @@ int ppk_mhd3d_halo_plan(const ppk_mhd3d_params *params, int capacity, ppk_halo_m
 /* Run on a caller-owned stream (a cudaStream_t, e.g. torch's current stream) instead of the
  * handle's own non-blocking stream. */
 int ppk_mhd3d_set_stream(ppk_mhd3d *handle, void *cuda_stream);
-/* Kernel schedule of one step (results are identical, bit for bit in exact mode):
- *   PPK_PIPELINE_UNFUSED (round 1's default; the schedule of decomposed runs): ghost fill | primitives + CFL | edge E +
+/* Kernel schedule of one step (results are identical, bit for bit in exact mode). The default is picked from measurements
+ * (DESIGN.md 4): UNFUSED for planes below 384^2 cells, ORDERED above; every schedule stays selectable and tested.
+ *   PPK_PIPELINE_UNFUSED: ghost fill | primitives + CFL | edge E +
  *       face-B slopes | Hancock trace | one TMA-staged kernel per flux direction and EMF component | update;
  *       stores Fluxes_x|y|z and Emf like the reference's v0 (what ppk_mhd3d_debug_array exposes);
  *   PPK_PIPELINE_FUSED: after the trace, ONE z-marching consumer kernel = HLLD fluxes x,y,z + edge EMFs z,y,x +
@@ -163,11 +165,15 @@ int ppk_mhd3d_set_stream(ppk_mhd3d *handle, void *cuda_stream);
  *   PPK_PIPELINE_STREAMED: after the trace, one z-marching kernel whose threads exchange one-sided states (warp
  *       shuffles / shared memory) solves the three HLLD fluxes of every cell and applies the hydro update (no flux
  *       array), then the TMA-staged EMF kernels and the CT update of the field.
- *   PPK_PIPELINE_TILED (default where available: even nx >= 32, mz = 1): ghost fill | CFL reduction (reads U only) |
+ *   PPK_PIPELINE_ORDERED: UNFUSED with the six flux / EMF kernels replaced by ONE launch whose CTAs are dispatched in the
+ *       order (y-slab, plane, task, tile): the basis numbers of a plane come from HBM for the first task that touches them
+ *       and from the L2 for the five others (512^3: 33.6 -> 31.2 ms). Works on decomposed runs (mz > 1) like UNFUSED;
+ *       falls back to UNFUSED where the TMA tiles do not exist (odd nx, nx < 32).
+ *   PPK_PIPELINE_TILED (even nx >= 32, mz = 1): ghost fill | CFL reduction (reads U only) |
  *       ONE fused producer kernel = primitives + edge electric field + face-field slopes + hydro slopes + Hancock trace
  *       on TMA-staged U tiles marching in z (Q and E never reach HBM) | ONE launch with the six flux / EMF tasks ordered
  *       (y-slab, plane, task, tile) so that the basis is read from HBM once and from the L2 five times | update. */
-enum ppk_pipeline { PPK_PIPELINE_UNFUSED = 0, PPK_PIPELINE_FUSED = 1, PPK_PIPELINE_FUSED_SPLIT = 2, PPK_PIPELINE_STREAMED = 3, PPK_PIPELINE_TILED = 4 };
+enum ppk_pipeline { PPK_PIPELINE_UNFUSED = 0, PPK_PIPELINE_FUSED = 1, PPK_PIPELINE_FUSED_SPLIT = 2, PPK_PIPELINE_STREAMED = 3, PPK_PIPELINE_TILED = 4, PPK_PIPELINE_ORDERED = 5 };
 int ppk_mhd3d_set_pipeline(ppk_mhd3d *handle, int pipeline);
 int ppk_mhd3d_get_pipeline(ppk_mhd3d *handle); /* the schedule in use (enum ppk_pipeline), -1 for a null handle */
 /* Per-kernel CUDA-event timing (replaces the coarse timers of SolverBase.h:35-42 for profiling).

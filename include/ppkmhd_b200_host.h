@@ -37,6 +37,16 @@ int ppk_init_condition_2d_from_ini(const char *ini_text, double *u_host);
  * needs no GPU (the solvers call the same writer after ppk_mhd3d_download). */
 int ppk_save_data_from_ini(const char *ini_text, int rank_z, const double *u_host, int i_step);
 
+/* 1 when a libhdf5 (>= 1.10) was found at run time (dlopen; PPK_HDF5_LIB overrides the search), else 0. The reference
+ * decides this at build time (USE_HDF5); with 0, [output] hdf5_enabled=true makes ppk_save_data_from_ini return
+ * PPK_ERR_UNSUPPORTED after writing the VTK files, and [run] restart_enabled=true stops the program with a message. */
+int ppk_hdf5_available(void);
+
+/* writeXdmfForHdf5Wrapper (src/utils/io/IO_HDF5.cpp:16-378): the Xdmf light-data file <outputPrefix>.xmf (or
+ * <outputPrefix>_%07d.xmf when single_step) in the current directory, naming the datasets of <outputPrefix>_%07d.h5 for
+ * the outputs 0 .. total_number_of_steps. Plain text: needs no HDF5 library. */
+int ppk_write_xdmf_from_ini(const char *ini_text, int total_number_of_steps, int single_step);
+
 /* The whole program of src/main.cpp: read the ini file, create the solver through SolverFactory, run the
  * time loop, write VTK output, print the monitoring table. rank < 0: take RANK / WORLD_SIZE from the env. */
 int ppk_run_ini(const char *ini_path, int rank, int nranks);

@@ -66,7 +66,7 @@ EXPORTS = [
     "ppk_mhd3d_debug_array", "ppk_mhd3d_device_bytes", "ppk_last_error_string", "ppk_version_string",
     "ppk_mhd3d_halo_plan", "ppk_selftest_fastmath", "ppk_mhd3d_set_pipeline",
     "ppk_mhd3d_get_pipeline", "ppk_mhd3d_stage_upload", "ppk_mhd3d_stage_swap", "ppk_mhd3d_stage_download",
-    "ppk_params_from_ini", "ppk_init_condition_from_ini", "ppk_run_ini", "ppk_save_data_from_ini", "ppk_init_condition_2d_from_ini",
+    "ppk_params_from_ini", "ppk_init_condition_from_ini", "ppk_run_ini", "ppk_save_data_from_ini", "ppk_hdf5_available", "ppk_write_xdmf_from_ini", "ppk_init_condition_2d_from_ini",
     "ppk_mhd2d_create", "ppk_mhd2d_destroy", "ppk_mhd2d_upload", "ppk_mhd2d_download", "ppk_mhd2d_set_time", "ppk_mhd2d_get_time",
     "ppk_mhd2d_make_boundaries", "ppk_mhd2d_compute_dt", "ppk_mhd2d_step", "ppk_mhd2d_run", "ppk_mhd2d_synchronize", "ppk_mhd2d_launch_count",
 ]
@@ -117,6 +117,7 @@ def load_library():
     L.ppk_params_from_ini.argtypes = [C.c_char_p, C.c_int, C.POINTER(Params), dp, ip]
     L.ppk_init_condition_from_ini.argtypes = [C.c_char_p, C.c_int, vp]
     L.ppk_save_data_from_ini.argtypes = [C.c_char_p, C.c_int, vp, C.c_int]
+    L.ppk_write_xdmf_from_ini.argtypes = [C.c_char_p, C.c_int, C.c_int]
     L.ppk_run_ini.argtypes = [C.c_char_p, C.c_int, C.c_int]
     L.ppk_init_condition_2d_from_ini.argtypes = [C.c_char_p, vp]
     L.ppk_mhd2d_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
@@ -165,6 +166,15 @@ def save_data_from_ini(ini_text: str, U: np.ndarray, i_step: int, rank_z: int = 
     L = load_library()
     U = np.ascontiguousarray(U, dtype=np.float64)
     _check(L.ppk_save_data_from_ini(ini_text.encode(), rank_z, U.ctypes.data, i_step))
+
+
+def hdf5_available() -> bool:
+    return bool(load_library().ppk_hdf5_available())
+
+
+def write_xdmf_from_ini(ini_text: str, total_steps: int, single_step: bool = False) -> None:
+    """ppk_write_xdmf_from_ini: the reference's Xdmf wrapper text (written into the current directory)."""
+    _check(load_library().ppk_write_xdmf_from_ini(ini_text.encode(), total_steps, 1 if single_step else 0))
 
 
 def init_condition_2d_from_ini(ini_text: str) -> np.ndarray:
@@ -324,7 +334,7 @@ class Mhd3d:
     def set_stream(self, stream_ptr):
         _check(self.L.ppk_mhd3d_set_stream(self.h, stream_ptr))
 
-    PIPELINES = {"unfused": 0, "fused": 1, "fused_split": 2, "streamed": 3, "tiled": 4}
+    PIPELINES = {"unfused": 0, "fused": 1, "fused_split": 2, "streamed": 3, "tiled": 4, "ordered": 5}
 
     def set_pipeline(self, name: str):
         _check(self.L.ppk_mhd3d_set_pipeline(self.h, self.PIPELINES[name]))

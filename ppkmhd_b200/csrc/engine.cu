@@ -106,7 +106,7 @@ struct ppk_mhd3d {
   void *tma = nullptr;  // tensor maps for the TMA-staged flux / EMF kernels
   void *prod = nullptr; // tensor maps of U / U2 for the fused producer (tiled pipeline)
   // split-phase host transfers (ppk_mhd3d_stage_*): a third conservative array and two copy streams
-  double *Ustage = nullptr;
+  double *Ustage = nullptr, *Uspare = nullptr;  // upload target / a second one while the first is still being downloaded
   cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   cudaEvent_t ev_h2d = nullptr, ev_main = nullptr;
   struct Pending { double *buf; cudaEvent_t done; };
@@ -345,16 +345,23 @@ int enqueue_step(ppk_mhd3d *h) {
   { Scope sc(h, KK_ELEC_DBF, s); h->kt->elec_dbf(g, Uin, h->Q, h->E, h->DBF, s); }
   if (multi) CUDA_TRY(cudaStreamWaitEvent(s, h->ev_dt, 0));
   { Scope sc(h, KK_TRACE, s); h->kt->trace(g, h->st, Uin, h->Q, h->E, h->BASIS, s); }
-  if (h->pipeline == PPK_PIPELINE_UNFUSED) {
+  if (h->pipeline == PPK_PIPELINE_UNFUSED || h->pipeline == PPK_PIPELINE_ORDERED) {
     if (!h->F[0]) {  // flux / EMF arrays are allocated on first use of this pipeline
-      if (int rc = ppk_mhd3d_set_pipeline(h, PPK_PIPELINE_UNFUSED)) return rc;
+      if (int rc = ppk_mhd3d_set_pipeline(h, h->pipeline)) return rc;
     }
-    { Scope sc(h, KK_FLUX_X, s); h->kt->flux(g, 0, h->BASIS, h->F[0], h->tma, s); }
-    { Scope sc(h, KK_FLUX_Y, s); h->kt->flux(g, 1, h->BASIS, h->F[1], h->tma, s); }
-    { Scope sc(h, KK_FLUX_Z, s); h->kt->flux(g, 2, h->BASIS, h->F[2], h->tma, s); }
-    { Scope sc(h, KK_EMF_Z, s); h->kt->emf(g, 2, h->BASIS, h->DBF, h->EMF, h->tma, s); }
-    { Scope sc(h, KK_EMF_Y, s); h->kt->emf(g, 1, h->BASIS, h->DBF, h->EMF, h->tma, s); }
-    { Scope sc(h, KK_EMF_X, s); h->kt->emf(g, 0, h->BASIS, h->DBF, h->EMF, h->tma, s); }
+    bool one_launch = false;
+    if (h->pipeline == PPK_PIPELINE_ORDERED) {  // the six tasks as ONE launch, ordered (y-slab, plane, task, tile) for the L2
+      Scope sc(h, KK_RIEMANN_ALL, s);
+      one_launch = h->kt->riemann_all(g, h->BASIS, h->DBF, h->F[0], h->F[1], h->F[2], h->EMF, h->tma, s) == 0;
+    }
+    if (!one_launch) {
+      { Scope sc(h, KK_FLUX_X, s); h->kt->flux(g, 0, h->BASIS, h->F[0], h->tma, s); }
+      { Scope sc(h, KK_FLUX_Y, s); h->kt->flux(g, 1, h->BASIS, h->F[1], h->tma, s); }
+      { Scope sc(h, KK_FLUX_Z, s); h->kt->flux(g, 2, h->BASIS, h->F[2], h->tma, s); }
+      { Scope sc(h, KK_EMF_Z, s); h->kt->emf(g, 2, h->BASIS, h->DBF, h->EMF, h->tma, s); }
+      { Scope sc(h, KK_EMF_Y, s); h->kt->emf(g, 1, h->BASIS, h->DBF, h->EMF, h->tma, s); }
+      { Scope sc(h, KK_EMF_X, s); h->kt->emf(g, 0, h->BASIS, h->DBF, h->EMF, h->tma, s); }
+    }
     const bool exch = h->exch_lo || h->exch_hi;
     if (exch && h->comm && h->early_halo && g.nz >= 2 * g.gw) {
       // Update the planes the neighbours need first, fill their x / y ghosts and start the z exchange of the NEXT
@@ -499,11 +506,15 @@ int create_impl(const ppk_mhd3d_params *p, ppk_mhd3d *h) {
     return rc;
   h->tma = h->kt->tma_create(g, h->BASIS, h->DBF);
   h->prod = h->kt->prod_create(g, h->U[0], h->U[1]);
-  // default schedule: the tiled pipeline where its TMA boxes exist (even isize, nx >= 32) and the slab has no z exchange
-  if (h->tma && h->prod && p->mz == 1) h->pipeline = PPK_PIPELINE_TILED;
+  // Default schedule, from the A/B measurements of profiles/r2 (B200, Orszag-Tang kt=1): one kernel per functor up to
+  // 256^2-cell planes (6.98 ms at 256^3 against 7.25 ms tiled); from there on the six Riemann tasks as one L2-ordered
+  // launch (512^3: 31.2 ms against 33.6 ms for the six launches, whose basis planes no longer stay in the L2 between them).
+  h->pipeline = PPK_PIPELINE_UNFUSED;
+  if (h->tma && (long long)g.nx * g.ny >= 384LL * 384LL) h->pipeline = PPK_PIPELINE_ORDERED;
   if (const char *e = getenv("PPK_PIPELINE")) {
     const int want = atoi(e);
-    if (want != PPK_PIPELINE_TILED || (h->tma && h->prod && p->mz == 1)) h->pipeline = want;
+    if (want == PPK_PIPELINE_ORDERED && !h->tma) h->pipeline = PPK_PIPELINE_UNFUSED;
+    else if (want != PPK_PIPELINE_TILED || (h->tma && h->prod && p->mz == 1)) h->pipeline = want;
   }
   CUDA_TRY(cudaMalloc((void **)&h->st, sizeof(StepState)));
   StepState st0{};
@@ -520,7 +531,7 @@ int ppk_mhd3d_destroy(ppk_mhd3d *h) {
   DeviceGuard guard(h->device);
   cudaDeviceSynchronize();
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
-  for (double *p : {h->U[0], h->U[1], h->Ustage, h->Q, h->E, h->DBF, h->BASIS, h->F[0], h->F[1], h->F[2], h->EMF, h->diag})
+  for (double *p : {h->U[0], h->U[1], h->Ustage, h->Uspare, h->Q, h->E, h->DBF, h->BASIS, h->F[0], h->F[1], h->F[2], h->EMF, h->diag})
     if (p) cudaFree(p);
   for (auto &pd : h->d2h_pending) cudaEventDestroy(pd.done);
   if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
@@ -657,7 +668,21 @@ int ppk_mhd3d_stage_upload(ppk_mhd3d *h, const double *u_host) {
   if (!h || !u_host) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
   DeviceGuard guard(h->device);
   if (int rc = stage_init(h)) return rc;
-  // the staging array may still be the source of a staged download: the copy waits for it (and for nothing else)
+  // Four arrays are busy at once when batches are pipelined (being uploaded | step input | step output | being downloaded):
+  // if the staging array is still the source of a running download, upload into the spare one instead
+  auto busy = [&](const double *buf) {
+    for (auto &pd : h->d2h_pending)
+      if (pd.buf == buf && cudaEventQuery(pd.done) == cudaErrorNotReady) return true;
+    return false;
+  };
+  if (busy(h->Ustage)) {
+    if (!h->Uspare) {
+      if (int rc = alloc_doubles(h, &h->Uspare, NBVAR * h->g.ncell)) return rc;
+      CUDA_TRY(cudaStreamSynchronize(h->stream));  // (its zero fill)
+    }
+    if (!busy(h->Uspare)) std::swap(h->Ustage, h->Uspare);
+  }
+  // whatever still reads the chosen array finishes first (and nothing else is waited for)
   for (auto &pd : h->d2h_pending)
     if (pd.buf == h->Ustage) CUDA_TRY(cudaStreamWaitEvent(h->h2d_stream, pd.done, 0));
   CUDA_TRY(cudaMemcpyAsync(h->Ustage, u_host, (size_t)NBVAR * h->g.ncell * sizeof(double), cudaMemcpyHostToDevice, h->h2d_stream));
@@ -979,11 +1004,12 @@ int ppk_mhd3d_set_stream(ppk_mhd3d *h, void *cuda_stream) {
 
 int ppk_mhd3d_set_pipeline(ppk_mhd3d *h, int pipeline) {
   if (!h) return fail(PPK_ERR_INVALID_ARGUMENT, "null handle");
-  if (pipeline < PPK_PIPELINE_UNFUSED || pipeline > PPK_PIPELINE_TILED) return fail(PPK_ERR_INVALID_ARGUMENT, "unknown pipeline");
+  if (pipeline < PPK_PIPELINE_UNFUSED || pipeline > PPK_PIPELINE_ORDERED) return fail(PPK_ERR_INVALID_ARGUMENT, "unknown pipeline");
+  if (pipeline == PPK_PIPELINE_ORDERED && !h->tma) pipeline = PPK_PIPELINE_UNFUSED;  // (no TMA tiles on this grid: the same kernels, one by one)
   if (pipeline == PPK_PIPELINE_TILED && (!h->tma || !h->prod || h->params.mz != 1))
     return fail(PPK_ERR_UNSUPPORTED, "the tiled pipeline needs an even nx >= 32 (16-byte TMA rows) and a single slab (mz = 1)");
   DeviceGuard guard(h->device);
-  if ((pipeline == PPK_PIPELINE_UNFUSED || pipeline == PPK_PIPELINE_TILED) && !h->F[0]) {  // flux / EMF arrays exist only for the unfused pipeline
+  if ((pipeline == PPK_PIPELINE_UNFUSED || pipeline == PPK_PIPELINE_TILED || pipeline == PPK_PIPELINE_ORDERED) && !h->F[0]) {  // flux / EMF arrays exist only for the unfused pipeline
     int rc = 0;
     const long long n = h->g.ncell;
     if ((rc = alloc_doubles(h, &h->F[0], NFLUX * n)) || (rc = alloc_doubles(h, &h->F[1], NFLUX * n)) ||

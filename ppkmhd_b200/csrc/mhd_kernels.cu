@@ -2093,8 +2093,9 @@ static void *l_tma_create(const GridParams &g, const double *BASIS, const double
   }
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-      cudaFuncSetAttribute(k_riemann_pers<RIEMANN_HLLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, RALL_SMEM) != cudaSuccess ||
-      cudaFuncSetAttribute(k_riemann_pers<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RALL_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(k_riemann_pers<RIEMANN_HLLD, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, RALL_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(k_riemann_pers<RIEMANN_HLLD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, RALL_SMEM) != cudaSuccess ||
+      cudaFuncSetAttribute(k_riemann_pers<-1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, RALL_SMEM) != cudaSuccess ||
       cudaMalloc(&c->counter, sizeof(unsigned)) != cudaSuccess) {
     l_tma_destroy(c);
     return nullptr;
@@ -2225,14 +2226,18 @@ static int l_riemann_all(const GridParams &g, const double *BASIS, const double 
   pl.per_slab = (unsigned)(g.nz + 1) * pl.per_plane;
   const unsigned long long total = (unsigned long long)nslab * pl.per_slab;
   if (total > 0x7FFFFFFFull || ntx < 1) return -1;
-  // persistent CTAs (mhd_rpers.inc) unless PPK_RALL_PERS=0 selects the single-shot form
-  static const int pers = getenv("PPK_RALL_PERS") ? atoi(getenv("PPK_RALL_PERS")) : 1;
+  // PPK_RALL_PERS=1 selects the persistent form (mhd_rpers.inc): built, bit-identical, and slower on B200 (256^3: 4.55 -
+  // 5.26 ms against 3.86 ms; the gathered operands of a solve have to live in registers across the hand-off, which costs
+  // either a CTA per SM or spills, and the solves are latency-bound, not load-bound: profiles/r2/README.md)
+  static const int pers = getenv("PPK_RALL_PERS") ? atoi(getenv("PPK_RALL_PERS")) : 0;
   static const int pers_ctas = getenv("PPK_RALL_CTAS") ? atoi(getenv("PPK_RALL_CTAS")) : 5;
+  static const int xmode = getenv("PPK_RALL_XMODE") ? atoi(getenv("PPK_RALL_XMODE")) : 0;
   if (pers && total > (unsigned long long)tma->sms * pers_ctas) {
     const unsigned G = (unsigned)(tma->sms * pers_ctas);
     cudaMemsetAsync(tma->counter, 0, sizeof(unsigned), s);
-    if (g.riemann == RIEMANN_HLLD) k_riemann_pers<RIEMANN_HLLD><<<G, 128, RALL_SMEM, s>>>(g, pl, tma->rall, F0, F1, F2, EMF, (unsigned)total, tma->counter);
-    else k_riemann_pers<-1><<<G, 128, RALL_SMEM, s>>>(g, pl, tma->rall, F0, F1, F2, EMF, (unsigned)total, tma->counter);
+    if (g.riemann == RIEMANN_HLLD && pers_ctas == 4) k_riemann_pers<RIEMANN_HLLD, 4><<<G, 128, RALL_SMEM, s>>>(g, pl, tma->rall, F0, F1, F2, EMF, (unsigned)total, tma->counter, xmode);
+    else if (g.riemann == RIEMANN_HLLD) k_riemann_pers<RIEMANN_HLLD, 5><<<G, 128, RALL_SMEM, s>>>(g, pl, tma->rall, F0, F1, F2, EMF, (unsigned)total, tma->counter, xmode);
+    else k_riemann_pers<-1, 5><<<G, 128, RALL_SMEM, s>>>(g, pl, tma->rall, F0, F1, F2, EMF, (unsigned)total, tma->counter, xmode);
   } else if (g.riemann == RIEMANN_HLLD) k_riemann_all<RIEMANN_HLLD><<<(unsigned)total, 128, RALL_SMEM, s>>>(g, pl, tma->rall, F0, F1, F2, EMF);
   else k_riemann_all<-1><<<(unsigned)total, 128, RALL_SMEM, s>>>(g, pl, tma->rall, F0, F1, F2, EMF);
   if (!wrap) {

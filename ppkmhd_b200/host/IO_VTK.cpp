@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <fstream>
 #include <iomanip>
+#include <iostream>
 #include <sstream>
 #include <vector>
 
@@ -189,13 +190,29 @@ IO_ReadWrite::IO_ReadWrite(HydroParams &params_, ConfigMap &configMap_, std::map
   hdf5_enabled = configMap.getBool("output", "hdf5_enabled", false);  // compile-gated in the reference (USE_HDF5)
 }
 
-void IO_ReadWrite::save_data(DataArray3dHost &Uhost, int iStep, real_t /*time*/, const std::string &debug_name) {
+bool IO_ReadWrite::load_data(DataArray3dHost &Uhost, int &iStep, real_t &time, std::string *why) {
+  const std::string inputFilename = configMap.getString("run", "restart_filename", "");
+  const std::string h5(".h5");
+  if (inputFilename.size() < h5.size() || inputFilename.compare(inputFilename.size() - h5.size(), h5.size(), h5) != 0) {
+    if (why) *why = "[run] restart_filename must name a .h5 file (the reference's other format, PnetCDF, needs MPI)";
+    return false;
+  }
+  return load_HDF5(Uhost, params, configMap, variables_names, inputFilename, iStep, time, why);
+}
+
+void IO_ReadWrite::save_data(DataArray3dHost &Uhost, int iStep, real_t time, const std::string &debug_name) {
   if (vtk_enabled) {
     if (params.dimType == TWO_D) save_VTK_2D(Uhost, params, configMap, params.nbvar, variables_names, iStep, debug_name);
     else if (params.nProcs > 1) save_VTK_3D_slab(Uhost, params, configMap, params.nbvar, variables_names, iStep, debug_name);
     else save_VTK_3D(Uhost, params, configMap, params.nbvar, variables_names, iStep, debug_name);
   }
-  // HDF5: libhdf5 is not available in this build (same situation as the reference built without USE_HDF5)
+  if (hdf5_enabled) {  // Save_HDF5 (IO_ReadWrite.cpp:108-125); libhdf5 is looked up at run time
+    std::string why;
+    if (!save_HDF5(Uhost, params, configMap, variables_names, iStep, time, &why)) {
+      if (!hdf5_failed && params.myRank == 0) std::cerr << "HDF5 output skipped: " << why << std::endl;
+      hdf5_failed = true;
+    }
+  }
 }
 
 }  // namespace io

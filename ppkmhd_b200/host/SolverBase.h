@@ -115,7 +115,11 @@ class IO_ReadWrite {
 public:
   IO_ReadWrite(HydroParams &params, ConfigMap &configMap, std::map<int, std::string> &variables_names);
   void save_data(DataArray3dHost &Uhost, int iStep, real_t time, const std::string &debug_name);
+  // restart (IO_ReadWrite::load_data_impl, src/utils/io/IO_ReadWrite.cpp:245-287): [run] restart_filename (.h5) -> Uhost,
+  // output counter and time of the file; false (with the reason) when HDF5 is unavailable or the file does not fit
+  bool load_data(DataArray3dHost &Uhost, int &iStep, real_t &time, std::string *why);
   bool vtk_enabled = true, hdf5_enabled = false;
+  bool hdf5_failed = false;  // an HDF5 output was requested and could not be written (reported once)
 
 private:
   HydroParams &params;
@@ -127,6 +131,15 @@ void save_VTK_3D(const DataArray3dHost &Uhost, HydroParams &params, ConfigMap &c
 // 2-D files of save_VTK_2D (src/utils/io/IO_VTK.cpp:24-206): Uhost is (isize, jsize, 1, nbvar)
 void save_VTK_2D(const DataArray3dHost &Uhost, HydroParams &params, ConfigMap &configMap, int nbvar,
                  const std::map<int, std::string> &variables_names, int iStep, const std::string &debug_name);
+// HDF5 + XDMF (IO_HDF5.cpp here; src/utils/io/IO_HDF5.h:73-526, :1537-2153 and IO_HDF5.cpp:16-378 in the reference).
+// libhdf5 is resolved at run time (dlopen): hdf5_available() says whether it was found.
+bool hdf5_available(std::string *why);
+void writeXdmfForHdf5Wrapper(HydroParams &params, ConfigMap &configMap, const std::map<int, std::string> &variables_names,
+                             int totalNumberOfSteps, bool singleStep);
+bool save_HDF5(const DataArray3dHost &Uhost, HydroParams &params, ConfigMap &configMap, const std::map<int, std::string> &variables_names,
+               int iStep, real_t totalTime, std::string *why);
+bool load_HDF5(DataArray3dHost &Uhost, HydroParams &params, ConfigMap &configMap, const std::map<int, std::string> &variables_names,
+               const std::string &filename, int &iStep, real_t &totalTime, std::string *why);
 void save_VTK_3D_slab(const DataArray3dHost &Uhost, HydroParams &params, ConfigMap &configMap, int nbvar,
                       const std::map<int, std::string> &variables_names, int iStep, const std::string &debug_name);
 }  // namespace io

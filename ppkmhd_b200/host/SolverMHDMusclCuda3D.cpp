@@ -628,9 +628,20 @@ SolverMHDMusclCuda3D::SolverMHDMusclCuda3D(HydroParams &params_, ConfigMap &conf
 
   Uhost = DataArray3dHost(params.isize, params.jsize, params.ksize, params.nbvar);
   const bool restartEnabled = configMap.getBool("run", "restart_enabled", false);
-  if (restartEnabled)
-    std::cout << "restart needs HDF5 (as in the reference, IO_ReadWrite.cpp:245-287): not available, starting from t=0\n";
-  m_problem_name = init_problem(params, configMap, m_problem_name, Uhost);
+  if (restartEnabled) {  // SolverMHDMuscl<dim>::init_restart (SolverMHDMuscl.h:615-643)
+    io::IO_ReadWrite reader(params, configMap, m_variables_names);
+    std::string why;
+    int times_saved = 0;
+    if (!reader.load_data(Uhost, times_saved, m_t, &why)) {  // a restart that cannot be honoured must not run something else
+      fprintf(stderr, "restart_enabled: %s\n", why.c_str());
+      std::abort();
+    }
+    m_times_saved = times_saved;
+    if (configMap.getBool("run", "restart_reset_totaltime", false)) m_t = 0;
+    if (params.myRank == 0) std::cout << "### This is a restarted run ! Current time is " << m_t << " ###\n";
+  } else {
+    m_problem_name = init_problem(params, configMap, m_problem_name, Uhost);
+  }
 
   // constructor sequence of the reference (SolverMHDMuscl.h:390-402): upload, ghost fill, dt
   PPK_CALL(ppk_mhd3d_upload(m_handle, Uhost.data()));

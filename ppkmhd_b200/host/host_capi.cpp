@@ -83,6 +83,18 @@ int ppk_save_data_from_ini(const char *ini_text, int rank_z, const double *u_hos
                                       {IA, "bx"},  {IB, "by"},     {IC, "bz"}};  // SolverBase.cpp:49-56
   io::IO_ReadWrite writer(p, cfg, names);
   writer.save_data(U, i_step, 0.0, "");
+  return writer.hdf5_failed ? PPK_ERR_UNSUPPORTED : 0;  // [output] hdf5_enabled without a usable libhdf5
+}
+
+int ppk_hdf5_available(void) { return io::hdf5_available(nullptr) ? 1 : 0; }
+
+int ppk_write_xdmf_from_ini(const char *ini_text, int total_number_of_steps, int single_step) {
+  if (!ini_text) return PPK_ERR_INVALID_ARGUMENT;
+  ConfigMap cfg(ini_text, (int)strlen(ini_text));
+  HydroParams p = params_for(cfg, 0);
+  std::map<int, std::string> names = {{ID, "rho"}, {IP, "energy"}, {IU, "rho_vx"}, {IV, "rho_vy"}, {IW, "rho_vz"},
+                                      {IA, "bx"},  {IB, "by"},     {IC, "bz"}};
+  io::writeXdmfForHdf5Wrapper(p, cfg, names, total_number_of_steps, single_step != 0);
   return 0;
 }
 
@@ -141,6 +153,9 @@ int ppk_run_ini(const char *ini_path, int rank, int nranks) {
   while (!solver->finished()) solver->next_iteration();
   solver->timers[TIMER_TOTAL]->stop();
   if (params.nOutput != 0) solver->save_solution();
+  // the Xdmf wrapper of the HDF5 series (src/main.cpp:163-170)
+  if (configMap.getBool("output", "hdf5_enabled", false) && params.myRank == 0)
+    io::writeXdmfForHdf5Wrapper(params, configMap, solver->m_variables_names, solver->m_times_saved - 1, false);
   if (params.myRank == 0) printf("final time is %f\n", solver->m_t);
   print_solver_monitoring_info(solver);
   delete solver;

@@ -24,7 +24,7 @@ BLAST = "[blast]\nradius=0.25\ndensity_in=1.0\ndensity_out=1.2\npressure_in=10.0
 
 
 def make_solver(ini, exact=True, pipeline=None):
-    """pipeline=None keeps the handle's default: "tiled" where its TMA boxes exist (even nx >= 32), else "unfused"."""
+    """pipeline=None keeps the handle's default: "unfused" below 384^2-cell planes, "ordered" above."""
     p, t_end, nstep = ppk.params_from_ini(ini, exact=exact)
     s = ppk.Mhd3d(p)
     if pipeline is not None:
@@ -91,7 +91,8 @@ def test_exact_mode_vs_oracle_with_intermediates(problem, n, extra, bounds, cfl,
     f, _ = make_solver(ini, exact=True, pipeline="fused")
     m, _ = make_solver(ini, exact=True, pipeline="streamed")
     tl, _ = make_solver(ini, exact=True, pipeline="tiled")   # fused producer + the six Riemann tasks in one launch
-    tf, _ = make_solver(ini, exact=False, pipeline="tiled")  # the same in fast arithmetic (what bench.py measures)
+    tf, _ = make_solver(ini, exact=False, pipeline="tiled")  # the same in fast arithmetic
+    od, _ = make_solver(ini, exact=True, pipeline="ordered")  # unfused producers + the six Riemann tasks in one launch
     for step in range(4):
         orc.step()
         s.step()
@@ -99,6 +100,8 @@ def test_exact_mode_vs_oracle_with_intermediates(problem, n, extra, bounds, cfl,
         m.step()
         tl.step()
         tf.step()
+        od.step()
+        assert np.array_equal(od.interior(), orc.interior()), f"ordered pipeline differs at step {step + 1}"
         assert np.array_equal(f.interior(), orc.interior()), f"fused pipeline differs at step {step + 1}"
         assert np.array_equal(m.interior(), orc.interior()), f"streamed pipeline differs at step {step + 1}"
         assert np.array_equal(tl.interior(), orc.interior()), f"tiled pipeline differs at step {step + 1}"
@@ -123,6 +126,7 @@ def test_exact_mode_vs_oracle_with_intermediates(problem, n, extra, bounds, cfl,
             assert np.array_equal(tl.debug_array("dbf")[inner], dbf[inner]), "face-field slopes of the fused producer"
             for name in ("Fluxes_x", "Fluxes_y", "Fluxes_z", "Emf"):
                 assert np.array_equal(tl.debug_array(name), s.debug_array(name)), name + " of the one-launch Riemann kernel"
+                assert np.array_equal(od.debug_array(name), s.debug_array(name)), name + " of the ordered pipeline"
             emf = s.debug_array("Emf")
             eo = orc.scratch_array("Emf", 3)
             nz, ny, nx = n[2], n[1], n[0]
@@ -145,6 +149,7 @@ def test_exact_mode_vs_oracle_with_intermediates(problem, n, extra, bounds, cfl,
     m.close()
     tl.close()
     tf.close()
+    od.close()
 
 
 def test_hundred_steps_conserved_sums_and_divb(oracle_mod):
@@ -171,8 +176,8 @@ def test_hundred_steps_conserved_sums_and_divb(oracle_mod):
 
 def test_benchmarked_workload_128_vs_oracle(oracle_mod):
     """The workload bench.py times (Orszag-Tang kt=1: a genuinely 3-D flow, every flux and EMF component exercised) at
-    128^3 against the oracle: the exact build bit for bit after 1 and 3 steps on the default (tiled) and the unfused
-    pipeline, the fast build (the one that is benchmarked) within 1e-12 per cell after one step."""
+    128^3 against the oracle: the exact build bit for bit after 1 and 3 steps on the default (unfused), the ordered and the
+    tiled pipeline, the fast build (the one that is benchmarked) within 1e-12 per cell after one step."""
     O = oracle_mod
     ini = O.make_ini("orszag_tang", (128, 128, 128), nstepmax=3, extra=OT, tend=10.0)
     orc = O.Oracle(ini)
@@ -181,7 +186,7 @@ def test_benchmarked_workload_128_vs_oracle(oracle_mod):
     orc.step()
     orc.step()
     ref3 = orc.interior()
-    for pipeline in (None, "unfused"):
+    for pipeline in (None, "ordered", "tiled"):
         s, _ = make_solver(ini, exact=True, pipeline=pipeline)
         s.step()
         assert np.array_equal(s.interior(), ref1), f"exact build, pipeline {pipeline}: step 1 differs from the oracle"
@@ -209,7 +214,7 @@ def test_benchmarked_workload_256_fast_vs_exact():
     want = e.interior()
     te, dte, _ = e.get_time()
     e.close()
-    for pipeline in (None, "unfused"):
+    for pipeline in (None, "ordered", "tiled"):
         f, _ = make_solver(ini, exact=False, pipeline=pipeline)
         f.step()
         tf, dtf, _ = f.get_time()
@@ -404,7 +409,7 @@ def test_fast_math_primitives_within_2ulp():
     assert np.array_equal(sq0, np.zeros(4))
 
 
-def _slab_worker(rank, world, port, ini, nsteps, exact, out_dir):
+def _slab_worker(rank, world, port, ini, nsteps, exact, out_dir, pipeline=None):
     import sys
 
     sys.path.insert(0, ROOT)
@@ -422,6 +427,8 @@ def _slab_worker(rank, world, port, ini, nsteps, exact, out_dir):
         idt = torch.tensor(list(P.nccl_unique_id()), dtype=torch.uint8)
     dist.broadcast(idt, 0)
     s.comm_init(bytes(idt.tolist()), world, rank)
+    if pipeline is not None:
+        s.set_pipeline(pipeline)
     s.upload(P.init_condition_from_ini(ini, rank_z=rank))
     s.set_time(0.0, t_end, 0)
     s.run(nsteps)
@@ -434,8 +441,9 @@ def _slab_worker(rank, world, port, ini, nsteps, exact, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,nxy,nzl", [(2, (24, 20), 12), (4, (24, 20), 12), (2, (64, 36), 16)])
-def test_z_slabs_bit_identical_to_single_gpu(tmp_path, world, nxy, nzl):
+@pytest.mark.parametrize("world,nxy,nzl,pipeline", [(2, (24, 20), 12, None), (4, (24, 20), 12, None), (2, (64, 36), 16, None),
+                                                     (2, (64, 36), 16, "ordered"), (4, (512, 512), 64, None)])
+def test_z_slabs_bit_identical_to_single_gpu(tmp_path, world, nxy, nzl, pipeline):
     """Decomposition invariance: N z-slabs over NCCL == the undecomposed run, bit for bit, dt included."""
     import socket
 
@@ -446,8 +454,9 @@ def test_z_slabs_bit_identical_to_single_gpu(tmp_path, world, nxy, nzl):
         pytest.skip(f"needs {world} GPUs")
     from oracle import oracle as O  # ini text helper only
 
-    # (64, 36): TMA-staged tiles, the wrapped x column and the early halo exchange in the decomposed run
-    nsteps = 6
+    # (64, 36): TMA-staged tiles, the wrapped x column and the early halo exchange in the decomposed run;
+    # (512, 512) x 64 planes per slab: the production schedule at bench.py's plane size (ordered pipeline, y-slabs for the L2)
+    nsteps = 6 if nxy[0] < 512 else 3
     kw = dict(nstepmax=nsteps, extra="[OrszagTang]\nkt=0.5\n", tend=10.0)
     ini_n = O.make_ini("orszag_tang", (*nxy, nzl), mz=world, **kw)
     ini_1 = O.make_ini("orszag_tang", (*nxy, nzl * world), **kw)
@@ -455,7 +464,7 @@ def test_z_slabs_bit_identical_to_single_gpu(tmp_path, world, nxy, nzl):
     sock.bind(("127.0.0.1", 0))
     port = sock.getsockname()[1]
     sock.close()
-    mp.spawn(_slab_worker, args=(world, port, ini_n, nsteps, True, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_slab_worker, args=(world, port, ini_n, nsteps, True, str(tmp_path), pipeline), nprocs=world, join=True)
     s, _ = make_solver(ini_1, exact=True)
     s.run(nsteps)
     t, dt, it = s.get_time()

@@ -170,3 +170,57 @@ def test_pvti_pieces_reassemble_to_the_single_vti(tmp_path):
             rebuilt[v, z0:z1, y0:y1, x0:x1] = np.frombuffer(blob, dtype="<f8", count=nbytes // 8, offset=pos + 8).reshape(z1 - z0, y1 - y0, x1 - x0)
             pos += 8 + nbytes
     assert np.array_equal(rebuilt, whole)
+
+
+def test_xdmf_wrapper_text_and_hdf5_error_path(tmp_path, monkeypatch):
+    """writeXdmfForHdf5Wrapper (src/utils/io/IO_HDF5.cpp:16-378) is plain text: the file must read, line for line, like the
+    reference's (header :138-143, per-output grid :176-186, geometry :208-227, one attribute block per variable in the
+    order rho, energy, rho_vx, rho_vy, rho_vz, bx, by, bz :229-360, footer :363-370). libhdf5 itself is looked up at run time:
+    where it is absent (this image), an HDF5 output request is reported as PPK_ERR_UNSUPPORTED, never silently dropped."""
+    import ppkmhd_b200 as ppk
+    from oracle import oracle as O
+
+    monkeypatch.chdir(tmp_path)
+    nx, ny, nz = 10, 6, 4
+    ini = O.make_ini("orszag_tang", (nx, ny, nz)).replace("outputPrefix=run", f"outputDir={tmp_path}\noutputPrefix=ot3d\nhdf5_enabled=true")
+    ppk.write_xdmf_from_ini(ini, 2)
+    got = open(tmp_path / "ot3d.xmf").read().splitlines()
+    names = ["rho", "energy", "rho_vx", "rho_vy", "rho_vz", "bx", "by", "bz"]
+    want = ['<?xml version="1.0" ?>', '<!DOCTYPE Xdmf SYSTEM "Xdmf.dtd" []>',
+            '<Xdmf xmlns:xi="http://www.w3.org/2003/XInclude" Version="2.2">', '  <Domain>',
+            '    <Grid Name="TimeSeries" GridType="Collection" CollectionType="Temporal">']
+    for step in range(3):  # outputs 0 .. totalNumberOfSteps inclusive (:160-163)
+        base = f"ot3d_{step:07d}"
+        want += [f'    <Grid Name="{base}" GridType="Uniform">', f'    <Time Value="{step}" />',
+                 f'      <Topology TopologyType="3DCoRectMesh" NumberOfElements="{nz} {ny} {nx}"/>',
+                 '    <Geometry Type="ORIGIN_DXDYDZ">']
+        for what, val in (("Origin", "0 0 0"), ("Spacing", "1 1 1")):
+            want += ['    <DataStructure', f'       Name="{what}"', '       DataType="Double"', '       Dimensions="3"',
+                     '       Format="XML">', f'       {val}', '    </DataStructure>']
+        want += ['    </Geometry>']
+        for nm in names:
+            want += [f'      <Attribute Center="Node" Name="{nm}">', '        <DataStructure', '           DataType="Double"',
+                     f'           Dimensions="{nz} {ny} {nx}"', '           Format="HDF">', f'           {base}.h5:/{nm}',
+                     '        </DataStructure>', '      </Attribute>']
+        want += ['   </Grid>']
+    want += ['   </Grid>', ' </Domain>', '</Xdmf>']
+    assert got == want
+    # single-step flavour: its own file name, outputs iStep and iStep+1 (:154-158)
+    ppk.write_xdmf_from_ini(ini, 5, single_step=True)
+    one = open(tmp_path / "ot3d_0000005.xmf").read()
+    assert one.count('GridType="Uniform"') == 2 and "ot3d_0000005.h5:/bz" in one and "ot3d_0000006.h5:/rho" in one
+
+    U = np.zeros((8, nz + 6, ny + 6, nx + 6))
+    if ppk.hdf5_available():
+        ppk.save_data_from_ini(ini, U, 0)
+        assert (tmp_path / "ot3d_0000000.h5").stat().st_size > 8 * nx * ny * nz * 8
+    else:
+        with pytest.raises(ppk.PpkError, match="10002"):  # PPK_ERR_UNSUPPORTED, after the .vti was written
+            ppk.save_data_from_ini(ini, U, 0)
+        assert (tmp_path / "ot3d_0000000.vti").exists()
+        # a restart that cannot be honoured stops the program instead of starting something else
+        import subprocess
+        exe = os.path.join(ROOT, "ppkmhd_b200", "bin", "ppkMHD_b200")
+        open(tmp_path / "r.ini", "w").write(ini.replace("[mesh]", "restart_enabled=true\nrestart_filename=ot3d_0000000.h5\n[mesh]"))
+        r = subprocess.run([exe, "r.ini"], cwd=tmp_path, capture_output=True, text=True)
+        assert r.returncode != 0 and ("restart_enabled" in r.stderr or "no CUDA device" in r.stderr), r.stderr[-500:]
