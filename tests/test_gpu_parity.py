@@ -475,5 +475,6 @@ def test_z_slabs_bit_identical_to_single_gpu(tmp_path, world, nxy, nzl, pipeline
         assert m[0] == t and m[1] == dt and m[2] == it, (r, m[:3], t, dt, it)
     assert np.array_equal(got, s.interior()), "z-slab run differs from the single-GPU run"
     tot = sum(np.load(tmp_path / f"meta{r}.npy")[4:] for r in range(world))
-    assert np.allclose(tot, sums, rtol=1e-12, atol=1e-12)
+    # (the per-slab sums add up in another order than the single-GPU reduction: round-off of ncell terms of O(1))
+    assert np.allclose(tot, sums, rtol=1e-12, atol=1e-15 * got[0].size)
     s.close()
