@@ -368,10 +368,12 @@ def run_ours(args):
     def timed_run(nsteps):
         """nsteps steps bracketed by barrier + synchronize, CUDA events on the launch stream, max over ranks; clocks sampled
         on rank 0 during the region"""
-        barrier()
+        # the sampler thread starts BEFORE the barrier: NVML's first initialisation takes ~0.1 s on rank 0, and a rank that
+        # enters the timed region late makes its neighbours wait inside theirs (seen as +7 ms per step on a 20-step region)
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
+        barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         solver.run(nsteps)

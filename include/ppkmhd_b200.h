@@ -56,8 +56,9 @@ typedef struct ppk_mhd3d_params {
                                  variant of the same arithmetic: runs v0's deterministic kernels, so results equal v0's, which
                                  the reference's own v1 matches to ~1e-15). 3-D rejects 2 (PPK_ERR_UNSUPPORTED); the 2-D entry
                                  points accept 0, 1 and 2 and always run the v0 formulation (v2 agrees to ~1e-15, not bitwise) */
-  int mx, my, mz;      /* Cartesian decomposition ([mpi] mx,my,mz); this build supports z-slabs: mx = my = 1 */
-  int rank_x, rank_y, rank_z; /* position of this slab (replaces myMpiPos, HydroParams.cpp:269-277) */
+  int mx, my, mz;      /* Cartesian decomposition ([mpi] mx,my,mz): slabs, pencils or blocks; z-slabs (mx = my = 1) are the
+                          fast path (no pack kernels, exchange overlapped with the update) */
+  int rank_x, rank_y, rank_z; /* position of this sub-domain (replaces myMpiPos, HydroParams.cpp:269-277) */
   int device;          /* CUDA device ordinal to run on */
   int exact_arithmetic;/* 1: kernels compiled --fmad=false, reference operation order => bit-identical
                           to the reference's OpenMP build; 0: same order, FMA contraction allowed */
@@ -141,13 +142,31 @@ int ppk_mhd3d_comm_init(ppk_mhd3d *handle, const void *unique_id_128_bytes, int 
  * (0 for mz == 1; faces with a physical, non-periodic BC are not exchanged) or -1 on bad arguments;
  * at most `capacity` entries are written. The engine posts exactly this list inside one NCCL group. */
 typedef struct ppk_halo_msg {
-  int peer;           /* rank_z of the neighbour slab */
+  int peer;           /* global rank of the neighbour: (rank_x*my + rank_y)*mz + rank_z' (= rank_z' for z-slabs) */
   int is_send;        /* 1: send, 0: receive */
   int var;            /* variable plane 0..7 */
   long long offset;   /* in doubles from U[0] */
   long long count;    /* doubles */
 } ppk_halo_msg;
 int ppk_mhd3d_halo_plan(const ppk_mhd3d_params *params, int capacity, ppk_halo_msg *msgs);
+
+/* Block decomposition ([mpi] mx, my > 1; HydroParams.cpp:231-351): the gw ghost layers of an x (dir 0) or y (dir 1) face are
+ * strided in memory, so they travel as ONE packed message per face with the shape of the reference's border buffers
+ * (borderBufSend_xmin_3d(gw, jsize, ksize, nbvar), SolverBase.cpp:77-95; pack / unpack = CopyDataArray_To_BorderBuf /
+ * CopyBorderBuf_To_DataArray, mpiBorderUtils.h:184-330), ghosts of the other directions included:
+ *   dir 0: buf[g + gw*(j + jsize*(k + ksize*v))] = U[first_layer+g, j, k, v]
+ *   dir 1: buf[i + isize*(g + gw*(k + ksize*v))] = U[i, first_layer+g, k, v]
+ * Returns the messages of this sub-domain for direction `dir` (0 when that direction is not decomposed, at most 4) in
+ * the order every rank posts them inside one NCCL group. `peer` is a global rank: rank = (rank_x*my + rank_y)*mz + rank_z,
+ * the layout MPI_Cart_create gives the reference. make_boundaries order stays X, then Y, then Z (SolverBase.cpp:618-691). */
+typedef struct ppk_face_msg {
+  int peer;           /* global rank of the neighbour */
+  int is_send;        /* 1: send, 0: receive */
+  int hi_face;        /* 0: the lower face of this sub-domain along dir, 1: the upper one */
+  int first_layer;    /* index along dir of the first of the gw layers packed (send) or overwritten (receive) */
+  long long count;    /* doubles in the message: gw * jsize (or isize) * ksize * 8 */
+} ppk_face_msg;
+int ppk_mhd3d_face_plan(const ppk_mhd3d_params *params, int dir, ppk_face_msg msgs[4]);
 
 /* ---- plumbing ----------------------------------------------------------------------------- */
 /* Run on a caller-owned stream (a cudaStream_t, e.g. torch's current stream) instead of the

@@ -450,7 +450,7 @@ def run_reference(ini_text: str, threads: int | None = None, workdir: str | None
 
 
 def make_ini(problem="orszag_tang", n=(32, 32, 32), nstepmax=5, tend=1.0, noutput=1, bounds=None, bc=3,
-             cfl=0.8, extra="", mz=1, prefix="run", nlog=10, riemann="hlld") -> str:
+             cfl=0.8, extra="", mz=1, prefix="run", nlog=10, riemann="hlld", mx=1, my=1) -> str:
     """The ini family of SURVEY 8(d): gamma0=1.666 cfl=0.8 slope_type=2 hlld smallr=smallc=1e-8, v0."""
     b = bounds or (0.0, 1.0, 0.0, 1.0, 0.0, 1.0)
     bcs = bc if isinstance(bc, (list, tuple)) else [bc] * 6
@@ -484,8 +484,8 @@ riemann={riemann}
 smallr=1e-8
 smallc=1e-8
 [mpi]
-mx=1
-my=1
+mx={mx}
+my={my}
 mz={mz}
 [output]
 outputPrefix={prefix}

@@ -55,6 +55,12 @@ class HaloMsg(C.Structure):
     _fields_ = [("peer", C.c_int), ("is_send", C.c_int), ("var", C.c_int), ("offset", C.c_longlong), ("count", C.c_longlong)]
 
 
+class FaceMsg(C.Structure):
+    """struct ppk_face_msg"""
+
+    _fields_ = [("peer", C.c_int), ("is_send", C.c_int), ("hi_face", C.c_int), ("first_layer", C.c_int), ("count", C.c_longlong)]
+
+
 _lib = None
 
 # every symbol include/*.h declares (tests/test_host_layer.py checks the library exports them all)
@@ -64,7 +70,7 @@ EXPORTS = [
     "ppk_mhd3d_synchronize", "ppk_mhd3d_diagnostics", "ppk_nccl_get_unique_id", "ppk_mhd3d_comm_init",
     "ppk_mhd3d_set_stream", "ppk_mhd3d_profile", "ppk_mhd3d_kernel_times", "ppk_mhd3d_launch_count",
     "ppk_mhd3d_debug_array", "ppk_mhd3d_device_bytes", "ppk_last_error_string", "ppk_version_string",
-    "ppk_mhd3d_halo_plan", "ppk_selftest_fastmath", "ppk_mhd3d_set_pipeline",
+    "ppk_mhd3d_halo_plan", "ppk_mhd3d_face_plan", "ppk_selftest_fastmath", "ppk_mhd3d_set_pipeline",
     "ppk_mhd3d_get_pipeline", "ppk_mhd3d_stage_upload", "ppk_mhd3d_stage_swap", "ppk_mhd3d_stage_download",
     "ppk_params_from_ini", "ppk_init_condition_from_ini", "ppk_run_ini", "ppk_save_data_from_ini", "ppk_hdf5_available", "ppk_write_xdmf_from_ini", "ppk_init_condition_2d_from_ini",
     "ppk_mhd2d_create", "ppk_mhd2d_destroy", "ppk_mhd2d_upload", "ppk_mhd2d_download", "ppk_mhd2d_set_time", "ppk_mhd2d_get_time",
@@ -111,6 +117,7 @@ def load_library():
     L.ppk_mhd3d_device_bytes.argtypes = [vp]
     L.ppk_mhd3d_device_bytes.restype = C.c_longlong
     L.ppk_mhd3d_halo_plan.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(HaloMsg)]
+    L.ppk_mhd3d_face_plan.argtypes = [C.POINTER(Params), C.c_int, C.POINTER(FaceMsg)]
     L.ppk_selftest_fastmath.argtypes = [C.c_int, vp, vp, vp, vp]
     L.ppk_last_error_string.restype = C.c_char_p
     L.ppk_version_string.restype = C.c_char_p
@@ -378,6 +385,16 @@ def halo_plan(params: Params):
     if n < 0:
         raise PpkError("ppk_mhd3d_halo_plan: bad arguments")
     return [(m.peer, bool(m.is_send), m.var, m.offset, m.count) for m in msgs[:n]]
+
+
+def face_plan(params: Params, direction: int):
+    """ppk_mhd3d_face_plan: list of (peer, is_send, hi_face, first_layer, count) of the packed x (0) or y (1) exchange."""
+    L = load_library()
+    msgs = (FaceMsg * 4)()
+    n = L.ppk_mhd3d_face_plan(C.byref(params), direction, msgs)
+    if n < 0:
+        raise PpkError("ppk_mhd3d_face_plan: bad arguments")
+    return [(m.peer, bool(m.is_send), bool(m.hi_face), m.first_layer, m.count) for m in msgs[:n]]
 
 
 def selftest_fastmath(x: np.ndarray):

@@ -125,6 +125,8 @@ struct ppk_mhd3d {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0, zlo = 0, zhi = 0;
   bool exch_lo = false, exch_hi = false;  // z faces filled by the halo exchange
+  bool exch_xy[4] = {false, false, false, false};  // x-lo, x-hi, y-lo, y-hi faces filled by the (packed) halo exchange
+  double *fbuf[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};  // [dir][send lo, send hi, recv lo, recv hi]
   int pipeline = PPK_PIPELINE_UNFUSED;
   double *halo_posted = nullptr;  // array whose z exchange was started at the end of the previous step
   bool early_halo = true, defer_dt = true;
@@ -219,6 +221,31 @@ int halo_exchange_z(ppk_mhd3d *h, double *U, cudaStream_t s) {
   return 0;
 }
 
+// x or y ghost layers of a block-decomposed run: pack kernel -> one grouped ncclSend / ncclRecv per face -> unpack kernel
+// (copy_boundaries + transfert_boundaries_3d + copy_boundaries_back of the reference, SolverBase.cpp:700-925). Runs on
+// stream s, in order: the layers that are sent already carry the ghosts of the directions exchanged before.
+int halo_exchange_face(ppk_mhd3d *h, double *U, int dir, cudaStream_t s) {
+  ppk_face_msg msgs[4];
+  const int n = ppk_mhd3d_face_plan(&h->params, dir, msgs);
+  if (n <= 0) return n < 0 ? fail(PPK_ERR_STATE, "face plan failed") : 0;
+  for (int b = 0; b < 4; ++b)
+    if (!h->fbuf[dir][b]) { if (int rc = alloc_doubles(h, &h->fbuf[dir][b], msgs[0].count)) return rc; }
+  Scope sc(h, KK_HALO, s);
+  for (int m = 0; m < n; ++m)
+    if (msgs[m].is_send) h->kt->face_copy(h->g, U, h->fbuf[dir][msgs[m].hi_face], dir, msgs[m].first_layer, 1, s);
+  NCCL_TRY(g_nccl.GroupStart());
+  for (int m = 0; m < n; ++m) {
+    double *buf = h->fbuf[dir][(msgs[m].is_send ? 0 : 2) + msgs[m].hi_face];
+    if (msgs[m].is_send) NCCL_TRY(g_nccl.Send(buf, (size_t)msgs[m].count, ncclDouble, msgs[m].peer, h->comm, s));
+    else NCCL_TRY(g_nccl.Recv(buf, (size_t)msgs[m].count, ncclDouble, msgs[m].peer, h->comm, s));
+  }
+  NCCL_TRY(g_nccl.GroupEnd());
+  for (int m = 0; m < n; ++m)
+    if (!msgs[m].is_send) h->kt->face_copy(h->g, U, h->fbuf[dir][2 + msgs[m].hi_face], dir, msgs[m].first_layer, 0, s);
+  h->launches += 2 * n - 1;
+  return 0;
+}
+
 // an array that a staged download (ppk_mhd3d_stage_download) is still reading must not be overwritten on stream s
 int wait_staged_reads(ppk_mhd3d *h, const double *buf, cudaStream_t s) {
   for (auto &pd : h->d2h_pending)
@@ -241,9 +268,17 @@ int boundaries_and_primitives(ppk_mhd3d *h, double *U, bool with_prim, bool defe
   cudaStream_t s = h->stream;
   const bool exch = h->exch_lo || h->exch_hi;
   const bool posted = exch && h->halo_posted == U;  // the z exchange of this array started at the end of the last step
-  if (exch && !h->comm) return fail(PPK_ERR_STATE, "mz > 1 but ppk_mhd3d_comm_init was not called");
+  const bool block = h->exch_xy[0] || h->exch_xy[1] || h->exch_xy[2] || h->exch_xy[3];
+  if ((exch || block) && !h->comm) return fail(PPK_ERR_STATE, "mx*my*mz > 1 but ppk_mhd3d_comm_init was not called");
   if (with_prim) { if (int rc = ensure_prim_arrays(h)) return rc; }
-  if (posted) {
+  if (block) {
+    // block decomposition: X -> Y (-> Z below) in the reference's order (SolverBase.cpp:618-691), every direction =
+    // local fill of the physical faces, then the exchange of the others; stream-ordered, no overlap
+    { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, U, 0, 0, g.ksize, s); }
+    if (int rc = halo_exchange_face(h, U, 0, s)) return rc;
+    { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, U, 1, 0, g.ksize, s); }
+    if (int rc = halo_exchange_face(h, U, 1, s)) return rc;
+  } else if (posted) {
     // the edge planes already carry their x / y ghosts (they are being sent), the z ghost planes are being received
     { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, U, 0, 2 * g.gw, g.nz, s); }
     { Scope sc(h, KK_BOUNDARY, s); h->kt->boundary(g, U, 1, 2 * g.gw, g.nz, s); }
@@ -433,8 +468,9 @@ int ppk_mhd3d_create(const ppk_mhd3d_params *p, ppk_mhd3d **out) {
   // the same deterministic kernels here. v2 is a different formulation (and faulty in 3-D).
   if (p->implementation_version != 0 && p->implementation_version != 1)
     return fail(PPK_ERR_UNSUPPORTED, "implementationVersion must be 0 or 1 (v1 runs v0's deterministic kernels; v2 is not implemented)");
-  if (p->mx != 1 || p->my != 1 || p->mz < 1) return fail(PPK_ERR_UNSUPPORTED, "only z-slab decompositions (mx=my=1) are supported");
-  if (p->rank_z < 0 || p->rank_z >= p->mz) return fail(PPK_ERR_INVALID_ARGUMENT, "rank_z out of range");
+  if (p->mx < 1 || p->my < 1 || p->mz < 1) return fail(PPK_ERR_INVALID_ARGUMENT, "mx, my, mz must be >= 1");
+  if (p->rank_x < 0 || p->rank_x >= p->mx || p->rank_y < 0 || p->rank_y >= p->my || p->rank_z < 0 || p->rank_z >= p->mz)
+    return fail(PPK_ERR_INVALID_ARGUMENT, "rank_x / rank_y / rank_z out of range");
   if (p->nx < 3 || p->ny < 3 || p->nz < 3) return fail(PPK_ERR_INVALID_ARGUMENT, "nx, ny, nz must be >= 3 (ghost width)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -467,9 +503,22 @@ int create_impl(const ppk_mhd3d_params *p, ppk_mhd3d *h) {
   g.gamma0 = p->gamma0; g.cfl = p->cfl; g.slope_type = p->slope_type;
   g.smallr = p->smallr; g.smallc = p->smallc; g.smallp = p->smallp;
   g.riemann = p->riemann_solver;
-  g.wrap_x = (p->boundary_type[0] == PPK_BC_PERIODIC && p->boundary_type[1] == PPK_BC_PERIODIC) ? 1 : 0;
+  // (the periodic-copy shortcut only holds where the x ghosts are this sub-domain's own cells)
+  g.wrap_x = (p->mx == 1 && p->boundary_type[0] == PPK_BC_PERIODIC && p->boundary_type[1] == PPK_BC_PERIODIC) ? 1 : 0;
   if (const char *e = getenv("PPK_WRAP_X")) g.wrap_x = g.wrap_x && atoi(e) != 0;
   for (int f = 0; f < 6; ++f) g.bc[f] = p->boundary_type[f];
+  // x / y faces of a block decomposition ([mpi] mx, my > 1): same rule as for z below
+  {
+    const int m[2] = {p->mx, p->my}, pos[2] = {p->rank_x, p->rank_y};
+    for (int d = 0; d < 2; ++d) {
+      if (m[d] <= 1) continue;
+      h->exch_xy[2 * d] = pos[d] != 0 || p->boundary_type[2 * d] == PPK_BC_PERIODIC;
+      h->exch_xy[2 * d + 1] = pos[d] != m[d] - 1 || p->boundary_type[2 * d + 1] == PPK_BC_PERIODIC;
+      for (int side = 0; side < 2; ++side)
+        if (h->exch_xy[2 * d + side]) g.bc[2 * d + side] = BC_COPY;
+    }
+    if (p->mx > 1 || p->my > 1) h->early_halo = false;  // the early z exchange assumes x / y ghosts are local fills
+  }
   // z faces of a decomposed run: inner faces, and outer faces of a periodic domain, belong to the halo
   // exchange (HydroParams.cpp:300-351: neighborsBC = BC_COPY unless on the outer boundary).
   if (p->mz > 1) {
@@ -496,7 +545,7 @@ int create_impl(const ppk_mhd3d_params *p, ppk_mhd3d *h) {
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_xy, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_dt, cudaEventDisableTiming));
-  if (const char *e = getenv("PPK_EARLY_HALO")) h->early_halo = atoi(e) != 0;
+  if (const char *e = getenv("PPK_EARLY_HALO")) h->early_halo = h->early_halo && atoi(e) != 0;
   if (const char *e = getenv("PPK_DEFER_DT")) h->defer_dt = atoi(e) != 0;
   int rc = 0;
   const long long n = g.ncell;
@@ -533,6 +582,9 @@ int ppk_mhd3d_destroy(ppk_mhd3d *h) {
   if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
   for (double *p : {h->U[0], h->U[1], h->Ustage, h->Uspare, h->Q, h->E, h->DBF, h->BASIS, h->F[0], h->F[1], h->F[2], h->EMF, h->diag})
     if (p) cudaFree(p);
+  for (int d = 0; d < 2; ++d)
+    for (int b = 0; b < 4; ++b)
+      if (h->fbuf[d][b]) cudaFree(h->fbuf[d][b]);
   for (auto &pd : h->d2h_pending) cudaEventDestroy(pd.done);
   if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
   if (h->ev_main) cudaEventDestroy(h->ev_main);
@@ -940,7 +992,9 @@ int ppk_mhd3d_halo_plan(const ppk_mhd3d_params *p, int capacity, ppk_halo_msg *m
   const bool lo_outer = p->rank_z == 0, hi_outer = p->rank_z == p->mz - 1;
   const bool exch_lo = !lo_outer || p->boundary_type[4] == PPK_BC_PERIODIC;
   const bool exch_hi = !hi_outer || p->boundary_type[5] == PPK_BC_PERIODIC;
-  const int zlo = (p->rank_z - 1 + p->mz) % p->mz, zhi = (p->rank_z + 1) % p->mz;
+  // ranks are laid out like MPI_Cart_create does for dims (mx, my, mz): z fastest (HydroParams.cpp:249-277)
+  const int base = (p->rank_x * p->my + p->rank_y) * p->mz;
+  const int zlo = base + (p->rank_z - 1 + p->mz) % p->mz, zhi = base + (p->rank_z + 1) % p->mz;
   int n = 0;
   auto add = [&](int peer, int is_send, int var, long long off) {
     if (n < capacity) msgs[n] = ppk_halo_msg{peer, is_send, var, var * ncell + off, cnt};
@@ -953,6 +1007,30 @@ int ppk_mhd3d_halo_plan(const ppk_mhd3d_params *p, int capacity, ppk_halo_msg *m
     if (exch_hi) add(zhi, 1, v, plane * p->nz);           // last interior planes k in [nz, nz+gw) go up
     if (exch_lo) add(zlo, 0, v, 0);                       // lower ghost planes k in [0, gw)
   }
+  return n;
+}
+
+int ppk_mhd3d_face_plan(const ppk_mhd3d_params *p, int dir, ppk_face_msg msgs[4]) {
+  if (!p || !msgs || dir < 0 || dir > 1) return -1;
+  const int m = dir == 0 ? p->mx : p->my, pos = dir == 0 ? p->rank_x : p->rank_y;
+  if (m <= 1) return 0;
+  const long long gw = p->ghost_width;
+  const long long isize = p->nx + 2 * gw, jsize = p->ny + 2 * gw, ksize = p->nz + 2 * gw;
+  const long long count = gw * (dir == 0 ? jsize : isize) * ksize * PPK_NBVAR;
+  const bool exch_lo = pos != 0 || p->boundary_type[2 * dir] == PPK_BC_PERIODIC;
+  const bool exch_hi = pos != m - 1 || p->boundary_type[2 * dir + 1] == PPK_BC_PERIODIC;
+  auto rank_of = [&](int q) {  // global rank of the block at position q along dir
+    const int cx = dir == 0 ? q : p->rank_x, cy = dir == 1 ? q : p->rank_y;
+    return (cx * p->my + cy) * p->mz + p->rank_z;
+  };
+  const int lo = rank_of((pos - 1 + m) % m), hi = rank_of((pos + 1) % m);
+  const int n_int = dir == 0 ? p->nx : p->ny;
+  int n = 0;
+  // same order on every rank (like the z plan): send down, receive from up, send up, receive from down
+  if (exch_lo) msgs[n++] = ppk_face_msg{lo, 1, 0, (int)gw, count};            // first interior layers [gw, 2gw) go down
+  if (exch_hi) msgs[n++] = ppk_face_msg{hi, 0, 1, (int)(n_int + gw), count};  // upper ghost layers [n+gw, n+2gw)
+  if (exch_hi) msgs[n++] = ppk_face_msg{hi, 1, 1, n_int, count};              // last interior layers [n, n+gw) go up
+  if (exch_lo) msgs[n++] = ppk_face_msg{lo, 0, 0, 0, count};                  // lower ghost layers [0, gw)
   return n;
 }
 
@@ -982,8 +1060,9 @@ int ppk_nccl_get_unique_id(void *out) {
 
 int ppk_mhd3d_comm_init(ppk_mhd3d *h, const void *unique_id, int nranks, int rank) {
   if (!h || !unique_id) return fail(PPK_ERR_INVALID_ARGUMENT, "null argument");
-  if (nranks != h->params.mz || rank != h->params.rank_z)
-    return fail(PPK_ERR_INVALID_ARGUMENT, "communicator shape must match (mz, rank_z)");
+  const ppk_mhd3d_params &q = h->params;
+  if (nranks != q.mx * q.my * q.mz || rank != (q.rank_x * q.my + q.rank_y) * q.mz + q.rank_z)
+    return fail(PPK_ERR_INVALID_ARGUMENT, "communicator shape must match mx*my*mz and rank = (rank_x*my + rank_y)*mz + rank_z");
   if (int rc = load_nccl()) return rc;
   DeviceGuard guard(h->device);
   ncclUniqueId id;

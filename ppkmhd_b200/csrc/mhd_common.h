@@ -102,6 +102,9 @@ struct KernelTable {
                   int k0, int k1, cudaStream_t s);
   int (*riemann_all)(const GridParams &g, const double *BASIS, const double *DBF, double *F0, double *F1, double *F2,
                      double *EMF, const void *tma, cudaStream_t s);
+  // block decomposition: pack (pack != 0) the gw layers starting at index c0 along dir (0: x, 1: y) into `buf`, or unpack
+  // `buf` into them; buffer shape = the reference's border buffers (see k_face_copy)
+  void (*face_copy)(const GridParams &g, double *U, double *buf, int dir, int c0, int pack, cudaStream_t s);
 };
 
 const KernelTable *kernel_table_exact();

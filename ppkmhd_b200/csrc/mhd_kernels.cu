@@ -737,6 +737,29 @@ __global__ void k_boundary(const GridParams g, double *__restrict__ U, const int
   }
 }
 
+// x / y faces of a block-decomposed run: the gw layers next to a face are strided in memory, so they travel through a
+// packed buffer with the shape of the reference's border buffers (CopyDataArray_To_BorderBuf / CopyBorderBuf_To_DataArray,
+// mpiBorderUtils.h:184-330; borderBufSend_xmin_3d(gw, jsize, ksize, nbvar), SolverBase.cpp:77-95), ghosts of the other two
+// directions included so that edges and corners propagate through the X -> Y -> Z order of make_boundaries.
+//   DIR 0: buf[g + gw*(j + jsize*(k + ksize*v))] <-> U[c0+g, j, k, v]      DIR 1: buf[i + isize*(g + gw*(k + ksize*v))] <-> U[i, c0+g, k, v]
+template <int DIR, bool PACK>
+__global__ void __launch_bounds__(256) k_face_copy(const GridParams g, double *__restrict__ U, double *__restrict__ buf, const int c0) {
+  const int gw = g.gw;
+  const long long per_var = (long long)gw * (DIR == 0 ? g.jsize : g.isize) * g.ksize;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= per_var) return;
+  int i, j, k;
+  long long r = t;
+  if (DIR == 0) { i = c0 + (int)(r % gw); r /= gw; j = (int)(r % g.jsize); k = (int)(r / g.jsize); }
+  else { i = (int)(r % g.isize); r /= g.isize; j = c0 + (int)(r % gw); k = (int)(r / gw); }
+  const long long c = cidx(g, i, j, k);
+#pragma unroll
+  for (int v = 0; v < NBVAR; ++v) {
+    if (PACK) buf[t + v * per_var] = U[c + v * g.ncell];
+    else U[c + v * g.ncell] = buf[t + v * per_var];
+  }
+}
+
 DEV double warp_max(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -1977,6 +2000,14 @@ static void l_boundary(const GridParams &g, double *U, int dir, int k0, int k1, 
   else if (dir == 1) k_boundary<1><<<cdiv(total, bs), bs, 0, s>>>(g, U, k0, k1 - k0);
   else k_boundary<2><<<cdiv(total, bs), bs, 0, s>>>(g, U, 0, g.ksize);
 }
+static void l_face_copy(const GridParams &g, double *U, double *buf, int dir, int c0, int pack, cudaStream_t s) {
+  const long long per_var = (long long)g.gw * (dir == 0 ? g.jsize : g.isize) * g.ksize;
+  const int bs = 256;
+  if (dir == 0 && pack) k_face_copy<0, true><<<cdiv(per_var, bs), bs, 0, s>>>(g, U, buf, c0);
+  else if (dir == 0) k_face_copy<0, false><<<cdiv(per_var, bs), bs, 0, s>>>(g, U, buf, c0);
+  else if (pack) k_face_copy<1, true><<<cdiv(per_var, bs), bs, 0, s>>>(g, U, buf, c0);
+  else k_face_copy<1, false><<<cdiv(per_var, bs), bs, 0, s>>>(g, U, buf, c0);
+}
 static void l_prim_dt(const GridParams &g, const double *U, double *Q, StepState *st, int k0, int k1, cudaStream_t s) {
   if (k1 <= k0) return;
   const int bs = 256;
@@ -2338,7 +2369,7 @@ static const KernelTable table = {
 #endif
   l_boundary, l_prim_dt, l_finalize_dt, l_advance_time, l_elec_dbf, l_trace, l_flux, l_emf, l_update, l_diagnostics, l_fastmath_selftest, l_consume, l_tma_create, l_tma_destroy, l_hydro, l_update_ct, l_wrap_x_column,
   l2_boundary, l2_prim_dt, l2_trace, l2_flux_emf, l2_update,
-  l_dt_only, l_prod_create, l_prod_destroy, l_producer, l_riemann_all,
+  l_dt_only, l_prod_create, l_prod_destroy, l_producer, l_riemann_all, l_face_copy,
 };
 
 }  // namespace PPK_NS

@@ -98,9 +98,8 @@ void HydroParams::setup(ConfigMap &cfg) {
 }
 
 void HydroParams::setup_multi_gpu(ConfigMap &cfg, int rank, int nranks) {
-  // [mpi] mx,my,mz (HydroParams.cpp:231-233) keep their meaning: a periodic Cartesian grid of
-  // sub-domains, x fastest (MPI_Cart_create row-major order is z fastest in MPI; ranks here are
-  // only ever laid out along z, so the two conventions coincide).
+  // [mpi] mx,my,mz (HydroParams.cpp:231-233) keep their meaning: a periodic Cartesian grid of sub-domains (slabs,
+  // pencils or blocks).
   mx = (int)cfg.getInteger("mpi", "mx", 1);
   my = (int)cfg.getInteger("mpi", "my", 1);
   mz = (int)cfg.getInteger("mpi", "mz", 1);
@@ -116,12 +115,18 @@ void HydroParams::setup_multi_gpu(ConfigMap &cfg, int rank, int nranks) {
     }
   }
   myRank = rank;
-  myMpiPos[0] = 0;
-  myMpiPos[1] = 0;
-  myMpiPos[2] = mz > 1 ? rank % mz : 0;
-  neighborsRank[X_MIN] = neighborsRank[X_MAX] = neighborsRank[Y_MIN] = neighborsRank[Y_MAX] = rank;
-  neighborsRank[Z_MIN] = (myMpiPos[2] - 1 + mz) % mz;
-  neighborsRank[Z_MAX] = (myMpiPos[2] + 1) % mz;
+  // MPI_Cart_create(dims = {mx, my, mz}) numbers the processes with z fastest (HydroParams.cpp:249-277)
+  const int r = nProcs > 1 ? rank % nProcs : 0;
+  myMpiPos[2] = r % mz;
+  myMpiPos[1] = (r / mz) % my;
+  myMpiPos[0] = r / (mz * my);
+  auto rank_of = [&](int cx, int cy, int cz) { return (((cx + mx) % mx) * my + (cy + my) % my) * mz + (cz + mz) % mz; };
+  neighborsRank[X_MIN] = rank_of(myMpiPos[0] - 1, myMpiPos[1], myMpiPos[2]);
+  neighborsRank[X_MAX] = rank_of(myMpiPos[0] + 1, myMpiPos[1], myMpiPos[2]);
+  neighborsRank[Y_MIN] = rank_of(myMpiPos[0], myMpiPos[1] - 1, myMpiPos[2]);
+  neighborsRank[Y_MAX] = rank_of(myMpiPos[0], myMpiPos[1] + 1, myMpiPos[2]);
+  neighborsRank[Z_MIN] = rank_of(myMpiPos[0], myMpiPos[1], myMpiPos[2] - 1);
+  neighborsRank[Z_MAX] = rank_of(myMpiPos[0], myMpiPos[1], myMpiPos[2] + 1);
   for (int f = 0; f < 6; ++f) neighborsBC[f] = BC_COPY;  // HydroParams.cpp:300-351
   if (myMpiPos[0] == 0) neighborsBC[X_MIN] = boundary_type_xmin;
   if (myMpiPos[0] == mx - 1) neighborsBC[X_MAX] = boundary_type_xmax;
@@ -195,8 +200,8 @@ void HydroParams::print() {  // same table as HydroParams.cpp:459-506
   printf("slope_type : %f\n", settings.slope_type);
   printf("riemann    : %d\n", riemannSolverType);
   printf("implementation version : %d\n", implementationVersion);
-  printf("multi-GPU topology     : %dx%dx%d, this slab at z=%d, device %d, %s arithmetic\n", mx, my, mz, myMpiPos[2],
-         device, exactArithmetic ? "exact (no FMA)" : "fast (FMA)");
+  printf("multi-GPU topology     : %dx%dx%d, this sub-domain at (%d,%d,%d), device %d, %s arithmetic\n", mx, my, mz, myMpiPos[0],
+         myMpiPos[1], myMpiPos[2], device, exactArithmetic ? "exact (no FMA)" : "fast (FMA)");
   printf("##########################\n");
 }
 

@@ -92,10 +92,12 @@ void write_pvti_header(const std::string &headerFilename, const std::string &out
   for (int v = 0; v < nbvar; ++v) out << "      <PDataArray type=\"Float64\" Name=\"" << names.at(v) << "\"/>" << std::endl;
   out << "    </PCellData>" << std::endl;
   for (int piece = 0; piece < p.nProcs; ++piece) {
-    const int cz = piece % p.mz;  // slabs: rank == z position
-    out << " <Piece Extent=\"" << 0 << " " << p.nx << " " << 0 << " " << p.ny << " ";
-    if (cz == 0) out << 0 << " " << p.nz << " ";
-    else out << cz * p.nz << " " << cz * p.nz + p.nz << " ";
+    // MPI_Cart coordinates of rank `piece` for dims (mx, my, mz): z fastest (IO_VTK.cpp:975-996 asks the communicator)
+    const int cz = piece % p.mz, cy = (piece / p.mz) % p.my, cx = piece / (p.mz * p.my);
+    out << " <Piece Extent=\"";
+    out << cx * p.nx << " " << cx * p.nx + p.nx << " ";
+    out << cy * p.ny << " " << cy * p.ny + p.ny << " ";
+    out << cz * p.nz << " " << cz * p.nz + p.nz << " ";
     out << "\" Source=\"" << outputPrefix + "_time" + padded(iStep, 7) + "_mpi" + padded(piece, 5) + ".vti" << "\"/>"
         << std::endl;
   }
@@ -124,8 +126,8 @@ void save_VTK_3D_slab(const DataArray3dHost &Uhost, HydroParams &params, ConfigM
   const std::string filename = debug_name.empty() ? dir + "/" + prefix + tail : dir + "/" + prefix + "_" + debug_name + tail;
   if (params.myRank == 0)
     write_pvti_header(dir + "/" + prefix + "_time" + padded(iStep, 7) + ".pvti", prefix, params, nbvar, variables_names, iStep);
-  const int z0 = params.myMpiPos[2] * params.nz;
-  Piece piece{"1.0", {0, params.nx, 0, params.ny, z0, z0 + params.nz}};
+  const int x0 = params.myMpiPos[0] * params.nx, y0 = params.myMpiPos[1] * params.ny, z0 = params.myMpiPos[2] * params.nz;
+  Piece piece{"1.0", {x0, x0 + params.nx, y0, y0 + params.ny, z0, z0 + params.nz}};
   write_vti(filename, Uhost, params, ascii, nbvar, variables_names, piece);
 }
 

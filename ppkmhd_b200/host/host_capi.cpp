@@ -17,9 +17,10 @@ using namespace ppkMHD;
 namespace {
 HydroParams params_for(ConfigMap &cfg, int rank_z) {
   HydroParams p;
-  const int mz = (int)cfg.getInteger("mpi", "mz", 1);
+  // `rank_z` is the process rank of the sub-domain: the slab index for z-slabs, (x*my + y)*mz + z in general
+  const long n = cfg.getInteger("mpi", "mx", 1) * cfg.getInteger("mpi", "my", 1) * cfg.getInteger("mpi", "mz", 1);
   p.forcedRank = rank_z;
-  p.forcedNranks = mz < 1 ? 1 : mz;
+  p.forcedNranks = n < 1 ? 1 : (int)n;
   p.setup(cfg);
   return p;
 }
@@ -134,7 +135,7 @@ int ppk_run_ini(const char *ini_path, int rank, int nranks) {
                              (nonce ? std::string(nonce) : std::to_string((long)getppid()));
     SolverMHDMusclCuda3D *solver3d = dynamic_cast<SolverMHDMusclCuda3D *>(solver);
     if (!solver3d) {
-      fprintf(stderr, "[mpi] mx*my*mz > 1 is only supported by MHD_Muscl_3D (z-slabs); %s is single-GPU\n", solver_name.c_str());
+      fprintf(stderr, "[mpi] mx*my*mz > 1 is only supported by MHD_Muscl_3D; %s is single-GPU\n", solver_name.c_str());
       delete solver;
       return PPK_ERR_UNSUPPORTED;
     }
