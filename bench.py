@@ -427,7 +427,7 @@ def run_ours(args):
     # measured per-kernel counters of this pipeline (profiles/r2/counters.json: ncu on one step, per launch): DRAM bytes
     # (dram__bytes_read.sum + dram__bytes_write.sum) and executed instructions (smsp__inst_executed.sum,
     # smsp__inst_executed_pipe_fp64.sum), both scaled to the cell count of this run
-    traffic, fp64 = None, None
+    traffic, fp64, cj = None, None, None
     cpath = os.path.join(ROOT, "profiles", "r2", "counters.json")
     if os.path.exists(cpath):
         allj = json.load(open(cpath))
@@ -446,12 +446,21 @@ def run_ours(args):
                     "source": f"ncu counters of one {cj['n']}^3 step (profiles/r2/counters.json): smsp__inst_executed_pipe_fp64.sum, "
                               "smsp__inst_executed.sum (warp instructions x 32), dram__bytes_read+write; FP64 peak 17.0 T "
                               "thread-inst/s measured by profiles/microbench/fp64_pipe.cu, issue peak 148 SMs x 4 x 32 x 1.9 GHz"}
+    # per kernel: measured DRAM bytes (ncu, scaled to this run's cell count) over this run's CUDA-event time = the DRAM
+    # bandwidth each kernel actually sustains, as a fraction of the measured copy peak (which kernels are HBM-bound, which not)
+    per_kernel_dram = None
+    if os.path.exists(cpath) and cj:
+        per_kernel_dram = {}
+        for k, v in per_kernel.items():
+            if k in cj["kernels"] and v["ms_per_step"] > 0:
+                gbs = cj["kernels"][k]["dram_bytes"] * (cells_rank / float(cj["cells"])) / (v["ms_per_step"] * 1e-3) / 1e9
+                per_kernel_dram[k] = {"dram_GBs": round(gbs, 1), "frac_of_peak": round(gbs / pk["hbm_gbs"], 3)}
     step_gbs = ALGO_BYTES_PER_CELL * cells_rank * K / (ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_kind + " copy bandwidth (burst)",
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": dom_ms,
                 "whole_step": {"achieved": step_gbs, "frac": step_gbs / pk["hbm_gbs"]},
-                "fp64_pipe": fp64,
+                "fp64_pipe": fp64, "per_kernel_measured_dram": per_kernel_dram,
                 "note": "128 algorithmic B per cell-update (read U^n, write U^n+1). The step executes ~2.9k FP64-pipe and ~6k "
                         "instructions per cell-update: FP64 pipe and instruction issue bound it near 5 Gcell/s = 10% of the "
                         "HBM roofline; see DESIGN.md"}
@@ -470,7 +479,7 @@ def run_ours(args):
         host_free = psutil.virtual_memory().available
     except Exception:
         host_free = 0
-    n_out = 2 if host_free > 4 * nbytes * max(world, 1) else 1
+    n_out = 2 if host_free > 6 * nbytes * max(world, 1) else 1
     host_in = [host, host]
     host_out = [torch.empty(p.shape, dtype=torch.float64).pin_memory() for _ in range(n_out)] * (2 // n_out)
 
