@@ -379,7 +379,7 @@ int enqueue_step(ppk_mhd3d *h) {
   }
   { Scope sc(h, KK_ELEC_DBF, s); h->kt->elec_dbf(g, Uin, h->Q, h->E, h->DBF, s); }
   if (multi) CUDA_TRY(cudaStreamWaitEvent(s, h->ev_dt, 0));
-  { Scope sc(h, KK_TRACE, s); h->kt->trace(g, h->st, Uin, h->Q, h->E, h->BASIS, s); }
+  { Scope sc(h, KK_TRACE, s); h->kt->trace(g, h->st, Uin, h->Q, h->E, h->BASIS, h->tma, s); }
   if (h->pipeline == PPK_PIPELINE_UNFUSED || h->pipeline == PPK_PIPELINE_ORDERED) {
     if (!h->F[0]) {  // flux / EMF arrays are allocated on first use of this pipeline
       if (int rc = ppk_mhd3d_set_pipeline(h, h->pipeline)) return rc;

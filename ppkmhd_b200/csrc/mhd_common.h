@@ -65,7 +65,7 @@ struct KernelTable {
   void (*advance_time)(StepState *st, cudaStream_t s);
   void (*elec_dbf)(const GridParams &g, const double *U, const double *Q, double *E, double *DBF, cudaStream_t s);
   void (*trace)(const GridParams &g, const StepState *st, const double *U, const double *Q, const double *E,
-                double *BASIS, cudaStream_t s);
+                double *BASIS, void *tma, cudaStream_t s);
   // `tma`: context from tma_create (TMA-staged tiles) or nullptr (plain loads)
   void (*flux)(const GridParams &g, int dir, const double *BASIS, double *F, const void *tma, cudaStream_t s);
   void (*emf)(const GridParams &g, int edir, const double *BASIS, const double *DBF, double *EMF, const void *tma, cudaStream_t s);

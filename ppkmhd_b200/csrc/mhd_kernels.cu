@@ -1463,6 +1463,7 @@ __global__ void __launch_bounds__(128, 5)
 }
 
 #include "mhd_rpers.inc"
+#include "mhd_trace_tma.inc"
 
 // Kokkos::deep_copy(data_out, data_in) (SolverMHDMuscl.cpp:477) + UpdateFunctor3D_MHD
 // (MHDRunFunctors3D.h:2430-2544) + UpdateEmfFunctor3D (:2549-2628) in one pass over the array:
@@ -2047,8 +2048,8 @@ static void l_elec_dbf(const GridParams &g, const double *U, const double *Q, do
   else if (minb == 1) k_elec_dbf<1><<<grid, bs, 0, s>>>(g, U, Q, E, DBF, rows);
   else k_elec_dbf<0><<<grid, bs, 0, s>>>(g, U, Q, E, DBF, rows);
 }
-static void l_trace(const GridParams &g, const StepState *st, const double *U, const double *Q, const double *E,
-                    double *BASIS, cudaStream_t s) {
+static void l_trace_plain(const GridParams &g, const StepState *st, const double *U, const double *Q, const double *E,
+                          double *BASIS, cudaStream_t s) {
   const int bs = 128;
   const int rows = slab_rows(g, 46, g.jsize - 4);
   dim3 grid(cdiv((long long)(g.isize - 4) * rows, bs), g.ksize - 4, cdiv(g.jsize - 4, rows));
@@ -2060,15 +2061,24 @@ static void l_trace(const GridParams &g, const StepState *st, const double *U, c
   else k_trace<4><<<grid, bs, 0, s>>>(g, st, U, Q, E, BASIS, rows);
 }
 // ---- TMA tensor maps (host) ---------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 struct TmaCtx {
   CUtensorMap emfB[3], emfD[3], fluxB[3];
   RiemannMaps rall;  // the same nine maps, as the single kernel parameter of k_riemann_all
   unsigned *counter = nullptr;  // work-item counter of k_riemann_pers (device memory, zeroed before every launch)
   int sms = 148;
+  // k_trace_tma: maps of Q and E (encoded at the first launch: both arrays are allocated lazily) and of the face fields of
+  // every conservative array that has been a step input (U, U2, the staging arrays of ppk_mhd3d_stage_*)
+  EncodeTiledFn enc = nullptr;
+  const double *tq = nullptr, *te = nullptr;
+  CUtensorMap trace_q, trace_e;
+  int ntu = 0;
+  const double *tu[4] = {nullptr, nullptr, nullptr, nullptr};
+  CUtensorMap trace_u[4][3];
+  bool trace_attr = false;
 };
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static bool encode_map(EncodeTiledFn enc, CUtensorMap *m, const GridParams &g, const double *base, int ncomp, int xb, int yb, int zb) {
   const cuuint64_t dims[4] = {(cuuint64_t)g.isize, (cuuint64_t)g.jsize, (cuuint64_t)g.ksize, (cuuint64_t)ncomp};
   const cuuint64_t strides[3] = {(cuuint64_t)g.isize * 8, (cuuint64_t)g.isize * g.jsize * 8, (cuuint64_t)g.ncell * 8};
@@ -2091,6 +2101,7 @@ static void *l_tma_create(const GridParams &g, const double *BASIS, const double
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return nullptr;
   EncodeTiledFn enc = (EncodeTiledFn)fn;
   TmaCtx *c = new TmaCtx();
+  c->enc = enc;
   bool ok = encode_cfg<EmfCfg<0>>(enc, &c->emfB[0], g, BASIS, NBASIS) && encode_cfg<EmfCfg<1>>(enc, &c->emfB[1], g, BASIS, NBASIS) &&
             encode_cfg<EmfCfg<2>>(enc, &c->emfB[2], g, BASIS, NBASIS) && encode_cfg<EmfCfg<0>>(enc, &c->emfD[0], g, DBF, NDBF) &&
             encode_cfg<EmfCfg<1>>(enc, &c->emfD[1], g, DBF, NDBF) && encode_cfg<EmfCfg<2>>(enc, &c->emfD[2], g, DBF, NDBF) &&
@@ -2137,6 +2148,52 @@ static void l_tma_destroy(void *ctx) {
   TmaCtx *c = (TmaCtx *)ctx;
   if (c && c->counter) cudaFree(c->counter);
   delete c;
+}
+
+// ComputeTrace: the TMA-staged kernel (mhd_trace_tma.inc) where its boxes exist (even isize, nx >= 32, a TMA context), else the
+// plain-load kernel. PPK_TRACE_TMA=0 forces the plain kernel (A/B).
+static void l_trace(const GridParams &g, const StepState *st, const double *U, const double *Q, const double *E, double *BASIS,
+                    void *tma_, cudaStream_t s) {
+  TmaCtx *c = (TmaCtx *)tma_;
+  static const int use_tma = getenv("PPK_TRACE_TMA") ? atoi(getenv("PPK_TRACE_TMA")) : 1;
+  if (!c || !use_tma || !c->enc || (unsigned long long)g.ncell * 8ull > 0xFFFFFFFFull) return l_trace_plain(g, st, U, Q, E, BASIS, s);
+  using T = TraceTile;
+  if (c->tq != Q || c->te != E) {  // (first launch: Q and E are allocated when a schedule first needs them)
+    if (!encode_map(c->enc, &c->trace_q, g, Q, NBVAR, T::QX, T::QY, T::QZ) || !encode_map(c->enc, &c->trace_e, g, E, NELEC, T::EX, T::EY, T::EZ))
+      return l_trace_plain(g, st, U, Q, E, BASIS, s);
+    c->tq = Q; c->te = E;
+  }
+  if (!c->trace_attr) {
+    if (cudaFuncSetAttribute(k_trace_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES) != cudaSuccess)
+      return l_trace_plain(g, st, U, Q, E, BASIS, s);
+    c->trace_attr = true;
+  }
+  int m = -1;
+  for (int a = 0; a < c->ntu; ++a)
+    if (c->tu[a] == U) m = a;
+  if (m < 0) {  // an array that has not been a step input yet
+    if (c->ntu >= 4) return l_trace_plain(g, st, U, Q, E, BASIS, s);
+    m = c->ntu;
+    if (!encode_map(c->enc, &c->trace_u[m][0], g, U, NBVAR, T::QX, T::TY, 1) || !encode_map(c->enc, &c->trace_u[m][1], g, U, NBVAR, T::QX, T::EY, 1) ||
+        !encode_map(c->enc, &c->trace_u[m][2], g, U, NBVAR, T::QX, T::TY, 2))
+      return l_trace_plain(g, st, U, Q, E, BASIS, s);
+    c->tu[m] = U;
+    c->ntu = m + 1;
+  }
+  TraceMaps maps;
+  maps.q = c->trace_q; maps.e = c->trace_e;
+  maps.ua = c->trace_u[m][0]; maps.ub = c->trace_u[m][1]; maps.uc = c->trace_u[m][2];
+  TracePlan pl;
+  const int nrows = g.jsize - 4, nk = g.ksize - 4;
+  pl.ntx = (int)cdiv(g.isize - 4, T::TX);
+  pl.rows = slab_rows(g, 46, nrows);
+  pl.rows = (pl.rows + T::TY - 1) / T::TY * T::TY;
+  pl.nslab = (int)cdiv(nrows, pl.rows);
+  pl.per_plane = (unsigned)pl.ntx * (unsigned)(pl.rows / T::TY);
+  pl.per_slab = (unsigned)nk * pl.per_plane;
+  const unsigned long long total = (unsigned long long)pl.nslab * pl.per_slab;
+  if (total > 0x7FFFFFFFull) return l_trace_plain(g, st, U, Q, E, BASIS, s);
+  k_trace_tma<<<(unsigned)total, 128, T::SMEM_BYTES, s>>>(g, st, maps, pl, BASIS);
 }
 
 template <int D>
