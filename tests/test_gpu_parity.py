@@ -520,3 +520,49 @@ def test_blocks_bit_identical_to_single_gpu(tmp_path, shape, nblock, bc):
         m = np.load(tmp_path / f"meta{r}.npy")
         assert m[0] == t and m[1] == dt and m[2] == it, (r, m[:3], t, dt, it)
     assert np.array_equal(got, want), "block-decomposed run differs from the single-GPU run"
+
+
+def test_split_phase_transfers_and_default_schedule():
+    """ppk_mhd3d_stage_upload / _stage_swap / _stage_download (pipelined host transfers on one handle, what bench.py's e2e
+    leg drives) return exactly what upload -> step -> download returns, batch after batch, while four device arrays
+    rotate; and the default schedule is the measured one: unfused below 384^2-cell planes, ordered from there on."""
+    import torch
+
+    from oracle import oracle as O  # ini text helper only
+
+    ini = O.make_ini("orszag_tang", (64, 36, 20), nstepmax=1, extra=OT, tend=10.0)
+    ref, _ = make_solver(ini, exact=True)
+    assert ref.pipeline() == "unfused"
+    u0 = ppk.init_condition_from_ini(ini)
+    ref.step()
+    want1 = ref.download().copy()       # one step from the initial state
+    ref.step()
+    want2 = ref.download().copy()       # two steps (same handle: U / U2 parity flips)
+    ref.close()
+
+    p, t_end, _ = ppk.params_from_ini(ini, exact=True)
+    s = ppk.Mhd3d(p)
+    s.set_time(0.0, t_end, 0)
+    pin = [torch.from_numpy(u0.copy()).pin_memory(), torch.from_numpy(want1.copy()).pin_memory()]
+    out = [torch.empty(p.shape, dtype=torch.float64).pin_memory() for _ in range(6)]
+    # batches alternate between the initial state and the one-step state: results must be want1 / want2 alternately
+    s.stage_upload(pin[0].data_ptr())
+    for b in range(6):
+        s.stage_swap()
+        s.step()
+        s.stage_download(out[b].data_ptr())
+        if b + 1 < 6:
+            s.stage_upload(pin[(b + 1) % 2].data_ptr())
+    s.synchronize()
+    gw = 3
+    inner = (slice(None), slice(gw, -gw), slice(gw, -gw), slice(gw, -gw))
+    for b in range(6):
+        want = want1 if b % 2 == 0 else want2
+        assert np.array_equal(out[b].numpy()[inner], want[inner]), f"batch {b} differs"
+    s.close()
+
+    big = O.make_ini("orszag_tang", (384, 384, 8), nstepmax=1, extra=OT, tend=10.0)
+    pb, _, _ = ppk.params_from_ini(big, exact=False)
+    sb = ppk.Mhd3d(pb)
+    assert sb.pipeline() == "ordered"
+    sb.close()
