@@ -198,6 +198,10 @@ int ppk_mhd3d_get_pipeline(ppk_mhd3d *handle); /* the schedule in use (enum ppk_
 /* Per-kernel CUDA-event timing (replaces the coarse timers of SolverBase.h:35-42 for profiling).
  * While enabled every kernel launch is bracketed by events on the launch stream. */
 int ppk_mhd3d_profile(ppk_mhd3d *handle, int enable);
+/* The launches timed since ppk_mhd3d_profile(handle, 1), in launch order: kernel name, whether it ran on the handle's
+ * communication stream (NCCL exchange, the deferred dt all-reduce) or on the compute stream, start and end in ms after that
+ * call. A CUDA-event timeline of the decomposed step (what runs under what); returns the number of entries written. */
+int ppk_mhd3d_kernel_timeline(ppk_mhd3d *handle, int capacity, const char **names, int *on_comm_stream, double *start_ms, double *end_ms);
 /* Accumulated milliseconds and launch counts per kernel since the last reset; returns the number of
  * kernel kinds (<= capacity). `names[i]` points to static strings. */
 int ppk_mhd3d_kernel_times(ppk_mhd3d *handle, int capacity, const char **names, double *ms, long *launches, int reset);

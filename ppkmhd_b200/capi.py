@@ -68,7 +68,7 @@ EXPORTS = [
     "ppk_mhd3d_create", "ppk_mhd3d_destroy", "ppk_mhd3d_upload", "ppk_mhd3d_download", "ppk_mhd3d_download_async", "ppk_mhd3d_set_time",
     "ppk_mhd3d_get_time", "ppk_mhd3d_make_boundaries", "ppk_mhd3d_compute_dt", "ppk_mhd3d_step", "ppk_mhd3d_run",
     "ppk_mhd3d_synchronize", "ppk_mhd3d_diagnostics", "ppk_nccl_get_unique_id", "ppk_mhd3d_comm_init",
-    "ppk_mhd3d_set_stream", "ppk_mhd3d_profile", "ppk_mhd3d_kernel_times", "ppk_mhd3d_launch_count",
+    "ppk_mhd3d_set_stream", "ppk_mhd3d_profile", "ppk_mhd3d_kernel_times", "ppk_mhd3d_kernel_timeline", "ppk_mhd3d_launch_count",
     "ppk_mhd3d_debug_array", "ppk_mhd3d_device_bytes", "ppk_last_error_string", "ppk_version_string",
     "ppk_mhd3d_halo_plan", "ppk_mhd3d_face_plan", "ppk_selftest_fastmath", "ppk_mhd3d_set_pipeline",
     "ppk_mhd3d_get_pipeline", "ppk_mhd3d_stage_upload", "ppk_mhd3d_stage_swap", "ppk_mhd3d_stage_download",
@@ -362,6 +362,18 @@ class Mhd3d:
         if k < 0:
             raise PpkError(self.L.ppk_last_error_string().decode())
         return {names[i].decode(): (ms[i], cnt[i]) for i in range(k)}
+
+    def kernel_timeline(self, capacity=4096):
+        """ppk_mhd3d_kernel_timeline: [(name, on_comm_stream, start_ms, end_ms)] of the launches since profile(True)."""
+        names = (C.c_char_p * capacity)()
+        comm = (C.c_int * capacity)()
+        t0 = (C.c_double * capacity)()
+        t1 = (C.c_double * capacity)()
+        self.L.ppk_mhd3d_kernel_timeline.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        k = self.L.ppk_mhd3d_kernel_timeline(self.h, capacity, names, comm, t0, t1)
+        if k < 0:
+            raise PpkError(self.L.ppk_last_error_string().decode())
+        return [(names[i].decode(), bool(comm[i]), t0[i], t1[i]) for i in range(k)]
 
     def launch_count(self):
         return self.L.ppk_mhd3d_launch_count(self.h)

@@ -116,8 +116,12 @@ struct ppk_mhd3d {
   long host_iteration = 0;  // parity selects U / U2 like SolverMHDMuscl::godunov_unsplit (SolverMHDMuscl.h:793-805)
   // profiling
   bool profile = false;
-  struct Timed { int kind; cudaEvent_t a, b; };
+  struct Timed { int kind; cudaEvent_t a, b; int on_comm; };
   std::vector<Timed> pending;
+  // optional timeline of the launches timed since ppk_mhd3d_profile(h, 1): start / end relative to that call
+  cudaEvent_t t0 = nullptr;
+  struct Span { int kind; int on_comm; float start_ms, end_ms; };
+  std::vector<Span> timeline;
   std::vector<cudaEvent_t> pool;
   double acc_ms[KK_COUNT] = {0};
   long acc_n[KK_COUNT] = {0};
@@ -177,7 +181,7 @@ struct Scope {  // brackets one kernel launch with events when profiling
     h->launches += 1;
     if (h->profile) {
       cudaEventRecord(b, s);
-      h->pending.push_back({kind, a, b});
+      h->pending.push_back({kind, a, b, s == h->comm_stream ? 1 : 0});
     }
   }
 };
@@ -189,6 +193,11 @@ int collect_timings(ppk_mhd3d *h) {
     CUDA_TRY(cudaEventElapsedTime(&ms, p.a, p.b));
     h->acc_ms[p.kind] += ms;
     h->acc_n[p.kind] += 1;
+    if (h->t0 && h->timeline.size() < 4096) {
+      float t_a = 0.f;
+      if (cudaEventElapsedTime(&t_a, h->t0, p.a) == cudaSuccess) h->timeline.push_back({p.kind, p.on_comm, t_a, t_a + ms});
+      else (void)cudaGetLastError();
+    }
     h->pool.push_back(p.a);
     h->pool.push_back(p.b);
   }
@@ -586,6 +595,7 @@ int ppk_mhd3d_destroy(ppk_mhd3d *h) {
     for (int b = 0; b < 4; ++b)
       if (h->fbuf[d][b]) cudaFree(h->fbuf[d][b]);
   for (auto &pd : h->d2h_pending) cudaEventDestroy(pd.done);
+  if (h->t0) cudaEventDestroy(h->t0);
   if (h->ev_h2d) cudaEventDestroy(h->ev_h2d);
   if (h->ev_main) cudaEventDestroy(h->ev_main);
   if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
@@ -1109,7 +1119,26 @@ int ppk_mhd3d_profile(ppk_mhd3d *h, int enable) {
   DeviceGuard guard(h->device);
   if (int rc = collect_timings(h)) return rc;
   h->profile = enable != 0;
+  if (h->profile) {  // origin of the timeline (ppk_mhd3d_kernel_timeline)
+    if (!h->t0) CUDA_TRY(cudaEventCreate(&h->t0));
+    h->timeline.clear();
+    CUDA_TRY(cudaEventRecord(h->t0, h->stream));
+  }
   return 0;
+}
+
+int ppk_mhd3d_kernel_timeline(ppk_mhd3d *h, int capacity, const char **names, int *on_comm_stream, double *start_ms, double *end_ms) {
+  if (!h) return -1;
+  DeviceGuard guard(h->device);
+  if (collect_timings(h)) return -1;
+  const int n = (int)h->timeline.size() < capacity ? (int)h->timeline.size() : capacity;
+  for (int i = 0; i < n; ++i) {
+    if (names) names[i] = kKernelNames[h->timeline[i].kind];
+    if (on_comm_stream) on_comm_stream[i] = h->timeline[i].on_comm;
+    if (start_ms) start_ms[i] = h->timeline[i].start_ms;
+    if (end_ms) end_ms[i] = h->timeline[i].end_ms;
+  }
+  return n;
 }
 
 int ppk_mhd3d_kernel_times(ppk_mhd3d *h, int capacity, const char **names, double *ms, long *launches, int reset) {
