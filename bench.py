@@ -115,7 +115,8 @@ def workload_config(args, world):
     title = {"orszag_tang": "Orszag-Tang 3D kt=1", "blast": "MHD blast 3D", "field_loop": "MHD field-loop advection 3D"}[args.workload]
     return {"workload": f"{title}, {n}x{n}x{nz} cells per GPU (global {n}x{n}x{nz * world}), z-slabs mz={world}, HLLD + CT, periodic, "
                         f"cfl {PROBLEMS[args.workload][2]}, gamma 1.666, implementationVersion=0 semantics",
-            "problem": args.workload, "n": n, "nz_per_gpu": nz, "scaling": "strong" if args.strong else "weak"}
+            "problem": args.workload, "n": n, "nz_per_gpu": nz, "scaling": "strong" if args.strong else "weak",
+            "l2": f"inputs larger than L2 (every array >= {8.0 * n * n * nz / 1e9:.1f} GB per GPU vs 126 MB L2), no flush needed"}
 
 
 def peaks():
@@ -280,12 +281,12 @@ def run_reference_arm(args):
         return
     threads = os.cpu_count() or 1
     n = args.ref_n
-    steps, warm = args.steps, max(args.warmup, 1)
+    steps, warm = args.steps, max(args.warmup, 3)  # (the same W >= 3 as our arm)
     v, kind, spp = cpu_reference_throughput(n, steps, warm, threads, args.workload)
     sample = (f"{args.workload} {n}^3 sample of the workload, {steps} timed steps after {warm} warm-up steps (total-time difference of "
               f"two runs of oracle/_ref/ppkMHD), {threads} OpenMP threads, implementationVersion=0")
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": spp * 1e3, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args, max(args.gpus, 1)),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
@@ -557,16 +558,15 @@ def run_ours(args):
         ref_cuda = ref_cuda_throughput(256, local)  # v0 of the reference needs 207 doubles per cell: 256^3 is what fits
 
     if rank == 0:
-        cfg = workload_config(args, world)
-        cfg.update({"pipeline": pipeline,
-                    "arithmetic": "fast (FMA contraction, within 1e-12 of the reference)" if not exact else "exact (--fmad=false, bit-identical)",
-                    "l2": f"inputs larger than L2 (every array >= {8 * cells_rank / 1e9:.1f} GB vs 126 MB L2)",
-                    "cells_with_ghosts_per_gpu": int(np.prod(p.shape[1:])),
-                    "reference_style_value_with_ghosts": value * float(np.prod(p.shape[1:])) / cells_rank})
+        cfg = workload_config(args, world)  # identical in the reference arm's line
+        details = {"pipeline": pipeline,
+                   "arithmetic": "fast (FMA contraction, within 1e-12 of the reference)" if not exact else "exact (--fmad=false, bit-identical)",
+                   "cells_with_ghosts_per_gpu": int(np.prod(p.shape[1:])),
+                   "reference_style_value_with_ghosts": value * float(np.prod(p.shape[1:])) / cells_rank}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": cfg,
+            "dtype": "f64", "data": "synthetic", "config": cfg, "details": details,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "sustained": sustained, "extra": extra, "reference_cuda_baseline": ref_cuda,
             "per_kernel_ms": {k: round(v["ms_per_step"], 4) for k, v in per_kernel.items()},

@@ -10,7 +10,7 @@ bash profiles/r2/counters.sh 256 tiled
 python - <<PY
 import json
 j=json.load(open("gpurun_out/r2_b10_default.json"))
-print(round(j["value"],1), "Mcell/s", round(j["ms_per_step"],3), "ms", j["config"]["pipeline"], j["per_kernel_ms"])
+print(round(j["value"],1), "Mcell/s", round(j["ms_per_step"],3), "ms", j["details"]["pipeline"], j["per_kernel_ms"])
 print("sustained", j["sustained"]); print("e2e", j["e2e"]["value"], "extra", j["extra"], "cpu", j["cpu_baseline"], "refcuda", j["reference_cuda_baseline"])
 print("roofline", j["roofline"]); print("clocks", j["clocks"])
 PY

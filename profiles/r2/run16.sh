@@ -13,7 +13,7 @@ import json
 for n in ("256","256o","512"):
     try:
         j=json.load(open(f"gpurun_out/r2_b${T}_{n}.json"))
-        print(n, j["config"]["pipeline"], round(j["value"],1), "Mcell/s", round(j["ms_per_step"],3), "ms", j["per_kernel_ms"], j["clocks"]["sm_mhz"])
+        print(n, j["details"]["pipeline"], round(j["value"],1), "Mcell/s", round(j["ms_per_step"],3), "ms", j["per_kernel_ms"], j["clocks"]["sm_mhz"])
     except Exception as e:
         print(n, "failed", e)
 PY

@@ -14,7 +14,7 @@ import json
 for n in ("256_0","256_1","512_0","512_1"):
     try:
         j=json.load(open(f"gpurun_out/r2_b${T}_{n}.json"))
-        print(n, j["config"]["pipeline"], round(j["value"],1), "Mcell/s", round(j["ms_per_step"],3), "ms trace", j["per_kernel_ms"]["trace"], j["clocks"]["sm_mhz"])
+        print(n, j["details"]["pipeline"], round(j["value"],1), "Mcell/s", round(j["ms_per_step"],3), "ms trace", j["per_kernel_ms"]["trace"], j["clocks"]["sm_mhz"])
     except Exception as e:
         print(n, "failed", e)
 PY
