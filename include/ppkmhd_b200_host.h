@@ -37,6 +37,13 @@ int ppk_init_condition_2d_from_ini(const char *ini_text, double *u_host);
  * needs no GPU (the solvers call the same writer after ppk_mhd3d_download). */
 int ppk_save_data_from_ini(const char *ini_text, int rank_z, const double *u_host, int i_step);
 
+/* IO_ReadWrite::load_data (src/utils/io/IO_ReadWrite.cpp:245-287 -> Load_HDF5<d>::load, src/utils/io/IO_HDF5.h:1537-2153): read the
+ * restart file named by [run] restart_filename (.h5) into `u_host` (8*isize*jsize*ksize doubles: the interior, or the whole array
+ * when the file carries its ghost zones) and return the file's "time step" and "total time" attributes. What
+ * SolverMHDMuscl<dim>::init_restart (SolverMHDMuscl.h:615-643) calls; PPK_ERR_UNSUPPORTED without a usable libhdf5 or when the
+ * file does not fit the [mesh] sizes. */
+int ppk_load_data_from_ini(const char *ini_text, int rank_z, double *u_host, int *i_step, double *time);
+
 /* 1 when a libhdf5 (>= 1.10) was found at run time (dlopen; PPK_HDF5_LIB overrides the search), else 0. The reference
  * decides this at build time (USE_HDF5); with 0, [output] hdf5_enabled=true makes ppk_save_data_from_ini return
  * PPK_ERR_UNSUPPORTED after writing the VTK files, and [run] restart_enabled=true stops the program with a message. */

@@ -13,6 +13,7 @@ from .capi import (  # noqa: F401
     selftest_fastmath,
     init_condition_from_ini,
     save_data_from_ini,
+    load_data_from_ini,
     hdf5_available,
     write_xdmf_from_ini,
     init_condition_2d_from_ini,
@@ -24,5 +25,5 @@ from .capi import (  # noqa: F401
 
 __all__ = [
     "Mhd3d", "Mhd2d", "Params", "PpkError", "lib_path", "load_library", "build_library",
-    "params_from_ini", "init_condition_from_ini", "save_data_from_ini", "hdf5_available", "write_xdmf_from_ini", "init_condition_2d_from_ini", "nccl_unique_id", "halo_plan", "face_plan", "selftest_fastmath",
+    "params_from_ini", "init_condition_from_ini", "save_data_from_ini", "load_data_from_ini", "hdf5_available", "write_xdmf_from_ini", "init_condition_2d_from_ini", "nccl_unique_id", "halo_plan", "face_plan", "selftest_fastmath",
 ]

@@ -72,7 +72,7 @@ EXPORTS = [
     "ppk_mhd3d_debug_array", "ppk_mhd3d_device_bytes", "ppk_last_error_string", "ppk_version_string",
     "ppk_mhd3d_halo_plan", "ppk_mhd3d_face_plan", "ppk_selftest_fastmath", "ppk_mhd3d_set_pipeline",
     "ppk_mhd3d_get_pipeline", "ppk_mhd3d_stage_upload", "ppk_mhd3d_stage_swap", "ppk_mhd3d_stage_download",
-    "ppk_params_from_ini", "ppk_init_condition_from_ini", "ppk_run_ini", "ppk_save_data_from_ini", "ppk_hdf5_available", "ppk_write_xdmf_from_ini", "ppk_init_condition_2d_from_ini",
+    "ppk_params_from_ini", "ppk_init_condition_from_ini", "ppk_run_ini", "ppk_save_data_from_ini", "ppk_load_data_from_ini", "ppk_hdf5_available", "ppk_write_xdmf_from_ini", "ppk_init_condition_2d_from_ini",
     "ppk_mhd2d_create", "ppk_mhd2d_destroy", "ppk_mhd2d_upload", "ppk_mhd2d_download", "ppk_mhd2d_set_time", "ppk_mhd2d_get_time",
     "ppk_mhd2d_make_boundaries", "ppk_mhd2d_compute_dt", "ppk_mhd2d_step", "ppk_mhd2d_run", "ppk_mhd2d_synchronize", "ppk_mhd2d_launch_count",
 ]
@@ -125,6 +125,7 @@ def load_library():
     L.ppk_init_condition_from_ini.argtypes = [C.c_char_p, C.c_int, vp]
     L.ppk_save_data_from_ini.argtypes = [C.c_char_p, C.c_int, vp, C.c_int]
     L.ppk_write_xdmf_from_ini.argtypes = [C.c_char_p, C.c_int, C.c_int]
+    L.ppk_load_data_from_ini.argtypes = [C.c_char_p, C.c_int, vp, C.POINTER(C.c_int), dp]
     L.ppk_run_ini.argtypes = [C.c_char_p, C.c_int, C.c_int]
     L.ppk_init_condition_2d_from_ini.argtypes = [C.c_char_p, vp]
     L.ppk_mhd2d_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
@@ -173,6 +174,15 @@ def save_data_from_ini(ini_text: str, U: np.ndarray, i_step: int, rank_z: int = 
     L = load_library()
     U = np.ascontiguousarray(U, dtype=np.float64)
     _check(L.ppk_save_data_from_ini(ini_text.encode(), rank_z, U.ctypes.data, i_step))
+
+
+def load_data_from_ini(ini_text: str, U: np.ndarray, rank_z: int = 0):
+    """ppk_load_data_from_ini: restart file ([run] restart_filename) -> U (in place), returns (output number, time)."""
+    L = load_library()
+    assert U.dtype == np.float64 and U.flags["C_CONTIGUOUS"]
+    step, t = C.c_int(0), C.c_double(0.0)
+    _check(L.ppk_load_data_from_ini(ini_text.encode(), rank_z, U.ctypes.data, C.byref(step), C.byref(t)))
+    return step.value, t.value
 
 
 def hdf5_available() -> bool:

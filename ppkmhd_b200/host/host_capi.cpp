@@ -87,6 +87,28 @@ int ppk_save_data_from_ini(const char *ini_text, int rank_z, const double *u_hos
   return writer.hdf5_failed ? PPK_ERR_UNSUPPORTED : 0;  // [output] hdf5_enabled without a usable libhdf5
 }
 
+int ppk_load_data_from_ini(const char *ini_text, int rank_z, double *u_host, int *i_step, double *time) {
+  if (!ini_text || !u_host) return PPK_ERR_INVALID_ARGUMENT;
+  ConfigMap cfg(ini_text, (int)strlen(ini_text));
+  HydroParams p = params_for(cfg, rank_z);
+  DataArray3dHost U(p.isize, p.jsize, p.dimType == TWO_D ? 1 : p.ksize, p.nbvar);
+  memcpy(U.data(), u_host, U.size() * sizeof(double));  // (cells the file does not cover keep the caller's values)
+  std::map<int, std::string> names = {{ID, "rho"}, {IP, "energy"}, {IU, "rho_vx"}, {IV, "rho_vy"}, {IW, "rho_vz"},
+                                      {IA, "bx"},  {IB, "by"},     {IC, "bz"}};
+  io::IO_ReadWrite reader(p, cfg, names);
+  std::string why;
+  int step = 0;
+  real_t t = 0;
+  if (!reader.load_data(U, step, t, &why)) {
+    fprintf(stderr, "ppk_load_data_from_ini: %s\n", why.c_str());
+    return PPK_ERR_UNSUPPORTED;
+  }
+  memcpy(u_host, U.data(), U.size() * sizeof(double));
+  if (i_step) *i_step = step;
+  if (time) *time = t;
+  return 0;
+}
+
 int ppk_hdf5_available(void) { return io::hdf5_available(nullptr) ? 1 : 0; }
 
 int ppk_write_xdmf_from_ini(const char *ini_text, int total_number_of_steps, int single_step) {
