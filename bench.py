@@ -591,7 +591,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the 256^3 (configs[1]) measurement beside the headline size")
     ap.add_argument("--mode", default="fast", choices=["fast", "exact"])
     ap.add_argument("--pipeline", default="auto", choices=["auto", "ordered", "tiled", "fused", "fused_split", "unfused", "streamed"],
-                    help="auto = the handle's default (unfused below 384^2-cell planes, ordered above)")
+                    help="auto = the handle's default (unfused: the schedule that measured fastest at 256^3 and 512^3)")
     ap.add_argument("--ref-n", type=int, default=256, help="grid of the reference arm's bounded sample (--impl reference)")
     ap.add_argument("--e2e-steps", type=int, default=9)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -172,10 +172,11 @@ int ppk_mhd3d_face_plan(const ppk_mhd3d_params *params, int dir, ppk_face_msg ms
 /* Run on a caller-owned stream (a cudaStream_t, e.g. torch's current stream) instead of the
  * handle's own non-blocking stream. */
 int ppk_mhd3d_set_stream(ppk_mhd3d *handle, void *cuda_stream);
-/* Kernel schedule of one step (results are identical, bit for bit in exact mode). The default is picked from measurements
- * (DESIGN.md 4): UNFUSED for planes below 384^2 cells, ORDERED above; every schedule stays selectable and tested.
- *   PPK_PIPELINE_UNFUSED: ghost fill | primitives + CFL | edge E +
- *       face-B slopes | Hancock trace | one TMA-staged kernel per flux direction and EMF component | update;
+/* Kernel schedule of one step (results are identical, bit for bit in exact mode). The default is the one that measured
+ * fastest at 256^3 and at 512^3: UNFUSED; every schedule stays selectable and tested.
+ *   PPK_PIPELINE_UNFUSED (default): ghost fill | primitives + CFL | edge E + face-B slopes | Hancock trace (TMA-staged) | x-faces +
+ *       y-faces + z-edges in ONE launch on shared TMA tiles (the three Riemann tasks that read plane k only) | z-faces | y-edges |
+ *       x-edges (one TMA-staged kernel each) | update;
  *       stores Fluxes_x|y|z and Emf like the reference's v0 (what ppk_mhd3d_debug_array exposes);
  *   PPK_PIPELINE_FUSED: after the trace, ONE z-marching consumer kernel = HLLD fluxes x,y,z + edge EMFs z,y,x +
  *       conservative and CT update; fluxes and EMFs never reach HBM (2.2x less DRAM traffic for that part, but
@@ -186,7 +187,7 @@ int ppk_mhd3d_set_stream(ppk_mhd3d *handle, void *cuda_stream);
  *       array), then the TMA-staged EMF kernels and the CT update of the field.
  *   PPK_PIPELINE_ORDERED: UNFUSED with the six flux / EMF kernels replaced by ONE launch whose CTAs are dispatched in the
  *       order (y-slab, plane, task, tile): the basis numbers of a plane come from HBM for the first task that touches them
- *       and from the L2 for the five others (512^3: 33.6 -> 31.2 ms). Works on decomposed runs (mz > 1) like UNFUSED;
+ *       and from the L2 for the others (the plane-k tasks are one merged work item here too). Works on decomposed runs like UNFUSED;
  *       falls back to UNFUSED where the TMA tiles do not exist (odd nx, nx < 32).
  *   PPK_PIPELINE_TILED (even nx >= 32, mz = 1): ghost fill | CFL reduction (reads U only) |
  *       ONE fused producer kernel = primitives + edge electric field + face-field slopes + hydro slopes + Hancock trace

@@ -88,7 +88,7 @@ int load_nccl() {
 const char *const kKernelNames[KK_COUNT] = {"boundary", "prim_dt", "finalize_dt", "elec_dbf", "trace",
                                             "flux_x", "flux_y", "flux_z", "emf_z", "emf_y", "emf_x",
                                             "update", "diagnostics", "halo_exchange", "consume", "hydro", "update_ct",
-                                            "dt_only", "producer", "riemann_all"};
+                                            "dt_only", "producer", "riemann_all", "flux_xy_emf_z"};
 
 }  // namespace
 
@@ -399,10 +399,15 @@ int enqueue_step(ppk_mhd3d *h) {
       one_launch = h->kt->riemann_all(g, h->BASIS, h->DBF, h->F[0], h->F[1], h->F[2], h->EMF, h->tma, s) == 0;
     }
     if (!one_launch) {
-      { Scope sc(h, KK_FLUX_X, s); h->kt->flux(g, 0, h->BASIS, h->F[0], h->tma, s); }
-      { Scope sc(h, KK_FLUX_Y, s); h->kt->flux(g, 1, h->BASIS, h->F[1], h->tma, s); }
+      bool grouped = false;  // x-faces, y-faces and z-edges read plane k only: one launch on shared tiles where available
+      { Scope sc(h, KK_PLANE_GROUP, s); grouped = h->kt->plane_group(g, h->BASIS, h->DBF, h->F[0], h->F[1], h->EMF, h->tma, s) == 0; }
+      if (!grouped) {
+        h->launches -= 1;
+        { Scope sc(h, KK_FLUX_X, s); h->kt->flux(g, 0, h->BASIS, h->F[0], h->tma, s); }
+        { Scope sc(h, KK_FLUX_Y, s); h->kt->flux(g, 1, h->BASIS, h->F[1], h->tma, s); }
+        { Scope sc(h, KK_EMF_Z, s); h->kt->emf(g, 2, h->BASIS, h->DBF, h->EMF, h->tma, s); }
+      }
       { Scope sc(h, KK_FLUX_Z, s); h->kt->flux(g, 2, h->BASIS, h->F[2], h->tma, s); }
-      { Scope sc(h, KK_EMF_Z, s); h->kt->emf(g, 2, h->BASIS, h->DBF, h->EMF, h->tma, s); }
       { Scope sc(h, KK_EMF_Y, s); h->kt->emf(g, 1, h->BASIS, h->DBF, h->EMF, h->tma, s); }
       { Scope sc(h, KK_EMF_X, s); h->kt->emf(g, 0, h->BASIS, h->DBF, h->EMF, h->tma, s); }
     }
@@ -564,11 +569,10 @@ int create_impl(const ppk_mhd3d_params *p, ppk_mhd3d *h) {
     return rc;
   h->tma = h->kt->tma_create(g, h->BASIS, h->DBF);
   h->prod = h->kt->prod_create(g, h->U[0], h->U[1]);
-  // Default schedule, from the A/B measurements of profiles/r2 (B200, Orszag-Tang kt=1): one kernel per functor up to
-  // 256^2-cell planes (6.98 ms at 256^3 against 7.25 ms tiled); from there on the six Riemann tasks as one L2-ordered
-  // launch (512^3: 31.2 ms against 33.6 ms for the six launches, whose basis planes no longer stay in the L2 between them).
+  // Default schedule, from the A/B measurements of profiles/r2 (B200, Orszag-Tang kt=1): one kernel per functor, with the three
+  // Riemann tasks that read plane k only (x-faces, y-faces, z-edges) merged into one launch on shared tiles (mhd_pgroup.inc):
+  // 6.84 ms at 256^3 (tiled 7.25, ordered 7.10), 56.0 ms at 512^3 (ordered 56.9, tiled 61.5).
   h->pipeline = PPK_PIPELINE_UNFUSED;
-  if (h->tma && (long long)g.nx * g.ny >= 384LL * 384LL) h->pipeline = PPK_PIPELINE_ORDERED;
   if (const char *e = getenv("PPK_PIPELINE")) {
     const int want = atoi(e);
     if (want == PPK_PIPELINE_ORDERED && !h->tma) h->pipeline = PPK_PIPELINE_UNFUSED;

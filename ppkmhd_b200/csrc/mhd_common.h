@@ -52,7 +52,7 @@ struct StepState {
 // kernel kinds, for the per-kernel timers
 enum KernelKind {
   KK_BOUNDARY = 0, KK_PRIM_DT, KK_FINALIZE_DT, KK_ELEC_DBF, KK_TRACE,
-  KK_FLUX_X, KK_FLUX_Y, KK_FLUX_Z, KK_EMF_Z, KK_EMF_Y, KK_EMF_X, KK_UPDATE, KK_DIAG, KK_HALO, KK_CONSUME, KK_HYDRO, KK_UPDATE_CT, KK_DT_ONLY, KK_PRODUCER, KK_RIEMANN_ALL, KK_COUNT
+  KK_FLUX_X, KK_FLUX_Y, KK_FLUX_Z, KK_EMF_Z, KK_EMF_Y, KK_EMF_X, KK_UPDATE, KK_DIAG, KK_HALO, KK_CONSUME, KK_HYDRO, KK_UPDATE_CT, KK_DT_ONLY, KK_PRODUCER, KK_RIEMANN_ALL, KK_PLANE_GROUP, KK_COUNT
 };
 
 // Launchers exported by each arithmetic build (mhd_kernels.cu compiled twice).
@@ -105,6 +105,10 @@ struct KernelTable {
   // block decomposition: pack (pack != 0) the gw layers starting at index c0 along dir (0: x, 1: y) into `buf`, or unpack
   // `buf` into them; buffer shape = the reference's border buffers (see k_face_copy)
   void (*face_copy)(const GridParams &g, double *U, double *buf, int dir, int c0, int pack, cudaStream_t s);
+  // x-faces + y-faces + z-edges (the three Riemann tasks that read plane k only) in one launch on shared TMA tiles;
+  // returns -1 when unavailable (the caller launches flux(0), flux(1), emf(2) instead)
+  int (*plane_group)(const GridParams &g, const double *BASIS, const double *DBF, double *F0, double *F1, double *EMF,
+                     const void *tma, cudaStream_t s);
 };
 
 const KernelTable *kernel_table_exact();

@@ -1407,6 +1407,8 @@ __global__ void __launch_bounds__(FluxCfg<D>::THREADS, FluxCfg<D>::MINB)
   flux_tile_body<D, RS>(g, &mapB, F, sm, &bar, i0, j0, k0);
 }
 
+#include "mhd_pgroup.inc"
+
 // ---------------------------------------------------------------------------------------------
 // All six Riemann tasks of the step in ONE launch, ordered for the L2: the grid is one-dimensional and CTAs are
 // dispatched in the order (y-slab, z-plane, task, tile), so the 38 basis / slope numbers of a plane are fetched from
@@ -1419,6 +1421,7 @@ __global__ void __launch_bounds__(FluxCfg<D>::THREADS, FluxCfg<D>::MINB)
 struct RiemannPlan {
   int ntx, nrows, rows;  // x tiles; rows of faces / edges (ny+1); rows per y-slab (a multiple of 12)
   unsigned per_task4, per_task3, per_plane, per_slab;
+  int merged;  // 1: x-faces + y-faces + z-edges of a tile as ONE work item on shared boxes (mhd_pgroup.inc): 4 items per plane, not 6
 };
 struct RiemannMaps {
   CUtensorMap fluxB[3], emfB[3], emfD[3];
@@ -1427,7 +1430,7 @@ struct RiemannMaps {
 // components = 41 KB like the y-edge boxes), so that every task fits five CTAs per SM
 struct EmfXCfg3 : TileCfg<3, 1, 1, 1, 1, 19, 5> {};
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
-constexpr int RALL_SMEM = cmax(cmax(EmfXCfg3::SMEM_BYTES, EmfCfg<1>::SMEM_BYTES), cmax(EmfCfg<2>::SMEM_BYTES, FluxCfg<2>::SMEM_BYTES));
+constexpr int RALL_SMEM = cmax(cmax(cmax(EmfXCfg3::SMEM_BYTES, EmfCfg<1>::SMEM_BYTES), cmax(EmfCfg<2>::SMEM_BYTES, FluxCfg<2>::SMEM_BYTES)), PGroup::SMEM_BYTES);
 static_assert(EmfCfg<1>::THREADS == 128 && EmfCfg<2>::THREADS == 128 && FluxCfg<0>::THREADS == 128 && FluxCfg<1>::THREADS == 128 &&
                 FluxCfg<2>::THREADS == 128 && EmfCfg<1>::TY == 4 && EmfCfg<2>::TY == 4 && FluxCfg<0>::TY == 4 && FluxCfg<1>::TY == 4 &&
                 FluxCfg<2>::TY == 4 && EmfXCfg3::THREADS == 96,
@@ -1444,7 +1447,10 @@ __global__ void __launch_bounds__(128, 5)
   const unsigned slab = r / pl.per_slab; r -= slab * pl.per_slab;
   const unsigned plane = r / pl.per_plane; r -= plane * pl.per_plane;
   unsigned task, th;  // th = tile height
-  if (r < 5u * pl.per_task4) { task = r / pl.per_task4; r -= task * pl.per_task4; th = 4; }
+  if (pl.merged) {  // items of a plane: plane group (task 6), z-faces (3), y-edges (4), x-edges (5)
+    if (r < 3u * pl.per_task4) { const unsigned t = r / pl.per_task4; r -= t * pl.per_task4; task = t == 0 ? 6u : 2u + t; th = 4; }
+    else { task = 5; r -= 3u * pl.per_task4; th = 3; }
+  } else if (r < 5u * pl.per_task4) { task = r / pl.per_task4; r -= task * pl.per_task4; th = 4; }
   else { task = 5; r -= 5u * pl.per_task4; th = 3; }
   const unsigned ty = r / (unsigned)pl.ntx, bx = r - ty * (unsigned)pl.ntx;
   const int jrow = (int)(slab * pl.rows + ty * th);  // first row of the tile
@@ -1458,6 +1464,7 @@ __global__ void __launch_bounds__(128, 5)
     case 2: if (!top) emf_tile_body<2>(g, &maps.emfB[2], &maps.emfD[2], EMF, sm, &bar, i0, j0, k0); break;
     case 3: if (!last_row) flux_tile_body<2, RS>(g, &maps.fluxB[2], F2, sm, &bar, i0, j0, k0); break;
     case 4: if (!last_row) emf_tile_body<1>(g, &maps.emfB[1], &maps.emfD[1], EMF, sm, &bar, i0, j0, k0); break;
+    case 6: if (!top) pgroup_tile_body<RS>(g, &maps.fluxB[1], &maps.emfD[2], F0, F1, EMF, sm, &bar, i0, j0, k0, last_row ? 2 : 3); break;
     default: emf_tile_body<0, EmfXCfg3>(g, &maps.emfB[0], &maps.emfD[0], EMF, sm, &bar, i0, j0, k0); break;
   }
 }
@@ -2284,6 +2291,39 @@ static void l_emf(const GridParams &g, int e, const double *BASIS, const double 
   else if (e == 1) launch_emf<1>(g, BASIS, DBF, EMF, (const TmaCtx *)tma, s);
   else launch_emf<2>(g, BASIS, DBF, EMF, (const TmaCtx *)tma, s);
 }
+// x-faces + y-faces + z-edges of every plane in one launch on shared tiles (mhd_pgroup.inc); returns -1 when unavailable
+// (no TMA context, PPK_PGROUP=0): the caller then launches the three kernels one by one.
+static int l_plane_group(const GridParams &g, const double *BASIS, const double *DBF, double *F0, double *F1, double *EMF,
+                         const void *tma_, cudaStream_t s) {
+  const TmaCtx *tma = (const TmaCtx *)tma_;
+  static const int on = getenv("PPK_PGROUP") ? atoi(getenv("PPK_PGROUP")) : 1;
+  if (!tma || !on) return -1;
+  const bool wrap = g.wrap_x && g.nx % 32 == 0;
+  int ntx = g.nx / 32;
+  if (!wrap && (g.nx + 1 - ntx * 32) < 8 && ntx > 1) --ntx;  // keep the left-over rows of the plain kernels coalesced
+  if (ntx < 1) return -1;
+  const int done = ntx * 32;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    if (cudaFuncSetAttribute(k_plane_group<RIEMANN_HLLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGroup::SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_plane_group<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGroup::SMEM_BYTES) != cudaSuccess)
+      return -1;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
+  dim3 grid(ntx, cdiv(g.ny + 1, PGroup::TY), g.nz);
+  if (g.riemann == RIEMANN_HLLD) k_plane_group<RIEMANN_HLLD><<<grid, PGroup::THREADS, PGroup::SMEM_BYTES, s>>>(g, tma->fluxB[1], tma->emfD[2], F0, F1, EMF);
+  else k_plane_group<-1><<<grid, PGroup::THREADS, PGroup::SMEM_BYTES, s>>>(g, tma->fluxB[1], tma->emfD[2], F0, F1, EMF);
+  if (!wrap) {
+    const int bs = 128;
+    if (done < g.nx + 1) k_flux<0, 5><<<dim3(cdiv((long long)(g.nx + 1 - done) * g.ny, bs), g.nz), bs, 0, s>>>(g, BASIS, F0, done, g.nx + 1 - done);
+    if (done < g.nx) k_flux<1, 5><<<dim3(cdiv((long long)(g.nx - done) * (g.ny + 1), bs), g.nz), bs, 0, s>>>(g, BASIS, F1, done, g.nx - done);
+    if (done < g.nx + 1) k_emf<2, 5><<<dim3(cdiv((long long)(g.nx + 1 - done) * (g.ny + 1), bs), g.nz), bs, 0, s>>>(g, BASIS, DBF, EMF, done, g.nx + 1 - done);
+  }
+  return 0;
+}
+
 // The six flux / EMF tasks in one L2-ordered launch (k_riemann_all); returns -1 when the TMA context is missing
 // (the caller then launches the tasks one by one). Columns beyond the last full 32-wide tile go through the plain
 // kernels, task by task, exactly like launch_flux / launch_emf.
@@ -2310,7 +2350,12 @@ static int l_riemann_all(const GridParams &g, const double *BASIS, const double 
   const unsigned nslab = cdiv(pl.nrows, rows);
   pl.per_task4 = (unsigned)ntx * (unsigned)(rows / 4);
   pl.per_task3 = (unsigned)ntx * (unsigned)(rows / 3);
-  pl.per_plane = 5u * pl.per_task4 + pl.per_task3;
+  // persistent CTAs (mhd_rpers.inc, PPK_RALL_PERS=1) enumerate the six tasks one by one; the single-shot kernel merges the
+  // three plane-k tasks of a tile into one work item (PPK_RALL_MERGE=0: six items, for A/B)
+  static const int pers_env = getenv("PPK_RALL_PERS") ? atoi(getenv("PPK_RALL_PERS")) : 0;
+  static const int merge_env = getenv("PPK_RALL_MERGE") ? atoi(getenv("PPK_RALL_MERGE")) : 1;
+  pl.merged = (!pers_env && merge_env) ? 1 : 0;
+  pl.per_plane = (pl.merged ? 3u : 5u) * pl.per_task4 + pl.per_task3;
   pl.per_slab = (unsigned)(g.nz + 1) * pl.per_plane;
   const unsigned long long total = (unsigned long long)nslab * pl.per_slab;
   if (total > 0x7FFFFFFFull || ntx < 1) return -1;
@@ -2426,7 +2471,7 @@ static const KernelTable table = {
 #endif
   l_boundary, l_prim_dt, l_finalize_dt, l_advance_time, l_elec_dbf, l_trace, l_flux, l_emf, l_update, l_diagnostics, l_fastmath_selftest, l_consume, l_tma_create, l_tma_destroy, l_hydro, l_update_ct, l_wrap_x_column,
   l2_boundary, l2_prim_dt, l2_trace, l2_flux_emf, l2_update,
-  l_dt_only, l_prod_create, l_prod_destroy, l_producer, l_riemann_all, l_face_copy,
+  l_dt_only, l_prod_create, l_prod_destroy, l_producer, l_riemann_all, l_face_copy, l_plane_group,
 };
 
 }  // namespace PPK_NS
