@@ -88,7 +88,7 @@ int load_nccl() {
 const char *const kKernelNames[KK_COUNT] = {"boundary", "prim_dt", "finalize_dt", "elec_dbf", "trace",
                                             "flux_x", "flux_y", "flux_z", "emf_z", "emf_y", "emf_x",
                                             "update", "diagnostics", "halo_exchange", "consume", "hydro", "update_ct",
-                                            "dt_only", "producer", "riemann_all", "flux_xy_emf_z"};
+                                            "dt_only", "producer", "riemann_all", "flux_xy_emf_z", "flux_z_emf_y"};
 
 }  // namespace
 
@@ -407,8 +407,13 @@ int enqueue_step(ppk_mhd3d *h) {
         { Scope sc(h, KK_FLUX_Y, s); h->kt->flux(g, 1, h->BASIS, h->F[1], h->tma, s); }
         { Scope sc(h, KK_EMF_Z, s); h->kt->emf(g, 2, h->BASIS, h->DBF, h->EMF, h->tma, s); }
       }
-      { Scope sc(h, KK_FLUX_Z, s); h->kt->flux(g, 2, h->BASIS, h->F[2], h->tma, s); }
-      { Scope sc(h, KK_EMF_Y, s); h->kt->emf(g, 1, h->BASIS, h->DBF, h->EMF, h->tma, s); }
+      bool grouped_xz = false;  // z-faces and y-edges read row j only: one launch on shared x-z tiles where available
+      { Scope sc(h, KK_XZ_GROUP, s); grouped_xz = h->kt->xz_group(g, h->BASIS, h->DBF, h->F[2], h->EMF, h->tma, s) == 0; }
+      if (!grouped_xz) {
+        h->launches -= 1;
+        { Scope sc(h, KK_FLUX_Z, s); h->kt->flux(g, 2, h->BASIS, h->F[2], h->tma, s); }
+        { Scope sc(h, KK_EMF_Y, s); h->kt->emf(g, 1, h->BASIS, h->DBF, h->EMF, h->tma, s); }
+      }
       { Scope sc(h, KK_EMF_X, s); h->kt->emf(g, 0, h->BASIS, h->DBF, h->EMF, h->tma, s); }
     }
     const bool exch = h->exch_lo || h->exch_hi;

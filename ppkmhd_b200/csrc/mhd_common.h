@@ -52,7 +52,7 @@ struct StepState {
 // kernel kinds, for the per-kernel timers
 enum KernelKind {
   KK_BOUNDARY = 0, KK_PRIM_DT, KK_FINALIZE_DT, KK_ELEC_DBF, KK_TRACE,
-  KK_FLUX_X, KK_FLUX_Y, KK_FLUX_Z, KK_EMF_Z, KK_EMF_Y, KK_EMF_X, KK_UPDATE, KK_DIAG, KK_HALO, KK_CONSUME, KK_HYDRO, KK_UPDATE_CT, KK_DT_ONLY, KK_PRODUCER, KK_RIEMANN_ALL, KK_PLANE_GROUP, KK_COUNT
+  KK_FLUX_X, KK_FLUX_Y, KK_FLUX_Z, KK_EMF_Z, KK_EMF_Y, KK_EMF_X, KK_UPDATE, KK_DIAG, KK_HALO, KK_CONSUME, KK_HYDRO, KK_UPDATE_CT, KK_DT_ONLY, KK_PRODUCER, KK_RIEMANN_ALL, KK_PLANE_GROUP, KK_XZ_GROUP, KK_COUNT
 };
 
 // Launchers exported by each arithmetic build (mhd_kernels.cu compiled twice).
@@ -109,6 +109,10 @@ struct KernelTable {
   // returns -1 when unavailable (the caller launches flux(0), flux(1), emf(2) instead)
   int (*plane_group)(const GridParams &g, const double *BASIS, const double *DBF, double *F0, double *F1, double *EMF,
                      const void *tma, cudaStream_t s);
+  // z-faces + y-edges (the two Riemann tasks that read row j only) in one launch on shared x-z TMA tiles; returns -1 when
+  // unavailable (the caller launches flux(2), emf(1) instead)
+  int (*xz_group)(const GridParams &g, const double *BASIS, const double *DBF, double *F2, double *EMF, const void *tma,
+                  cudaStream_t s);
 };
 
 const KernelTable *kernel_table_exact();

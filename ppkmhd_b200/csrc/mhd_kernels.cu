@@ -1408,6 +1408,7 @@ __global__ void __launch_bounds__(FluxCfg<D>::THREADS, FluxCfg<D>::MINB)
 }
 
 #include "mhd_pgroup.inc"
+#include "mhd_xzgroup.inc"
 
 // ---------------------------------------------------------------------------------------------
 // All six Riemann tasks of the step in ONE launch, ordered for the L2: the grid is one-dimensional and CTAs are
@@ -2073,6 +2074,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 struct TmaCtx {
   CUtensorMap emfB[3], emfD[3], fluxB[3];
+  CUtensorMap xzB, xzD;  // 34 x 1 x 5 boxes of the basis / the face-field slopes (mhd_xzgroup.inc)
+  bool xz_ok = false;
   RiemannMaps rall;  // the same nine maps, as the single kernel parameter of k_riemann_all
   unsigned *counter = nullptr;  // work-item counter of k_riemann_pers (device memory, zeroed before every launch)
   int sms = 148;
@@ -2135,6 +2138,12 @@ static void *l_tma_create(const GridParams &g, const double *BASIS, const double
   ok = ok && cudaFuncSetAttribute(k_riemann_all<RIEMANN_HLLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, RALL_SMEM) == cudaSuccess &&
        cudaFuncSetAttribute(k_riemann_all<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, RALL_SMEM) == cudaSuccess;
   if (!ok) { delete c; return nullptr; }
+  c->xz_ok = encode_map(enc, &c->xzB, g, BASIS, NBASIS, XZGroup::XB, 1, XZGroup::ZB) &&
+             encode_map(enc, &c->xzD, g, DBF, NDBF, XZGroup::XB, 1, XZGroup::ZB) &&
+             cudaFuncSetAttribute(k_xz_group<RIEMANN_HLLD, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, XZGroup::SMEM_BYTES) == cudaSuccess &&
+             cudaFuncSetAttribute(k_xz_group<RIEMANN_HLLD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, XZGroup::SMEM_BYTES) == cudaSuccess &&
+             cudaFuncSetAttribute(k_xz_group<RIEMANN_HLLD, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, XZGroup::SMEM_BYTES) == cudaSuccess &&
+             cudaFuncSetAttribute(k_xz_group<-1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, XZGroup::SMEM_BYTES) == cudaSuccess;
   for (int d = 0; d < 3; ++d) { c->rall.fluxB[d] = c->fluxB[d]; c->rall.emfB[d] = c->emfB[d]; c->rall.emfD[d] = c->emfD[d]; }
   if (!encode_cfg<EmfXCfg3>(enc, &c->rall.emfB[0], g, BASIS, NBASIS) || !encode_cfg<EmfXCfg3>(enc, &c->rall.emfD[0], g, DBF, NDBF)) {
     delete c;
@@ -2324,6 +2333,46 @@ static int l_plane_group(const GridParams &g, const double *BASIS, const double 
   return 0;
 }
 
+// z-faces + y-edges of every row in one launch on shared x-z tiles (mhd_xzgroup.inc); returns -1 when unavailable (no TMA
+// context, PPK_XZGROUP=0): the caller then launches flux(2) and emf(1).
+#ifndef PPK_XZGROUP_DEFAULT
+#  define PPK_XZGROUP_DEFAULT 0
+#endif
+static int l_xz_group(const GridParams &g, const double *BASIS, const double *DBF, double *F2, double *EMF, const void *tma_,
+                      cudaStream_t s) {
+  const TmaCtx *tma = (const TmaCtx *)tma_;
+  static const int on = getenv("PPK_XZGROUP") ? atoi(getenv("PPK_XZGROUP")) : PPK_XZGROUP_DEFAULT;
+  if (!tma || !on || !tma->xz_ok) return -1;
+  const bool wrap = g.wrap_x && g.nx % 32 == 0;
+  int ntx = g.nx / 32;
+  if (!wrap && (g.nx + 1 - ntx * 32) < 8 && ntx > 1) --ntx;  // keep the left-over rows of the plain kernels coalesced
+  if (ntx < 1) return -1;
+  const int done = ntx * 32;
+  const int ntz = (int)cdiv(g.nz + 1, XZGroup::TZ);
+  // y-slabs: the four planes a z-tile of a slab reads (23 streams each) pass through the L2 between two uses of its top plane
+  static const int slab_mb = getenv("PPK_XZ_SLAB_MB") ? atoi(getenv("PPK_XZ_SLAB_MB")) : 48;
+  long long rows = ((long long)slab_mb << 20) / ((long long)XZGroup::TZ * XZGroup::NSLOT * g.isize * 8);
+  rows &= ~7LL;
+  if (rows < 8) rows = 8;
+  if (rows >= g.ny - 8) rows = g.ny;  // no sliver slab
+  if (rows * ntz > 65535) rows = 65535 / ntz;  // grid.y limit
+  if (rows < 1) return -1;
+  const int yslab = (int)rows;
+  dim3 grid(ntx, (unsigned)(yslab * ntz), cdiv(g.ny, yslab));
+  const unsigned ymagic = yslab > 1 ? 0xFFFFFFFFu / (unsigned)yslab + 1u : 0u;
+  static const int minb = getenv("PPK_XZ_MINB") ? atoi(getenv("PPK_XZ_MINB")) : 5;  // register target (A/B): 4 = 128, 5 = 96, 6 = 80 registers
+  if (g.riemann != RIEMANN_HLLD) k_xz_group<-1, 5><<<grid, XZGroup::THREADS, XZGroup::SMEM_BYTES, s>>>(g, tma->xzB, tma->xzD, F2, EMF, yslab, ymagic);
+  else if (minb == 4) k_xz_group<RIEMANN_HLLD, 4><<<grid, XZGroup::THREADS, XZGroup::SMEM_BYTES, s>>>(g, tma->xzB, tma->xzD, F2, EMF, yslab, ymagic);
+  else if (minb == 6) k_xz_group<RIEMANN_HLLD, 6><<<grid, XZGroup::THREADS, XZGroup::SMEM_BYTES, s>>>(g, tma->xzB, tma->xzD, F2, EMF, yslab, ymagic);
+  else k_xz_group<RIEMANN_HLLD, 5><<<grid, XZGroup::THREADS, XZGroup::SMEM_BYTES, s>>>(g, tma->xzB, tma->xzD, F2, EMF, yslab, ymagic);
+  if (!wrap) {
+    const int bs = 128;
+    if (done < g.nx) k_flux<2, 5><<<dim3(cdiv((long long)(g.nx - done) * g.ny, bs), g.nz + 1), bs, 0, s>>>(g, BASIS, F2, done, g.nx - done);
+    if (done < g.nx + 1) k_emf<1, 5><<<dim3(cdiv((long long)(g.nx + 1 - done) * g.ny, bs), g.nz + 1), bs, 0, s>>>(g, BASIS, DBF, EMF, done, g.nx + 1 - done);
+  }
+  return 0;
+}
+
 // The six flux / EMF tasks in one L2-ordered launch (k_riemann_all); returns -1 when the TMA context is missing
 // (the caller then launches the tasks one by one). Columns beyond the last full 32-wide tile go through the plain
 // kernels, task by task, exactly like launch_flux / launch_emf.
@@ -2471,7 +2520,7 @@ static const KernelTable table = {
 #endif
   l_boundary, l_prim_dt, l_finalize_dt, l_advance_time, l_elec_dbf, l_trace, l_flux, l_emf, l_update, l_diagnostics, l_fastmath_selftest, l_consume, l_tma_create, l_tma_destroy, l_hydro, l_update_ct, l_wrap_x_column,
   l2_boundary, l2_prim_dt, l2_trace, l2_flux_emf, l2_update,
-  l_dt_only, l_prod_create, l_prod_destroy, l_producer, l_riemann_all, l_face_copy, l_plane_group,
+  l_dt_only, l_prod_create, l_prod_destroy, l_producer, l_riemann_all, l_face_copy, l_plane_group, l_xz_group,
 };
 
 }  // namespace PPK_NS
