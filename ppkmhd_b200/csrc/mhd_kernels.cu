@@ -2341,7 +2341,9 @@ static int l_plane_group(const GridParams &g, const double *BASIS, const double 
 static int l_xz_group(const GridParams &g, const double *BASIS, const double *DBF, double *F2, double *EMF, const void *tma_,
                       cudaStream_t s) {
   const TmaCtx *tma = (const TmaCtx *)tma_;
-  static const int on = getenv("PPK_XZGROUP") ? atoi(getenv("PPK_XZGROUP")) : PPK_XZGROUP_DEFAULT;
+  // (the three knobs of this launcher are read at every launch, so that one process can A/B them: profiles/r2/ab_xz.py)
+  const char *e_on = getenv("PPK_XZGROUP"), *e_slab = getenv("PPK_XZ_SLAB_MB"), *e_minb = getenv("PPK_XZ_MINB");
+  const int on = e_on ? atoi(e_on) : PPK_XZGROUP_DEFAULT;
   if (!tma || !on || !tma->xz_ok) return -1;
   const bool wrap = g.wrap_x && g.nx % 32 == 0;
   int ntx = g.nx / 32;
@@ -2350,7 +2352,7 @@ static int l_xz_group(const GridParams &g, const double *BASIS, const double *DB
   const int done = ntx * 32;
   const int ntz = (int)cdiv(g.nz + 1, XZGroup::TZ);
   // y-slabs: the four planes a z-tile of a slab reads (23 streams each) pass through the L2 between two uses of its top plane
-  static const int slab_mb = getenv("PPK_XZ_SLAB_MB") ? atoi(getenv("PPK_XZ_SLAB_MB")) : 48;
+  const int slab_mb = e_slab && atoi(e_slab) > 0 ? atoi(e_slab) : 48;
   long long rows = ((long long)slab_mb << 20) / ((long long)XZGroup::TZ * XZGroup::NSLOT * g.isize * 8);
   rows &= ~7LL;
   if (rows < 8) rows = 8;
@@ -2360,7 +2362,7 @@ static int l_xz_group(const GridParams &g, const double *BASIS, const double *DB
   const int yslab = (int)rows;
   dim3 grid(ntx, (unsigned)(yslab * ntz), cdiv(g.ny, yslab));
   const unsigned ymagic = yslab > 1 ? 0xFFFFFFFFu / (unsigned)yslab + 1u : 0u;
-  static const int minb = getenv("PPK_XZ_MINB") ? atoi(getenv("PPK_XZ_MINB")) : 5;  // register target (A/B): 4 = 128, 5 = 96, 6 = 80 registers
+  const int minb = e_minb ? atoi(e_minb) : 5;  // register target (A/B): 4 = 128, 5 = 96, 6 = 80 registers
   if (g.riemann != RIEMANN_HLLD) k_xz_group<-1, 5><<<grid, XZGroup::THREADS, XZGroup::SMEM_BYTES, s>>>(g, tma->xzB, tma->xzD, F2, EMF, yslab, ymagic);
   else if (minb == 4) k_xz_group<RIEMANN_HLLD, 4><<<grid, XZGroup::THREADS, XZGroup::SMEM_BYTES, s>>>(g, tma->xzB, tma->xzD, F2, EMF, yslab, ymagic);
   else if (minb == 6) k_xz_group<RIEMANN_HLLD, 6><<<grid, XZGroup::THREADS, XZGroup::SMEM_BYTES, s>>>(g, tma->xzB, tma->xzD, F2, EMF, yslab, ymagic);
