@@ -2302,6 +2302,9 @@ static void l_emf(const GridParams &g, int e, const double *BASIS, const double 
 }
 // x-faces + y-faces + z-edges of every plane in one launch on shared tiles (mhd_pgroup.inc); returns -1 when unavailable
 // (no TMA context, PPK_PGROUP=0): the caller then launches the three kernels one by one.
+#ifndef PPK_PGROUP_MINB_DEFAULT
+#  define PPK_PGROUP_MINB_DEFAULT 5
+#endif
 static int l_plane_group(const GridParams &g, const double *BASIS, const double *DBF, double *F0, double *F1, double *EMF,
                          const void *tma_, cudaStream_t s) {
   const TmaCtx *tma = (const TmaCtx *)tma_;
@@ -2316,14 +2319,19 @@ static int l_plane_group(const GridParams &g, const double *BASIS, const double 
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-    if (cudaFuncSetAttribute(k_plane_group<RIEMANN_HLLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGroup::SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_plane_group<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGroup::SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_plane_group<RIEMANN_HLLD, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGroup::SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_plane_group<RIEMANN_HLLD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGroup::SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_plane_group<-1, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, PGroup::SMEM_BYTES) != cudaSuccess)
       return -1;
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   dim3 grid(ntx, cdiv(g.ny + 1, PGroup::TY), g.nz);
-  if (g.riemann == RIEMANN_HLLD) k_plane_group<RIEMANN_HLLD><<<grid, PGroup::THREADS, PGroup::SMEM_BYTES, s>>>(g, tma->fluxB[1], tma->emfD[2], F0, F1, EMF);
-  else k_plane_group<-1><<<grid, PGroup::THREADS, PGroup::SMEM_BYTES, s>>>(g, tma->fluxB[1], tma->emfD[2], F0, F1, EMF);
+  // register target (read at every launch, A/B): 5 CTAs per SM at 96 registers (124 B of spills) or 4 at 128 (none)
+  const char *e_minb = getenv("PPK_PGROUP_MINB");
+  const int minb = e_minb ? atoi(e_minb) : PPK_PGROUP_MINB_DEFAULT;
+  if (g.riemann != RIEMANN_HLLD) k_plane_group<-1, 5><<<grid, PGroup::THREADS, PGroup::SMEM_BYTES, s>>>(g, tma->fluxB[1], tma->emfD[2], F0, F1, EMF);
+  else if (minb == 4) k_plane_group<RIEMANN_HLLD, 4><<<grid, PGroup::THREADS, PGroup::SMEM_BYTES, s>>>(g, tma->fluxB[1], tma->emfD[2], F0, F1, EMF);
+  else k_plane_group<RIEMANN_HLLD, 5><<<grid, PGroup::THREADS, PGroup::SMEM_BYTES, s>>>(g, tma->fluxB[1], tma->emfD[2], F0, F1, EMF);
   if (!wrap) {
     const int bs = 128;
     if (done < g.nx + 1) k_flux<0, 5><<<dim3(cdiv((long long)(g.nx + 1 - done) * g.ny, bs), g.nz), bs, 0, s>>>(g, BASIS, F0, done, g.nx + 1 - done);
@@ -2336,7 +2344,7 @@ static int l_plane_group(const GridParams &g, const double *BASIS, const double 
 // z-faces + y-edges of every row in one launch on shared x-z tiles (mhd_xzgroup.inc); returns -1 when unavailable (no TMA
 // context, PPK_XZGROUP=0): the caller then launches flux(2) and emf(1).
 #ifndef PPK_XZGROUP_DEFAULT
-#  define PPK_XZGROUP_DEFAULT 0
+#  define PPK_XZGROUP_DEFAULT 1
 #endif
 static int l_xz_group(const GridParams &g, const double *BASIS, const double *DBF, double *F2, double *EMF, const void *tma_,
                       cudaStream_t s) {
@@ -2362,11 +2370,11 @@ static int l_xz_group(const GridParams &g, const double *BASIS, const double *DB
   const int yslab = (int)rows;
   dim3 grid(ntx, (unsigned)(yslab * ntz), cdiv(g.ny, yslab));
   const unsigned ymagic = yslab > 1 ? 0xFFFFFFFFu / (unsigned)yslab + 1u : 0u;
-  const int minb = e_minb ? atoi(e_minb) : 5;  // register target (A/B): 4 = 128, 5 = 96, 6 = 80 registers
+  const int minb = e_minb ? atoi(e_minb) : 4;  // register target: 4 CTAs per SM at 128 registers without spills (512^3: 8.67 ms) beat 5 at 96 (9.3 ms) and 6 at 80 (11.5 ms)
   if (g.riemann != RIEMANN_HLLD) k_xz_group<-1, 5><<<grid, XZGroup::THREADS, XZGroup::SMEM_BYTES, s>>>(g, tma->xzB, tma->xzD, F2, EMF, yslab, ymagic);
-  else if (minb == 4) k_xz_group<RIEMANN_HLLD, 4><<<grid, XZGroup::THREADS, XZGroup::SMEM_BYTES, s>>>(g, tma->xzB, tma->xzD, F2, EMF, yslab, ymagic);
+  else if (minb == 5) k_xz_group<RIEMANN_HLLD, 5><<<grid, XZGroup::THREADS, XZGroup::SMEM_BYTES, s>>>(g, tma->xzB, tma->xzD, F2, EMF, yslab, ymagic);
   else if (minb == 6) k_xz_group<RIEMANN_HLLD, 6><<<grid, XZGroup::THREADS, XZGroup::SMEM_BYTES, s>>>(g, tma->xzB, tma->xzD, F2, EMF, yslab, ymagic);
-  else k_xz_group<RIEMANN_HLLD, 5><<<grid, XZGroup::THREADS, XZGroup::SMEM_BYTES, s>>>(g, tma->xzB, tma->xzD, F2, EMF, yslab, ymagic);
+  else k_xz_group<RIEMANN_HLLD, 4><<<grid, XZGroup::THREADS, XZGroup::SMEM_BYTES, s>>>(g, tma->xzB, tma->xzD, F2, EMF, yslab, ymagic);
   if (!wrap) {
     const int bs = 128;
     if (done < g.nx) k_flux<2, 5><<<dim3(cdiv((long long)(g.nx - done) * g.ny, bs), g.nz + 1), bs, 0, s>>>(g, BASIS, F2, done, g.nx - done);

@@ -1,4 +1,4 @@
-"""In-process A/B of the x-z group kernel (PPK_XZGROUP / PPK_XZ_MINB / PPK_XZ_SLAB_MB are read at every launch): Orszag-Tang kt=1
+"""In-process A/B of launcher knobs that are read at every launch (PPK_XZGROUP / PPK_XZ_MINB / PPK_XZ_SLAB_MB / PPK_PGROUP_MINB): Orszag-Tang kt=1
 at n^3 through the C ABI, fast build, default schedule; per setting 3 warm-up + K timed steps, CUDA events around every launch."""
 import json
 import os
@@ -19,12 +19,19 @@ s.upload(ppk.init_condition_from_ini(ini))
 s.set_time(0.0, t_end, 0)
 s.run(5)
 s.synchronize()
-settings = [{"PPK_XZGROUP": "0"}, {"PPK_XZGROUP": "1"}, {"PPK_XZGROUP": "0"}, {"PPK_XZGROUP": "1"},
-            {"PPK_XZGROUP": "1", "PPK_XZ_MINB": "4"}, {"PPK_XZGROUP": "1", "PPK_XZ_MINB": "6"},
-            {"PPK_XZGROUP": "1", "PPK_XZ_SLAB_MB": "24"}, {"PPK_XZGROUP": "1", "PPK_XZ_SLAB_MB": "1000"}]
+SETS = {
+    # run30: the x-z group against the two kernels it replaces, its register targets and y-slab sizes
+    "xz": [{"PPK_XZGROUP": "0"}, {"PPK_XZGROUP": "1", "PPK_XZ_MINB": "5"}, {"PPK_XZGROUP": "0"}, {"PPK_XZGROUP": "1", "PPK_XZ_MINB": "5"},
+           {"PPK_XZGROUP": "1", "PPK_XZ_MINB": "4"}, {"PPK_XZGROUP": "1", "PPK_XZ_MINB": "6"},
+           {"PPK_XZGROUP": "1", "PPK_XZ_MINB": "5", "PPK_XZ_SLAB_MB": "24"}, {"PPK_XZGROUP": "1", "PPK_XZ_MINB": "5", "PPK_XZ_SLAB_MB": "1000"}],
+    # run31: register target of the plane group (5 CTAs per SM at 96 registers with spills | 4 at 128 without)
+    "pg": [{"PPK_PGROUP_MINB": "5"}, {"PPK_PGROUP_MINB": "4"}, {"PPK_PGROUP_MINB": "5"}, {"PPK_PGROUP_MINB": "4"}],
+}
+settings = SETS[sys.argv[3] if len(sys.argv) > 3 else "xz"]
+KNOBS = sorted({k for v in SETS.values() for st in v for k in st})
 out = []
 for st in settings:
-    for k in ("PPK_XZGROUP", "PPK_XZ_MINB", "PPK_XZ_SLAB_MB"):
+    for k in KNOBS:
         os.environ.pop(k, None)
     os.environ.update(st)
     s.run(3)

@@ -3,7 +3,7 @@
 instructions.  Usage: python profiles/r2/counters.py gpurun_out/r2_counters_<n>_<pipeline>.csv <n> <pipeline> <steps>"""
 import csv, json, os, re, sys
 
-KEY = [(r"k_plane_group", "flux_xy_emf_z"), (r"k_trace_tma", "trace"), (r"k_producer", "producer"), (r"k_riemann_all|k_riemann_pers", "riemann_all"), (r"k_prim_dt<0>", "dt_only"),
+KEY = [(r"k_plane_group", "flux_xy_emf_z"), (r"k_xz_group", "flux_z_emf_y"), (r"k_trace_tma", "trace"), (r"k_producer", "producer"), (r"k_riemann_all|k_riemann_pers", "riemann_all"), (r"k_prim_dt<0>", "dt_only"),
        (r"k_prim_dt", "prim_dt"), (r"k_elec_dbf", "elec_dbf"), (r"k_trace", "trace"),
        (r"k_flux(_tma)?<0", "flux_x"), (r"k_flux(_tma)?<1", "flux_y"), (r"k_flux(_tma)?<2", "flux_z"),
        (r"k_emf(_tma)?<2", "emf_z"), (r"k_emf(_tma)?<1", "emf_y"), (r"k_emf(_tma)?<0", "emf_x"),
