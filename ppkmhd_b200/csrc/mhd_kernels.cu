@@ -2303,7 +2303,7 @@ static void l_emf(const GridParams &g, int e, const double *BASIS, const double 
 // x-faces + y-faces + z-edges of every plane in one launch on shared tiles (mhd_pgroup.inc); returns -1 when unavailable
 // (no TMA context, PPK_PGROUP=0): the caller then launches the three kernels one by one.
 #ifndef PPK_PGROUP_MINB_DEFAULT
-#  define PPK_PGROUP_MINB_DEFAULT 5
+#  define PPK_PGROUP_MINB_DEFAULT 4
 #endif
 static int l_plane_group(const GridParams &g, const double *BASIS, const double *DBF, double *F0, double *F1, double *EMF,
                          const void *tma_, cudaStream_t s) {
@@ -2326,7 +2326,8 @@ static int l_plane_group(const GridParams &g, const double *BASIS, const double 
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   dim3 grid(ntx, cdiv(g.ny + 1, PGroup::TY), g.nz);
-  // register target (read at every launch, A/B): 5 CTAs per SM at 96 registers (124 B of spills) or 4 at 128 (none)
+  // register target (read at every launch, A/B): 4 CTAs per SM at 128 registers without spills (512^3: 11.4 ms) beat 5 at 96
+  // registers with 124 B of spills (12.4 ms)
   const char *e_minb = getenv("PPK_PGROUP_MINB");
   const int minb = e_minb ? atoi(e_minb) : PPK_PGROUP_MINB_DEFAULT;
   if (g.riemann != RIEMANN_HLLD) k_plane_group<-1, 5><<<grid, PGroup::THREADS, PGroup::SMEM_BYTES, s>>>(g, tma->fluxB[1], tma->emfD[2], F0, F1, EMF);
