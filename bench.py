@@ -462,9 +462,9 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": dom_ms,
                 "whole_step": {"achieved": step_gbs, "frac": step_gbs / pk["hbm_gbs"]},
                 "fp64_pipe": fp64, "per_kernel_measured_dram": per_kernel_dram,
-                "note": "128 algorithmic B per cell-update (read U^n, write U^n+1). The step executes ~2.9k FP64-pipe and ~6k "
-                        "instructions per cell-update: FP64 pipe and instruction issue bound it near 5 Gcell/s = 10% of the "
-                        "HBM roofline; see DESIGN.md"}
+                "note": "128 algorithmic B per cell-update (read U^n, write U^n+1). The step executes ~2.45k FP64-pipe and ~5.7k "
+                        "instructions per cell-update (fp64_pipe.*): the FP64 pipe alone caps it at 6.9 Gcell/s = 13.6% of the HBM "
+                        "roofline, instruction issue at 6.5 Gcell/s; see DESIGN.md 4.1"}
 
     nbytes = int(np.prod(p.shape)) * 8
     # ---- e2e leg: host buffers through the C ABI, H2D + step + D2H every step ------------------

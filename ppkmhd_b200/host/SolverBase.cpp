@@ -69,6 +69,16 @@ void SolverBase::init_io() { m_io_reader_writer = std::make_shared<io::IO_ReadWr
 void SolverBase::save_data(DataArray3dHost &Uhost, int iStep, real_t time) {
   m_io_reader_writer->save_data(Uhost, iStep, time, "");
 }
+void SolverBase::save_data_debug(DataArray3dHost &Uhost, int iStep, real_t time, const std::string &debug_name) {
+  m_io_reader_writer->save_data(Uhost, iStep, time, debug_name);
+}
+void SolverBase::load_data(DataArray3dHost &Uhost, int &iStep, real_t &time) {
+  std::string why;
+  if (!m_io_reader_writer->load_data(Uhost, iStep, time, &why)) {  // a restart that cannot be honoured must not run something else
+    fprintf(stderr, "load_data: %s\n", why.c_str());
+    exit(EXIT_FAILURE);
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 SolverFactory &SolverFactory::Instance() {

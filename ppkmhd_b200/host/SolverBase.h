@@ -84,9 +84,19 @@ public:
   virtual void save_solution_impl();
   virtual int should_save_solution();   // SolverBase.cpp:265-290
   virtual void init_io();               // called by SolverFactory::create after construction
+  virtual void read_restart_file() {}   // an empty TODO in the reference too (SolverBase.cpp:255-260); restart = load_data below
+  // ghost fill of the solver's current array, all faces in the reference's order X -> Y -> Z. The GPU path fills a direction
+  // per launch, so the per-face make_boundary(Udata, faceId, mhd) of the reference (SolverBase.h:191-193) has no counterpart;
+  // the two whole-array entry points map onto the same call (the engine exchanges the faces a neighbour owns, fills the others)
   virtual void make_boundaries() {}
+  virtual void make_boundaries_serial() { make_boundaries(); }  // SolverBase.cpp:527-537
+  virtual void make_boundaries_mpi() { make_boundaries(); }     // SolverBase.cpp:610-693
 
-  void save_data(DataArray3dHost &Uhost, int iStep, real_t time);
+  void save_data(DataArray3dHost &Uhost, int iStep, real_t time);                                       // SolverBase.cpp:286-310
+  void save_data_debug(DataArray3dHost &Uhost, int iStep, real_t time, const std::string &debug_name);  // SolverBase.h:166-179
+  // restart: fills Uhost, iStep and time from [run] restart_filename (SolverBase.h:184-187 -> IO_ReadWrite::load_data);
+  // the reference has no error path here (HDF5 is a build-time option): without a usable libhdf5 this prints why and exits
+  void load_data(DataArray3dHost &Uhost, int &iStep, real_t &time);
 
 protected:
   std::shared_ptr<io::IO_ReadWrite> m_io_reader_writer;
