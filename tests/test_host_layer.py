@@ -224,3 +224,34 @@ def test_xdmf_wrapper_text_and_hdf5_error_path(tmp_path, monkeypatch):
         open(tmp_path / "r.ini", "w").write(ini.replace("[mesh]", "restart_enabled=true\nrestart_filename=ot3d_0000000.h5\n[mesh]"))
         r = subprocess.run([exe, "r.ini"], cwd=tmp_path, capture_output=True, text=True)
         assert r.returncode != 0 and ("restart_enabled" in r.stderr or "no CUDA device" in r.stderr), r.stderr[-500:]
+
+
+def test_solverbase_members_besides_the_time_loop(tmp_path):
+    """SolverBase members a reference-side caller may use besides the time loop (src/shared/SolverBase.h:137, 166-198):
+    save_data_debug writes outputPrefix_<debug_name>_%07d.vti next to save_data's file (IO_VTK.cpp:278-281), with the same
+    payload; make_boundaries_serial / _mpi reach the solver's ghost fill; read_restart_file is the reference's empty TODO;
+    load_data (restart) stops the program with the reason when it cannot be honoured. A C++ harness with a dummy solver
+    (tests/host_harness/solverbase_members.cpp), linked against the in-tree library; no GPU involved."""
+    import subprocess
+    from oracle import oracle as O
+
+    host = os.path.join(ROOT, "ppkmhd_b200", "host")
+    libdir = os.path.join(ROOT, "ppkmhd_b200", "lib")
+    exe = str(tmp_path / "harness")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O1", "-std=c++17", "-I", host, "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "host_harness", "solverbase_members.cpp"), "-L", libdir, "-lppkmhd_b200",
+                           f"-Wl,-rpath,{libdir}", "-o", exe])
+    ini = O.make_ini("orszag_tang", (10, 6, 4)).replace("outputPrefix=run", f"outputDir={tmp_path}\noutputPrefix=dbg")
+    open(tmp_path / "a.ini", "w").write(ini)
+    r = subprocess.run([exe, "a.ini", "debug"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0 and "fills=2" in r.stdout, r.stdout + r.stderr
+    plain, dbg = tmp_path / "dbg_0000003.vti", tmp_path / "dbg_afterBC_0000003.vti"
+    assert plain.exists() and dbg.exists()
+    assert plain.read_bytes() == dbg.read_bytes()
+    import ppkmhd_b200 as ppk
+    if not ppk.hdf5_available():
+        open(tmp_path / "r.ini", "w").write(ini.replace("[mesh]", "restart_enabled=true\nrestart_filename=dbg_0000003.h5\n[mesh]"))
+        r = subprocess.run([exe, "r.ini", "load"], cwd=tmp_path, capture_output=True, text=True)
+        assert r.returncode != 0 and "load_data:" in r.stderr and "returned" not in r.stdout, r.stdout + r.stderr
+
