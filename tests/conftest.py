@@ -17,6 +17,12 @@ def golden_cases():
     return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
 
 
+def slope_cases():
+    """3-D fixtures with slope_type=1 (minmod) and slope_type=0 (no hydro slopes), tests/golden_slope/make_golden_slope.py."""
+    d = os.path.join(ROOT, "tests", "golden_slope")
+    return sorted(f[:-4] for f in os.listdir(d) if f.endswith(".npz"))
+
+
 def init_only_cases():
     """Fixtures holding only the reference's step-0 state (problems the reference itself cannot step in 3-D: its rotor
     run produces NaN from the first step on, tests/golden/make_golden.py)."""

@@ -6,7 +6,7 @@ This is what pins the oracle ("parity pinned"): every later GPU-vs-oracle check 
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, golden_cases
+from conftest import GOLDEN, ROOT, golden_cases, slope_cases
 
 
 def load(case):
@@ -26,6 +26,22 @@ def test_oracle_matches_reference_bitwise(case, oracle_mod):
     assert np.array_equal(orc.interior(), g["stepN"]), "state after N steps differs from the reference"
     # the reference prints dt with 8 decimals and the final time with 6
     assert abs(dts[0] - g["log_dt"][0]) <= 0.5e-8 + 1e-15
+    assert abs(orc.t - float(g["final_time"])) <= 0.5e-6 + 1e-12
+
+
+@pytest.mark.parametrize("case", slope_cases())
+def test_oracle_matches_reference_bitwise_other_limiters(case, oracle_mod):
+    """slope_type=1 (minmod) and slope_type=0 (hydro slopes switched off, face-field slopes limited to zero) in 3-D: the branches
+    of slope_unsplit_hydro_3d / slope_unsplit_mhd_3d (MHDBaseFunctor3D.h:362-495, 561-668) the main fixtures never take."""
+    g = np.load(f"{ROOT}/tests/golden_slope/{case}.npz")
+    orc = oracle_mod.Oracle(str(g["ini"]))
+    assert np.array_equal(orc.interior(), g["init"]), "initial condition differs from the reference"
+    dt1 = orc.step()
+    assert np.array_equal(orc.interior(), g["step1"]), "state after 1 step differs from the reference"
+    orc.run()
+    assert orc.iteration == int(g["nsteps"])
+    assert np.array_equal(orc.interior(), g["stepN"]), "state after N steps differs from the reference"
+    assert abs(dt1 - g["log_dt"][0]) <= 0.5e-8 + 1e-15
     assert abs(orc.t - float(g["final_time"])) <= 0.5e-6 + 1e-12
 
 
